@@ -1,0 +1,178 @@
+"""ORACLE (test infrastructure, not product code): CPU fp32 restatement of the reference's
+BiCodec detokenize path, written as plain functional torch over a checkpoint state dict.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of
+``bench.py`` may import this module.  The product path (``spark-tts_b200/``) never does.
+
+Parity pinning: the reference holds no golden vectors for this path.  This
+restatement is pinned instead against the reference's own modules imported from /root/reference
+(``oracle/validate_against_reference.py``: outputs agree to the fp32 round-off of re-associated
+sums) and against fixtures generated from those modules (``tests/golden/make_golden.py`` ->
+``tests/golden/*.npz``).  All arithmetic bottoms out in ATen (oneDNN on CPU), as the reference's does.
+
+Each function cites the reference lines it restates (paths relative to /root/reference).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+
+def _wn_weight(sd, prefix: str) -> torch.Tensor:
+    """Fold weight_norm(dim=0): w = v * (g / ||v||), norm over all dims but 0.
+    sparktts/models/bicodec.py:213-221 (remove_weight_norm), sparktts/modules/blocks/layers.py:24-29."""
+    if prefix + ".weight" in sd:
+        return sd[prefix + ".weight"]
+    v, g = sd[prefix + ".weight_v"], sd[prefix + ".weight_g"]
+    return torch._weight_norm(v, g, 0)
+
+
+def snake(x: torch.Tensor, alpha: torch.Tensor) -> torch.Tensor:
+    """sparktts/modules/blocks/layers.py:32-39: x + (alpha+1e-9)^-1 * sin(alpha*x)^2, alpha (1,C,1)."""
+    return x + (alpha + 1e-9).reciprocal() * torch.sin(alpha * x).pow(2)
+
+
+def fsq_codes(indices: torch.Tensor, levels) -> torch.Tensor:
+    """sparktts/modules/fsq/finite_scalar_quantization.py:143-162:
+    level_j = (idx // basis_j) % levels_j ; code_j = (level_j - levels_j//2) / (levels_j//2)."""
+    lv = torch.tensor(levels, dtype=torch.int32)
+    basis = torch.cumprod(torch.tensor([1] + list(levels[:-1])), dim=0).to(torch.int32)
+    level_idx = (indices.unsqueeze(-1) // basis) % lv
+    half = lv // 2
+    return (level_idx - half) / half  # int / int -> float32 true division
+
+
+def vq_detokenize(sd, semantic: torch.Tensor) -> torch.Tensor:
+    """sparktts/modules/vq/factorized_vector_quantize.py:154-167: codebook gather, transpose,
+    out_project (weight-normed 1x1 conv).  semantic (B,T) int -> (B, d_model, T)."""
+    e = F.embedding(semantic.long(), sd["quantizer.codebook.weight"]).transpose(1, 2)
+    return F.conv1d(e, _wn_weight(sd, "quantizer.out_project"), sd["quantizer.out_project.bias"])
+
+
+def speaker_detokenize(sd, global_tokens: torch.Tensor, levels) -> torch.Tensor:
+    """sparktts/modules/speaker/speaker_encoder.py:107-112 + residual_fsq.py:112-199 (num_quantizers=1,
+    scales == 1): global (B,1,N) int -> d_vector (B, d_model)."""
+    idx = global_tokens.long().transpose(1, 2).squeeze(-1)          # (B, N)
+    codes = fsq_codes(idx, levels)                                   # (B, N, 6)
+    z = F.linear(codes.to(sd["speaker_encoder.quantizer.project_out.weight"].dtype),
+                 sd["speaker_encoder.quantizer.project_out.weight"],
+                 sd["speaker_encoder.quantizer.project_out.bias"])   # (B, N, latent)
+    z = z.transpose(1, 2)                                            # (B, latent, N)
+    x = z.reshape(z.shape[0], -1)                                    # flat index = c*N + n
+    return F.linear(x, sd["speaker_encoder.project.weight"], sd["speaker_encoder.project.bias"])
+
+
+def _norm(sd, prefix, x, cond):
+    """nn.LayerNorm(eps 1e-6) or AdaLayerNorm (sparktts/modules/blocks/vocos.py:87-110)."""
+    C = x.shape[-1]
+    if prefix + ".scale.weight" in sd:
+        scale = F.linear(cond, sd[prefix + ".scale.weight"], sd[prefix + ".scale.bias"])
+        shift = F.linear(cond, sd[prefix + ".shift.weight"], sd[prefix + ".shift.bias"])
+        x = F.layer_norm(x, (C,), eps=1e-6)
+        return x * scale.unsqueeze(1) + shift.unsqueeze(1)
+    return F.layer_norm(x, (C,), sd[prefix + ".weight"], sd[prefix + ".bias"], eps=1e-6)
+
+
+def vocos_backbone(sd, prefix, x, cond, taps: Optional[dict] = None):
+    """sparktts/modules/blocks/vocos.py:324-335 (VocosBackbone.forward) and :65-84 (ConvNeXtBlock.forward).
+    x (B,C,T) -> (B,T,C)."""
+    x = F.conv1d(x, sd[prefix + ".embed.weight"], sd[prefix + ".embed.bias"], padding=3)
+    x = _norm(sd, prefix + ".norm", x.transpose(1, 2), cond).transpose(1, 2)
+    if taps is not None:
+        taps[prefix + ".norm"] = x.transpose(1, 2)
+    i = 0
+    while f"{prefix}.convnext.{i}.gamma" in sd:
+        p = f"{prefix}.convnext.{i}"
+        C = x.shape[1]
+        r = x
+        y = F.conv1d(x, sd[p + ".dwconv.weight"], sd[p + ".dwconv.bias"], padding=3, groups=C)
+        y = _norm(sd, p + ".norm", y.transpose(1, 2), cond)
+        y = F.linear(y, sd[p + ".pwconv1.weight"], sd[p + ".pwconv1.bias"])
+        y = F.gelu(y)
+        y = F.linear(y, sd[p + ".pwconv2.weight"], sd[p + ".pwconv2.bias"])
+        y = sd[p + ".gamma"] * y
+        x = r + y.transpose(1, 2)
+        if taps is not None:
+            taps[p] = x.transpose(1, 2)
+        i += 1
+    return F.layer_norm(x.transpose(1, 2), (x.shape[1],), sd[prefix + ".final_layer_norm.weight"],
+                        sd[prefix + ".final_layer_norm.bias"], eps=1e-6)
+
+
+def prenet(sd, z_q, d_vector, n_downsample: int = 2, taps: Optional[dict] = None):
+    """sparktts/modules/encoder_decoder/feat_decoder.py:78-94 with sample_ratios [1,1]; the
+    SamplingBlock with both ratios 1 returns conv_res + skip1_res + skip2_res = 3*x
+    (sparktts/modules/blocks/samper.py:79-100).  z_q (B,D,T), d (B,D) -> (B,D,T)."""
+    x = F.linear(z_q.transpose(1, 2), sd["prenet.linear_pre.weight"], sd["prenet.linear_pre.bias"])
+    for i in range(n_downsample):
+        xt = x.transpose(1, 2)
+        xt = xt + xt + xt                     # SamplingBlock(ratio 1): three aliases of x summed
+        x = vocos_backbone(sd, f"prenet.downsample.{i}.1", xt, None, taps)
+        if taps is not None:
+            taps[f"prenet.downsample.{i}"] = x
+    x = vocos_backbone(sd, "prenet.vocos_backbone", x.transpose(1, 2), d_vector, taps)
+    if taps is not None:
+        taps["prenet.vocos_backbone"] = x
+    x = F.linear(x, sd["prenet.linear.weight"], sd["prenet.linear.bias"]).transpose(1, 2)
+    return x
+
+
+def wave_generator(sd, x, rates, kernel_sizes, taps: Optional[dict] = None):
+    """sparktts/modules/encoder_decoder/wave_generator.py:29-88; ResidualUnit layers.py:51-67.
+    x (B,D,T) -> (B,1,prod(rates)*T)."""
+    x = F.conv1d(x, _wn_weight(sd, "decoder.model.0"), sd["decoder.model.0.bias"], padding=3)
+    if taps is not None:
+        taps["decoder.model.0"] = x.transpose(1, 2)
+    for i, (k, s) in enumerate(zip(kernel_sizes, rates)):
+        p = f"decoder.model.{i + 1}.block"
+        x = snake(x, sd[p + ".0.alpha"])
+        x = F.conv_transpose1d(x, _wn_weight(sd, p + ".1"), sd[p + ".1.bias"], stride=s,
+                               padding=(k - s) // 2)
+        if taps is not None:
+            taps[p + ".1"] = x.transpose(1, 2)
+        for j, dil in enumerate((1, 3, 9)):
+            q = f"{p}.{j + 2}.block"
+            y = snake(x, sd[q + ".0.alpha"])
+            y = F.conv1d(y, _wn_weight(sd, q + ".1"), sd[q + ".1.bias"], dilation=dil, padding=3 * dil)
+            y = snake(y, sd[q + ".2.alpha"])
+            y = F.conv1d(y, _wn_weight(sd, q + ".3"), sd[q + ".3.bias"])
+            x = x + y
+            if taps is not None:
+                taps[f"{p}.{j + 2}"] = x.transpose(1, 2)
+    n = len(rates)
+    x = snake(x, sd[f"decoder.model.{n + 1}.alpha"])
+    x = F.conv1d(x, _wn_weight(sd, f"decoder.model.{n + 2}"), sd[f"decoder.model.{n + 2}.bias"], padding=3)
+    return torch.tanh(x)
+
+
+@torch.no_grad()
+def detokenize(sd: Dict[str, torch.Tensor], cfg, semantic_tokens: torch.Tensor,
+               global_tokens: torch.Tensor, taps: Optional[dict] = None) -> torch.Tensor:
+    """sparktts/models/bicodec.py:171-189 (BiCodec.detokenize).
+    semantic (B,T), global (B,1,N) -> waveform (B,1,hop*T) float32."""
+    z_q = vq_detokenize(sd, semantic_tokens)
+    d = speaker_detokenize(sd, global_tokens, cfg.fsq_levels)
+    if taps is not None:
+        taps["z_q"] = z_q.transpose(1, 2)
+        taps["d_vector"] = d
+    x = prenet(sd, z_q, d, len(cfg.sample_ratios), taps)
+    x = x + d.unsqueeze(-1)
+    if taps is not None:
+        taps["prenet_plus_d"] = x.transpose(1, 2)
+    return wave_generator(sd, x, cfg.rates, cfg.kernel_sizes, taps)
+
+
+@torch.no_grad()
+def tokenizer_detokenize(sd, cfg, global_tokens: torch.Tensor, semantic_tokens: torch.Tensor):
+    """sparktts/models/audio_tokenizer.py:132-146 (BiCodecTokenizer.detokenize): global (B,N),
+    semantic (B,T) -> numpy float32 (B, hop*T), squeezed to (hop*T,) when B == 1."""
+    wav = detokenize(sd, cfg, semantic_tokens, global_tokens.unsqueeze(1))
+    return wav.detach().squeeze().cpu().numpy()
+
+
+def snr_db(ref: torch.Tensor, test: torch.Tensor) -> float:
+    ref = ref.double().flatten()
+    err = test.double().flatten() - ref
+    return float(10.0 * torch.log10(ref.pow(2).sum() / err.pow(2).sum().clamp_min(1e-300)))

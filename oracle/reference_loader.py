@@ -1,0 +1,89 @@
+"""ORACLE tooling (this container only): build the reference's own detokenize modules from
+/root/reference and load a checkpoint state dict into them.
+
+/root/reference does not exist on the GPU box, so nothing under ``tests -m gpu``, ``smoke()`` or
+``bench.py`` imports this file; it is used by ``oracle/validate_against_reference.py`` and
+``tests/golden/make_golden.py`` and by CPU tests that skip when the reference is absent.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import torch
+
+REFERENCE_ROOT = os.environ.get("SPARKTTS_REFERENCE", "/root/reference")
+
+
+def reference_available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "sparktts"))
+
+
+def _import_reference():
+    if not reference_available():
+        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
+    if "omegaconf" not in sys.modules:      # not installed here; only imported for a type name
+        stub = types.ModuleType("omegaconf")
+        stub.DictConfig = dict
+        stub.OmegaConf = object
+        sys.modules["omegaconf"] = stub
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+
+
+class ReferenceDetokenizer(torch.nn.Module):
+    """The four reference sub-modules of BiCodec.detokenize (sparktts/models/bicodec.py:171-189),
+    composed exactly as BiCodecVocoderWrapper does (export_sparktts_onnx.py:267-312), i.e. with
+    ``onnx_export_mode=True`` for the FSQ gather because ``einx`` is not installed here."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        _import_reference()
+        from sparktts.modules.vq.factorized_vector_quantize import FactorizedVectorQuantize
+        from sparktts.modules.speaker.speaker_encoder import SpeakerEncoder
+        from sparktts.modules.encoder_decoder.feat_decoder import Decoder
+        from sparktts.modules.encoder_decoder.wave_generator import WaveGenerator
+
+        self.quantizer = FactorizedVectorQuantize(
+            input_dim=cfg.d_model, codebook_size=cfg.codebook_size, codebook_dim=cfg.codebook_dim,
+            commitment=0.25)
+        self.speaker_encoder = SpeakerEncoder(
+            input_dim=128, out_dim=cfg.d_model, latent_dim=cfg.latent_dim, token_num=cfg.token_num,
+            fsq_levels=list(cfg.fsq_levels), fsq_num_quantizers=1)
+        self.prenet = Decoder(
+            input_channels=cfg.d_model, vocos_dim=cfg.vocos_dim,
+            vocos_intermediate_dim=cfg.vocos_intermediate_dim, vocos_num_layers=cfg.vocos_num_layers,
+            out_channels=cfg.d_model, condition_dim=cfg.d_model, sample_ratios=list(cfg.sample_ratios),
+            use_tanh_at_final=False)
+        self.decoder = WaveGenerator(
+            input_channel=cfg.d_model, channels=cfg.dec_channels, rates=list(cfg.rates),
+            kernel_sizes=list(cfg.kernel_sizes))
+        self.eval()
+
+    def load_checkpoint(self, sd):
+        missing, unexpected = self.load_state_dict(sd, strict=False)
+        # everything in the synthetic checkpoint must be consumed; the only keys the checkpoint may
+        # lack are encode-side ones (ECAPA/perceiver, in_project, cluster_size, project_in)
+        assert not unexpected, unexpected
+        on_path = [k for k in missing if not (
+            k.startswith("speaker_encoder.speaker_encoder.") or k.startswith("speaker_encoder.perceiver_sampler.")
+            or k.startswith("quantizer.in_project") or k == "quantizer.cluster_size"
+            or k.startswith("speaker_encoder.quantizer.project_in"))]
+        assert not on_path, on_path
+
+        def _rm(m):  # bicodec.py:213-221
+            try:
+                torch.nn.utils.remove_weight_norm(m)
+            except ValueError:
+                pass
+        self.apply(_rm)
+        return self
+
+    @torch.no_grad()
+    def detokenize(self, semantic_tokens, global_tokens):
+        z_q = self.quantizer.detokenize(semantic_tokens)
+        d_vector = self.speaker_encoder.detokenize(global_tokens, onnx_export_mode=True)
+        x = self.prenet(z_q, d_vector)
+        x = x + d_vector.unsqueeze(-1)
+        return self.decoder(x)

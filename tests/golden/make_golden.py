@@ -1,0 +1,66 @@
+"""Generate the golden fixtures from the REFERENCE's own modules (run in this container only):
+
+    python tests/golden/make_golden.py
+
+Weights are the synthetic checkpoint (seed 0, regenerated bit-identically anywhere from
+``spark_tts_b200.synthetic``); inputs/outputs of the reference modules
+(/root/reference sparktts/models/bicodec.py:171-189 composed as export_sparktts_onnx.py:267-312)
+are stored as tests/golden/detok_*.npz.  The GPU box has no /root/reference, so GPU parity tests
+compare against these files and against the oracle restatement.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle.reference_loader import ReferenceDetokenizer            # noqa: E402
+from spark_tts_b200.config import BiCodecConfig                     # noqa: E402
+from spark_tts_b200.synthetic import synthetic_state_dict, synthetic_tokens  # noqa: E402
+
+# name, batch, frames, token seed, semantic dtype, global dtype
+CASES = [
+    ("a_b1_t25", 1, 25, 101, torch.int64, torch.int32),
+    ("b_b3_t16", 3, 16, 102, torch.int32, torch.int64),
+    ("c_b1_t1", 1, 1, 103, torch.int64, torch.int32),
+    ("d_b2_t130", 2, 130, 104, torch.int64, torch.int32),
+]
+WEIGHT_SEED = 0
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    cfg = BiCodecConfig()
+    sd = synthetic_state_dict(cfg, seed=WEIGHT_SEED)
+    ref = ReferenceDetokenizer(cfg).load_checkpoint(sd)
+    out_dir = os.path.dirname(os.path.abspath(__file__))
+    for name, B, T, seed, sdt, gdt in CASES:
+        sem, glob = synthetic_tokens(cfg, B, T, seed)
+        sem, glob = sem.to(sdt), glob.to(gdt)
+        with torch.no_grad():
+            z_q = ref.quantizer.detokenize(sem)                                    # (B,1024,T)
+            codebook_rows = ref.quantizer.embed_code(sem.long())                   # (B,T,8) exact gather
+            fsq = ref.speaker_encoder.quantizer.get_codes_from_indices(
+                glob.long().transpose(1, 2), onnx_export_mode=True).squeeze(0)    # (B,32,6) exact
+            d = ref.speaker_encoder.detokenize(glob, onnx_export_mode=True)        # (B,1024)
+            x = ref.prenet(z_q, d) + d.unsqueeze(-1)                               # (B,1024,T)
+            wav = ref.detokenize(sem, glob)                                        # (B,1,320T)
+        np.savez_compressed(
+            os.path.join(out_dir, f"detok_{name}.npz"),
+            weight_seed=np.int64(WEIGHT_SEED),
+            semantic_tokens=sem.numpy(), global_tokens=glob.numpy(),
+            codebook_rows=codebook_rows.numpy(), fsq_codes=fsq.numpy(),
+            z_q_first8=z_q[:, :, :8].numpy(), d_vector=d.numpy(),
+            prenet_plus_d_first8=x[:, :, :8].numpy(), output_waveform=wav.numpy(),
+        )
+        print(name, "wav", tuple(wav.shape), "rms", float(wav.pow(2).mean().sqrt()))
+
+
+if __name__ == "__main__":
+    main()
