@@ -1,0 +1,174 @@
+/*
+ * sparkcodec.h -- C ABI of the B200-native BiCodec detokenize path (libsparkcodec.so).
+ *
+ * Plain C: pointers, sizes and ints only; no torch / CUDA types in any signature (streams are
+ * passed as void* = cudaStream_t).  Every function returns 0 on success or a negative
+ * SPARKCODEC_E* code; sparkcodec_last_error() returns the thread-local message.
+ *
+ * The reference (arghyasur1991/Spark-TTS) is pure Python and has no FFI for this path; each entry
+ * point below names the reference interface it replaces (paths relative to the reference root).
+ * INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ */
+#ifndef SPARKCODEC_H_
+#define SPARKCODEC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPARKCODEC_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define SPARKCODEC_API __attribute__((visibility("default")))
+#else
+#define SPARKCODEC_API
+#endif
+
+enum {
+  SPARKCODEC_OK = 0,
+  SPARKCODEC_EINVAL = -1,    /* bad argument / shape / dtype            -> ValueError   */
+  SPARKCODEC_EINDEX = -2,    /* token id outside its codebook           -> IndexError   */
+  SPARKCODEC_ECUDA = -3,     /* CUDA runtime / driver failure           -> RuntimeError */
+  SPARKCODEC_ESTATE = -4,    /* call order (e.g. detokenize before finalize)            */
+  SPARKCODEC_ENOMEM = -5,    /* workspace too small / allocation failed                 */
+  SPARKCODEC_EMISSING = -6   /* a checkpoint tensor the path needs was never set        */
+};
+
+/* token dtypes accepted for either input (ONNX contract: semantic int64, global int32;
+ * the CLI passes int64 for both, Triton int32 for both -- export_sparktts_onnx.py:819-840,
+ * cli/SparkTTS.py:213-234, runtime/triton_trtllm/model_repo/vocoder/config.pbtxt:28-46) */
+enum { SPARKCODEC_I32 = 0, SPARKCODEC_I64 = 1 };
+
+/* arithmetic of the dense contractions (activations and I/O are fp32 either way):
+ *   FP32 : error-compensated bf16x3 split products on tcgen05, fp32 accumulate
+ *          (parity bound vs the reference fp32: max-abs 1e-3, SNR >= 60 dB)
+ *   BF16 : single bf16 product, fp32 accumulate (looser stated bound)            */
+enum { SPARKCODEC_PREC_FP32 = 0, SPARKCODEC_PREC_BF16 = 1 };
+
+/* which implementation of the dense contraction runs: tcgen05 tensor cores (product path) or the
+ * CUDA-core verification kernel with the same operands/epilogue (tests only). */
+enum { SPARKCODEC_IMPL_TC = 0, SPARKCODEC_IMPL_SIMT = 1 };
+
+/* Mirrors the `audio_tokenizer` section of BiCodec/config.yaml consumed by
+ * BiCodec.load_from_checkpoint (sparktts/models/bicodec.py:81-88). */
+typedef struct sparkcodec_config {
+  int32_t d_model;               /* quantizer.input_dim = prenet in/out = decoder.input_channel */
+  int32_t codebook_size;         /* quantizer.codebook_size */
+  int32_t codebook_dim;          /* quantizer.codebook_dim  */
+  int32_t fsq_num_levels;        /* len(speaker_encoder.fsq_levels), <= 8 */
+  int32_t fsq_levels[8];
+  int32_t token_num;             /* speaker_encoder.token_num  */
+  int32_t latent_dim;            /* speaker_encoder.latent_dim */
+  int32_t vocos_dim;             /* prenet.vocos_dim */
+  int32_t vocos_intermediate_dim;
+  int32_t vocos_num_layers;      /* prenet.vocos_num_layers (AdaLN-conditioned backbone) */
+  int32_t downsample_layers;     /* ConvNeXt layers of each downsample backbone (2) */
+  int32_t num_downsample;        /* len(prenet.sample_ratios), all ratios must be 1 */
+  int32_t dec_channels;          /* decoder.channels */
+  int32_t num_upsample;          /* len(decoder.rates), <= 8 */
+  int32_t rates[8];
+  int32_t kernel_sizes[8];
+} sparkcodec_config;
+
+typedef struct sparkcodec_handle sparkcodec_handle;
+
+SPARKCODEC_API const char* sparkcodec_last_error(void);
+SPARKCODEC_API int sparkcodec_abi_version(void);
+
+/* Replaces the module construction half of BiCodec.load_from_checkpoint
+ * (sparktts/models/bicodec.py:69-98).  `device` is the CUDA ordinal. */
+SPARKCODEC_API int sparkcodec_create(const sparkcodec_config* cfg, int device, sparkcodec_handle** out);
+SPARKCODEC_API int sparkcodec_destroy(sparkcodec_handle* h);
+
+/* Replaces load_state_dict (bicodec.py:100-101): hand over one checkpoint tensor by its
+ * model.safetensors key (e.g. "decoder.model.1.block.1.weight_v").  `data` is fp32 HOST memory,
+ * copied during the call.  Keys that the detokenize path does not use are ignored (return 0). */
+SPARKCODEC_API int sparkcodec_set_tensor(sparkcodec_handle* h, const char* key, const float* data,
+                          const int64_t* shape, int ndim);
+
+/* Replaces model.eval() + remove_weight_norm() (bicodec.py:108-109, 213-221): folds weight-norm
+ * (dim 0), re-lays every dense weight out for the tcgen05 kernels (K-major bf16 hi/lo planes,
+ * polyphase split of the transposed convolutions), uploads, and frees the host copies.
+ * Returns SPARKCODEC_EMISSING (message names the key) if a needed tensor was never set. */
+SPARKCODEC_API int sparkcodec_finalize(sparkcodec_handle* h);
+
+/* Device workspace needed by one detokenize call of (batch, frames). The library never allocates
+ * per call; the caller (torch caching allocator) owns the workspace. */
+SPARKCODEC_API int sparkcodec_workspace_bytes(sparkcodec_handle* h, int batch, int frames, size_t* bytes);
+
+/* Replaces BiCodec.detokenize (sparktts/models/bicodec.py:171-189) == the ONNX `bicodec_vocoder`
+ * graph (export_sparktts_onnx.py:267-312):
+ *   semantic  : device ptr, (batch, frames) row-major, dtype sem_dtype, ids in [0, codebook_size)
+ *   global    : device ptr, (batch, token_num) row-major [(B,1,N) and (B,N) are the same bytes]
+ *   wav_out   : device ptr, (batch, hop*frames) fp32 [== (B,1,hop*T) contiguous]
+ * Asynchronous on `stream`; inputs are borrowed until the stream reaches the end of the call.
+ * Token ids are validated on the device: the first error is latched in the handle and reported by
+ * sparkcodec_check_tokens() (the reference raises IndexError on CPU / device-asserts on CUDA). */
+SPARKCODEC_API int sparkcodec_detokenize(sparkcodec_handle* h, const void* semantic, int sem_dtype,
+                          const void* global_tokens, int glob_dtype, int batch, int frames,
+                          int precision, void* workspace, size_t workspace_bytes, float* wav_out,
+                          void* stream);
+
+/* The two halves of detokenize, split at the prenet -> WaveGenerator boundary (bicodec.py:185-187).
+ * They exist for time-sharding (BASELINE config 5): a rank runs sparkcodec_prenet on its own frame
+ * window (tokens are replicated, so the window simply carries `prenet_halo` extra frames each side and
+ * the caller crops), exchanges `wavegen_halo` boundary rows of x with its neighbours over NCCL, and
+ * runs sparkcodec_wavegen on the widened window.  Zero padding is applied at the edges of whatever
+ * window is passed, which is the true utterance edge only for the first/last shard; rows within the
+ * halo of a shard edge are discarded by the caller.
+ *   x_out / x_in : device, (batch, frames, d_model) fp32 channels-last = prenet(z_q, d) + d          */
+SPARKCODEC_API int sparkcodec_prenet(sparkcodec_handle* h, const void* semantic, int sem_dtype,
+                      const void* global_tokens, int glob_dtype, int batch, int frames, int precision,
+                      void* workspace, size_t workspace_bytes, float* x_out, void* stream);
+SPARKCODEC_API int sparkcodec_wavegen(sparkcodec_handle* h, const float* x_in, int batch, int frames, int precision,
+                       void* workspace, size_t workspace_bytes, float* wav_out, void* stream);
+/* Receptive-field half-widths in token frames: prenet (57 for the released config) and
+ * WaveGenerator (conservative ceil; SURVEY.md §8e measured 9.82 frames). */
+SPARKCODEC_API int sparkcodec_halo_frames(sparkcodec_handle* h, int* prenet_halo, int* wavegen_halo);
+
+/* Synchronises `stream` and returns SPARKCODEC_EINDEX if any token id seen since the last check
+ * was out of range (message holds which input, position and value). */
+SPARKCODEC_API int sparkcodec_check_tokens(sparkcodec_handle* h, void* stream);
+
+/* ---- test / profiling hooks (not needed by a drop-in user) --------------------------------- */
+
+/* Selects tcgen05 (default) or the CUDA-core verification kernels for the dense contractions. */
+SPARKCODEC_API int sparkcodec_set_impl(sparkcodec_handle* h, int impl);
+
+/* Runs detokenize but also copies the activation named `tap` (oracle tap names, e.g. "d_vector",
+ * "prenet.downsample.0", "decoder.model.1.block.2") as fp32 (batch, rows, channels) into tap_out
+ * (device, capacity tap_capacity floats); writes its rows/channels to tap_shape[0..1]. */
+SPARKCODEC_API int sparkcodec_detokenize_tap(sparkcodec_handle* h, const void* semantic, int sem_dtype,
+                              const void* global_tokens, int glob_dtype, int batch, int frames,
+                              int precision, void* workspace, size_t workspace_bytes, float* wav_out,
+                              const char* tap, float* tap_out, size_t tap_capacity,
+                              int64_t* tap_shape, void* stream);
+
+/* Stand-alone dense convolution through the same packing + kernels the model uses.
+ *   kind 0: Conv1d weight (C_out, C_in, k), dilation `param`, padding (k-1)/2*dilation
+ *   kind 1: ConvTranspose1d weight (C_in, C_out, k), stride `param`, padding (k-stride)/2
+ * x_dev (batch, L, C_in) fp32 channels-last; y_dev (batch, L_out, C_out) fp32.
+ * act: 0 none, 1 GELU(erf), 2 snake(alpha_host[C_out]); residual_dev optional (same shape as y). */
+SPARKCODEC_API int sparkcodec_op_conv(int device, int kind, const float* w_host, const int64_t* wshape,
+                       const float* bias_host, int param, int batch, int L, const float* x_dev,
+                       float* y_dev, const float* residual_dev, int act, const float* alpha_host,
+                       int precision, int impl, void* stream);
+
+/* Host-side weight re-layout, exposed so it can be checked without a GPU.
+ * Fills w_hi/w_lo (uint16 bf16 bit patterns, (n_total, kt*c_in) row-major), shifts (n_phase*kt,
+ * unused = INT32_MIN) and returns kt / n_phase / n_total through the out params. */
+SPARKCODEC_API int sparkcodec_pack_conv(int kind, const float* w_host, const int64_t* wshape, int param,
+                         uint16_t* w_hi, uint16_t* w_lo, size_t w_capacity, int32_t* shifts,
+                         int32_t* ntaps, int32_t* kt, int32_t* n_phase, int32_t* n_total);
+
+/* Number of this library's kernel launches issued since the handle was created (bench.py's
+ * `gpu_launches`). */
+SPARKCODEC_API int sparkcodec_launch_count(sparkcodec_handle* h, int64_t* count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPARKCODEC_H_ */

@@ -6,3 +6,6 @@ Public surface mirrors the reference (paths relative to /root/reference):
   * ONNX ``bicodec_vocoder`` I/O contract                            export_sparktts_onnx.py:767-867
 """
 from .config import BiCodecConfig, load_bicodec_yaml  # noqa: F401
+from .bicodec import BiCodec  # noqa: F401,E402
+from .audio_tokenizer import BiCodecTokenizer  # noqa: F401,E402
+from .onnx_contract import VocoderSession  # noqa: F401,E402

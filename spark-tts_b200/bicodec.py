@@ -1,0 +1,265 @@
+"""``BiCodec`` -- host-side mirror of the reference class for the detokenize path.
+
+Same surface as /root/reference sparktts/models/bicodec.py (``load_from_checkpoint`` :69-111,
+``detokenize`` :171-189, ``remove_weight_norm`` :213-221, plus the harmless ``.to()``/``.eval()``
+the callers use), but every stage runs in libsparkcodec.so (hand-written sm_100a kernels).
+PyTorch only provides device memory, the current stream and the output tensor.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+from .config import BiCodecConfig, load_bicodec_yaml
+
+_TOKEN_DTYPES = {torch.int32: _lib.I32, torch.int64: _lib.I64}
+
+
+class BiCodec:
+    """B200-native BiCodec vocoder (semantic + global tokens -> waveform)."""
+
+    def __init__(self, cfg: BiCodecConfig, state_dict: Dict[str, torch.Tensor],
+                 device: Optional[torch.device] = None, precision: str = "fp32",
+                 workspace_limit_bytes: int = 24 << 30):
+        if precision not in _lib.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}")
+        self.cfg = cfg
+        self.precision = precision
+        self.validate_tokens = True          # sync + IndexError on out-of-range ids, like the CPU reference
+        self.workspace_limit_bytes = int(workspace_limit_bytes)
+        self._sd = state_dict                # kept on the host so .to(other_device) can rebuild
+        self._handle: Optional[C.c_void_p] = None
+        self._device: Optional[torch.device] = None
+        self._ws: Optional[torch.Tensor] = None
+        self._impl = "tc"
+        if device is not None:
+            self.to(device)
+
+    # ------------------------------------------------------------------ construction (bicodec.py:69-111)
+    @classmethod
+    def load_from_checkpoint(cls, model_dir, device=None, **kwargs) -> "BiCodec":
+        """``model_dir`` holds ``config.yaml`` + ``model.safetensors`` exactly as the reference expects."""
+        from safetensors.torch import load_file
+
+        cfg = load_bicodec_yaml(os.path.join(str(model_dir), "config.yaml"))
+        sd = load_file(os.path.join(str(model_dir), "model.safetensors"))
+        return cls(cfg, sd, device=device, **kwargs)
+
+    @classmethod
+    def from_state_dict(cls, cfg: BiCodecConfig, state_dict, device=None, **kwargs) -> "BiCodec":
+        return cls(cfg, state_dict, device=device, **kwargs)
+
+    def _build(self, device: torch.device) -> None:
+        if not torch.cuda.is_available():
+            raise _lib.SparkCodecError(
+                "BiCodec detokenize runs only on a CUDA device (sm_100a); there is no CPU fallback")
+        lib = _lib.load()
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        device = torch.device("cuda", idx)
+        h = C.c_void_p()
+        ccfg = _lib.make_config(self.cfg)
+        _lib.check(lib.sparkcodec_create(C.byref(ccfg), idx, C.byref(h)))
+        try:
+            for key, t in self._sd.items():
+                t = t.detach().to("cpu", torch.float32).contiguous()
+                shape = (C.c_int64 * max(t.dim(), 1))(*t.shape)
+                _lib.check(lib.sparkcodec_set_tensor(h, key.encode(), C.c_void_p(t.data_ptr()), shape, t.dim()))
+            _lib.check(lib.sparkcodec_finalize(h))
+        except Exception:
+            lib.sparkcodec_destroy(h)
+            raise
+        self._free()
+        self._handle, self._device, self._ws = h, device, None
+        self.set_impl(self._impl)
+
+    def _free(self) -> None:
+        if self._handle is not None:
+            _lib.load().sparkcodec_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self._free()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ nn.Module-like no-ops
+    def to(self, device) -> "BiCodec":
+        device = torch.device(device) if device is not None else None
+        if device is None:
+            return self
+        if device.type != "cuda":
+            raise _lib.SparkCodecError(f"BiCodec runs only on CUDA devices, got {device}")
+        if self._device is None or (device.index is not None and device.index != self._device.index):
+            self._build(device)
+        return self
+
+    def eval(self) -> "BiCodec":
+        return self
+
+    def remove_weight_norm(self) -> None:
+        """weight-norm is folded once inside sparkcodec_finalize (bicodec.py:213-221)."""
+
+    @property
+    def device(self) -> Optional[torch.device]:
+        return self._device
+
+    @property
+    def hop(self) -> int:
+        return self.cfg.hop
+
+    # ------------------------------------------------------------------ helpers
+    def _ensure(self, *tensors: torch.Tensor) -> None:
+        dev = None
+        for t in tensors:
+            if not isinstance(t, torch.Tensor):
+                raise TypeError("tokens must be torch tensors")
+            if t.device.type != "cuda":
+                raise RuntimeError(
+                    f"expected tokens on a CUDA device, got {t.device} (the detokenize path has no CPU fallback)")
+            dev = dev or t.device
+            if t.device != dev:
+                raise RuntimeError("semantic_tokens and global_tokens are on different devices")
+        if self._device is None:
+            self._build(dev)
+        elif dev != self._device:
+            raise RuntimeError(f"model is on {self._device} but tokens are on {dev}")
+
+    def _workspace(self, batch: int, frames: int) -> Tuple[int, int]:
+        need = C.c_size_t()
+        _lib.check(_lib.load().sparkcodec_workspace_bytes(self._handle, batch, frames, C.byref(need)))
+        want = min(need.value, max(self.workspace_limit_bytes, 1))
+        if want < need.value:   # the library splits the batch; make sure one utterance fits
+            one = C.c_size_t()
+            _lib.check(_lib.load().sparkcodec_workspace_bytes(self._handle, 1, frames, C.byref(one)))
+            want = max(want, one.value)
+        if self._ws is None or self._ws.numel() < want:
+            self._ws = None
+            self._ws = torch.empty(want, dtype=torch.uint8, device=self._device)
+        return self._ws.data_ptr(), self._ws.numel()
+
+    def _tokens(self, semantic_tokens, global_tokens):
+        if semantic_tokens.dim() != 2:
+            raise ValueError(f"semantic_tokens must be (B, T), got {tuple(semantic_tokens.shape)}")
+        B, T = semantic_tokens.shape
+        N = self.cfg.token_num
+        if global_tokens.dim() == 3 and tuple(global_tokens.shape) == (B, 1, N):
+            pass
+        elif global_tokens.dim() == 2 and tuple(global_tokens.shape) == (B, N):
+            pass
+        else:
+            raise ValueError(f"global_tokens must be ({B}, 1, {N}) or ({B}, {N}), got {tuple(global_tokens.shape)}")
+        for name, t in (("semantic_tokens", semantic_tokens), ("global_tokens", global_tokens)):
+            if t.dtype not in _TOKEN_DTYPES:
+                raise ValueError(f"{name} must be int32 or int64, got {t.dtype}")
+        return semantic_tokens.contiguous(), global_tokens.contiguous(), B, T
+
+    def _stream(self) -> C.c_void_p:
+        return C.c_void_p(torch.cuda.current_stream(self._device).cuda_stream)
+
+    def _prec(self, precision: Optional[str]) -> int:
+        return _lib.PRECISIONS[precision or self.precision]
+
+    def check_tokens(self) -> None:
+        """Raises IndexError if any token id since the last check was out of range (synchronises)."""
+        _lib.check(_lib.load().sparkcodec_check_tokens(self._handle, self._stream()))
+
+    # ------------------------------------------------------------------ the hot path (bicodec.py:171-189)
+    @torch.no_grad()
+    def detokenize(self, semantic_tokens: torch.Tensor, global_tokens: torch.Tensor,
+                   precision: Optional[str] = None) -> torch.Tensor:
+        """semantic (B,T) int, global (B,1,32) int -> waveform (B,1,hop*T) float32 on the input device."""
+        self._ensure(semantic_tokens, global_tokens)
+        sem, glob, B, T = self._tokens(semantic_tokens, global_tokens)
+        wav = torch.empty((B, 1, self.hop * T), dtype=torch.float32, device=self._device)
+        if B == 0 or T == 0:
+            return wav
+        ws, ws_bytes = self._workspace(B, T)
+        _lib.check(_lib.load().sparkcodec_detokenize(
+            self._handle, C.c_void_p(sem.data_ptr()), _TOKEN_DTYPES[sem.dtype], C.c_void_p(glob.data_ptr()),
+            _TOKEN_DTYPES[glob.dtype], B, T, self._prec(precision), C.c_void_p(ws), ws_bytes,
+            C.c_void_p(wav.data_ptr()), self._stream()))
+        if self.validate_tokens:
+            self.check_tokens()
+        return wav
+
+    __call__ = detokenize
+
+    # ------------------------------------------------------------------ halves, for time-sharding
+    @torch.no_grad()
+    def prenet(self, semantic_tokens, global_tokens, precision: Optional[str] = None) -> torch.Tensor:
+        """-> x = prenet(z_q, d) + d as (B, T, d_model) fp32 channels-last."""
+        self._ensure(semantic_tokens, global_tokens)
+        sem, glob, B, T = self._tokens(semantic_tokens, global_tokens)
+        x = torch.empty((B, T, self.cfg.d_model), dtype=torch.float32, device=self._device)
+        if B == 0 or T == 0:
+            return x
+        ws, ws_bytes = self._workspace(B, T)
+        _lib.check(_lib.load().sparkcodec_prenet(
+            self._handle, C.c_void_p(sem.data_ptr()), _TOKEN_DTYPES[sem.dtype], C.c_void_p(glob.data_ptr()),
+            _TOKEN_DTYPES[glob.dtype], B, T, self._prec(precision), C.c_void_p(ws), ws_bytes,
+            C.c_void_p(x.data_ptr()), self._stream()))
+        if self.validate_tokens:
+            self.check_tokens()
+        return x
+
+    @torch.no_grad()
+    def wavegen(self, x: torch.Tensor, precision: Optional[str] = None) -> torch.Tensor:
+        """x (B, T, d_model) fp32 channels-last -> waveform (B, 1, hop*T)."""
+        self._ensure(x)
+        if x.dim() != 3 or x.shape[2] != self.cfg.d_model or x.dtype != torch.float32:
+            raise ValueError(f"x must be float32 (B, T, {self.cfg.d_model})")
+        x = x.contiguous()
+        B, T, _ = x.shape
+        wav = torch.empty((B, 1, self.hop * T), dtype=torch.float32, device=self._device)
+        if B == 0 or T == 0:
+            return wav
+        ws, ws_bytes = self._workspace(B, T)
+        _lib.check(_lib.load().sparkcodec_wavegen(
+            self._handle, C.c_void_p(x.data_ptr()), B, T, self._prec(precision), C.c_void_p(ws), ws_bytes,
+            C.c_void_p(wav.data_ptr()), self._stream()))
+        return wav
+
+    def halo_frames(self) -> Tuple[int, int]:
+        if self._handle is None:
+            raise _lib.SparkCodecError("model is not on a device yet")
+        a, b = C.c_int(), C.c_int()
+        _lib.check(_lib.load().sparkcodec_halo_frames(self._handle, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    # ------------------------------------------------------------------ test / profiling hooks
+    def set_impl(self, impl: str) -> None:
+        """'tc' (tcgen05, the product path) or 'simt' (CUDA-core verification kernels, tests only)."""
+        if impl not in ("tc", "simt"):
+            raise ValueError("impl must be 'tc' or 'simt'")
+        self._impl = impl
+        if self._handle is not None:
+            _lib.check(_lib.load().sparkcodec_set_impl(
+                self._handle, _lib.IMPL_TC if impl == "tc" else _lib.IMPL_SIMT))
+
+    @torch.no_grad()
+    def detokenize_tap(self, semantic_tokens, global_tokens, tap: str, precision: Optional[str] = None):
+        """Runs detokenize and also returns the named intermediate activation as (B, rows, channels) fp32."""
+        self._ensure(semantic_tokens, global_tokens)
+        sem, glob, B, T = self._tokens(semantic_tokens, global_tokens)
+        wav = torch.empty((B, 1, self.hop * T), dtype=torch.float32, device=self._device)
+        ws, ws_bytes = self._workspace(B, T)
+        cap = B * T * self.hop * 96 + 4096          # largest activation: (B, 320T, 96) / (B, 160T, 192)
+        cap = max(cap, B * T * max(self.cfg.dec_channels, self.cfg.vocos_intermediate_dim))
+        out = torch.empty(cap, dtype=torch.float32, device=self._device)
+        shape = (C.c_int64 * 2)()
+        _lib.check(_lib.load().sparkcodec_detokenize_tap(
+            self._handle, C.c_void_p(sem.data_ptr()), _TOKEN_DTYPES[sem.dtype], C.c_void_p(glob.data_ptr()),
+            _TOKEN_DTYPES[glob.dtype], B, T, self._prec(precision), C.c_void_p(ws), ws_bytes,
+            C.c_void_p(wav.data_ptr()), tap.encode(), C.c_void_p(out.data_ptr()), cap, shape, self._stream()))
+        rows, ch = int(shape[0]), int(shape[1])
+        return wav, out[: B * rows * ch].view(B, rows, ch).clone()
+
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        _lib.check(_lib.load().sparkcodec_launch_count(self._handle, C.byref(n)))
+        return n.value

@@ -1,0 +1,913 @@
+// C ABI of libsparkcodec: handle, checkpoint ingestion, workspace planning and the detokenize schedule.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "gemm_params.cuh"
+#include "pack.h"
+
+namespace sparkcodec {
+
+static thread_local char g_err[1024] = "";
+thread_local int64_t* g_launch_counter = nullptr;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+struct HostTensor {
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+  int64_t numel() const { int64_t n = 1; for (auto d : shape) n *= d; return n; }
+};
+
+struct SnakeParams { float* alpha = nullptr; float* inv = nullptr; };
+
+struct ConvNeXt {
+  float* dw_w = nullptr;   // [7][C]
+  float* dw_b = nullptr;
+  float* ln_w = nullptr;   // plain LayerNorm affine (null when AdaLN)
+  float* ln_b = nullptr;
+  GemmWeights pw1, pw2;    // pw2 has gamma folded in
+};
+struct Backbone {
+  bool ada = false;
+  GemmWeights embed;
+  float* norm_w = nullptr; float* norm_b = nullptr;
+  std::vector<ConvNeXt> blocks;
+  float* final_w = nullptr; float* final_b = nullptr;   // x3 of the following SamplingBlock folded in
+};
+struct ResUnit {
+  GemmWeights c7, c1;
+  SnakeParams s_mid;    // snake between conv7 and conv1 (applied in conv7's epilogue)
+  SnakeParams s_next;   // snake that consumes this unit's output (applied in conv1's epilogue)
+};
+struct UpBlock {
+  int stride = 1, c_in = 0, c_out = 0;
+  GemmWeights convt;
+  SnakeParams s_after;  // first residual unit's input snake, phase-replicated (convT epilogue)
+  ResUnit ru[3];
+};
+
+}  // namespace sparkcodec
+
+using namespace sparkcodec;
+
+struct sparkcodec_handle {
+  sparkcodec_config cfg;
+  int device = 0, num_sms = 148;
+  bool finalized = false;
+  int impl = SPARKCODEC_IMPL_TC;
+  int64_t launches = 0;
+  std::map<std::string, HostTensor> host;
+  std::vector<void*> allocs;
+  int* err_flag = nullptr;   // device int[4]
+
+  // token stages
+  float *codebook = nullptr, *vq_mat = nullptr, *vq_vec = nullptr, *vq_w = nullptr, *vq_b = nullptr;
+  int* fsq_levels = nullptr;
+  float *fsq_wpo = nullptr, *fsq_bpo = nullptr, *spk_w = nullptr, *spk_b = nullptr;
+  float *ada_w = nullptr, *ada_b = nullptr;
+  int n_ada = 0;
+  // prenet
+  std::vector<Backbone> backbones;
+  GemmWeights linear;
+  // wave generator
+  GemmWeights conv_in;
+  SnakeParams s_conv_in;   // first block's input snake (conv_in epilogue)
+  std::vector<UpBlock> ups;
+  SnakeParams s_head;
+  float* head_w = nullptr;   // [7][C]
+  float head_bias = 0.f;
+  int head_c = 0;
+  int hop = 1;
+};
+
+namespace sparkcodec {
+
+// ------------------------------------------------------------------------------- device helpers
+static int dev_alloc(sparkcodec_handle* h, size_t bytes, void** out) {
+  void* p = nullptr;
+  SC_CUDA(cudaMalloc(&p, bytes ? bytes : 4));
+  h->allocs.push_back(p);
+  *out = p;
+  return 0;
+}
+template <typename T>
+static int upload(sparkcodec_handle* h, const std::vector<T>& v, T** out) {
+  void* p;
+  SC_TRY(dev_alloc(h, v.size() * sizeof(T), &p));
+  SC_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *out = static_cast<T*>(p);
+  return 0;
+}
+static int upload_gemm(sparkcodec_handle* h, const PackedGemm& pk, GemmWeights* g) {
+  g->c_in = pk.c_in; g->n_total = pk.n_total; g->kt = pk.kt; g->taps = pk.taps;
+  uint16_t *hi, *lo;
+  SC_TRY(upload(h, pk.w_hi, &hi));
+  SC_TRY(upload(h, pk.w_lo, &lo));
+  g->w_hi = reinterpret_cast<__nv_bfloat16*>(hi);
+  g->w_lo = reinterpret_cast<__nv_bfloat16*>(lo);
+  SC_TRY(upload(h, pk.bias, &g->bias));
+  return make_weight_tmaps(*g);
+}
+
+static int get(sparkcodec_handle* h, const std::string& key, const HostTensor** out,
+               std::initializer_list<int64_t> shape = {}) {
+  auto it = h->host.find(key);
+  if (it == h->host.end()) {
+    set_error("missing checkpoint tensor '%s'", key.c_str());
+    return SPARKCODEC_EMISSING;
+  }
+  if (shape.size()) {
+    std::vector<int64_t> want(shape);
+    if (it->second.shape != want) {
+      std::string got;
+      for (auto d : it->second.shape) got += std::to_string(d) + ",";
+      std::string exp;
+      for (auto d : want) exp += std::to_string(d) + ",";
+      set_error("tensor '%s' has shape (%s) but the config implies (%s)", key.c_str(), got.c_str(), exp.c_str());
+      return SPARKCODEC_EINVAL;
+    }
+  }
+  *out = &it->second;
+  return 0;
+}
+
+// weight of a (possibly weight-normed) conv: `prefix.weight` or fold(prefix.weight_g, prefix.weight_v)
+static int conv_weight(sparkcodec_handle* h, const std::string& prefix, std::initializer_list<int64_t> shape,
+                       std::vector<float>* w) {
+  const HostTensor* t;
+  if (h->host.count(prefix + ".weight")) {
+    SC_TRY(get(h, prefix + ".weight", &t, shape));
+    *w = t->data;
+    return 0;
+  }
+  const HostTensor *v, *g;
+  SC_TRY(get(h, prefix + ".weight_v", &v, shape));
+  SC_TRY(get(h, prefix + ".weight_g", &g));
+  const int64_t d0 = v->shape[0];
+  if (g->numel() != d0) {
+    set_error("tensor '%s.weight_g' must have %lld elements", prefix.c_str(), (long long)d0);
+    return SPARKCODEC_EINVAL;
+  }
+  fold_weight_norm(v->data.data(), g->data.data(), d0, v->numel() / d0, *w);
+  return 0;
+}
+
+static int upload_snake(sparkcodec_handle* h, const std::string& key, int c, int replicate, SnakeParams* sp) {
+  const HostTensor* t;
+  SC_TRY(get(h, key, &t, {1, c, 1}));
+  std::vector<float> a((size_t)c * replicate), inv((size_t)c * replicate);
+  for (int r = 0; r < replicate; ++r)
+    for (int i = 0; i < c; ++i) {
+      a[(size_t)r * c + i] = t->data[i];
+      inv[(size_t)r * c + i] = 1.0f / (t->data[i] + 1e-9f);   // (alpha + 1e-9).reciprocal(), layers.py:37
+    }
+  SC_TRY(upload(h, a, &sp->alpha));
+  SC_TRY(upload(h, inv, &sp->inv));
+  return 0;
+}
+
+static int build_conv1d(sparkcodec_handle* h, const std::string& prefix, int c_out, int c_in, int k, int dil,
+                        bool linear_shape, const float* row_scale, GemmWeights* g) {
+  std::vector<float> w;
+  if (linear_shape) SC_TRY(conv_weight(h, prefix, {c_out, c_in}, &w));
+  else SC_TRY(conv_weight(h, prefix, {c_out, c_in, k}, &w));
+  const HostTensor* b;
+  SC_TRY(get(h, prefix + ".bias", &b, {c_out}));
+  PackedGemm pk;
+  pack_conv1d(w.data(), c_out, c_in, k, dil, b->data.data(), row_scale, pk);
+  return upload_gemm(h, pk, g);
+}
+
+static int build_backbone(sparkcodec_handle* h, const std::string& prefix, int layers, bool ada, float post_scale,
+                          Backbone* bb) {
+  const int C = h->cfg.vocos_dim, H = h->cfg.vocos_intermediate_dim;
+  bb->ada = ada;
+  SC_TRY(build_conv1d(h, prefix + ".embed", C, C, 7, 1, false, nullptr, &bb->embed));
+  const HostTensor *t, *u;
+  if (!ada) {
+    SC_TRY(get(h, prefix + ".norm.weight", &t, {C}));
+    SC_TRY(get(h, prefix + ".norm.bias", &u, {C}));
+    SC_TRY(upload(h, t->data, &bb->norm_w));
+    SC_TRY(upload(h, u->data, &bb->norm_b));
+  }
+  bb->blocks.resize(layers);
+  for (int i = 0; i < layers; ++i) {
+    const std::string p = prefix + ".convnext." + std::to_string(i);
+    ConvNeXt& blk = bb->blocks[i];
+    SC_TRY(get(h, p + ".dwconv.weight", &t, {C, 1, 7}));
+    std::vector<float> dw((size_t)7 * C);
+    for (int c = 0; c < C; ++c)
+      for (int j = 0; j < 7; ++j) dw[(size_t)j * C + c] = t->data[(size_t)c * 7 + j];
+    SC_TRY(upload(h, dw, &blk.dw_w));
+    SC_TRY(get(h, p + ".dwconv.bias", &t, {C}));
+    SC_TRY(upload(h, t->data, &blk.dw_b));
+    if (!ada) {
+      SC_TRY(get(h, p + ".norm.weight", &t, {C}));
+      SC_TRY(get(h, p + ".norm.bias", &u, {C}));
+      SC_TRY(upload(h, t->data, &blk.ln_w));
+      SC_TRY(upload(h, u->data, &blk.ln_b));
+    }
+    SC_TRY(build_conv1d(h, p + ".pwconv1", H, C, 1, 1, true, nullptr, &blk.pw1));
+    const HostTensor* gamma;
+    SC_TRY(get(h, p + ".gamma", &gamma, {C}));
+    SC_TRY(build_conv1d(h, p + ".pwconv2", C, H, 1, 1, true, gamma->data.data(), &blk.pw2));
+  }
+  SC_TRY(get(h, prefix + ".final_layer_norm.weight", &t, {C}));
+  SC_TRY(get(h, prefix + ".final_layer_norm.bias", &u, {C}));
+  std::vector<float> fw(t->data), fb(u->data);
+  for (auto& v : fw) v *= post_scale;
+  for (auto& v : fb) v *= post_scale;
+  SC_TRY(upload(h, fw, &bb->final_w));
+  SC_TRY(upload(h, fb, &bb->final_b));
+  return 0;
+}
+
+static int do_finalize(sparkcodec_handle* h) {
+  const sparkcodec_config& c = h->cfg;
+  const int D = c.d_model, C = c.vocos_dim;
+  const HostTensor *t, *u;
+
+  void* ef;
+  SC_TRY(dev_alloc(h, 4 * sizeof(int), &ef));
+  h->err_flag = static_cast<int*>(ef);
+  SC_CUDA(cudaMemset(h->err_flag, 0, 4 * sizeof(int)));
+
+  // ---- quantizer: codebook, out_project, and the folded (x3 . linear_pre . out_project) map ----
+  SC_TRY(get(h, "quantizer.codebook.weight", &t, {c.codebook_size, c.codebook_dim}));
+  SC_TRY(upload(h, t->data, &h->codebook));
+  std::vector<float> wout;
+  SC_TRY(conv_weight(h, "quantizer.out_project", {D, c.codebook_dim, 1}, &wout));
+  const HostTensor* bout;
+  SC_TRY(get(h, "quantizer.out_project.bias", &bout, {D}));
+  SC_TRY(upload(h, wout, &h->vq_w));
+  SC_TRY(upload(h, bout->data, &h->vq_b));
+  SC_TRY(get(h, "prenet.linear_pre.weight", &t, {C, D}));
+  SC_TRY(get(h, "prenet.linear_pre.bias", &u, {C}));
+  {
+    // SamplingBlock with both ratios 1 returns 3*x (samper.py:79-100): one per downsample stage
+    const double s3 = c.num_downsample > 0 ? 3.0 : 1.0;
+    std::vector<float> mat((size_t)C * c.codebook_dim), vec(C);
+    for (int o = 0; o < C; ++o) {
+      for (int j = 0; j < c.codebook_dim; ++j) {
+        double a = 0.0;
+        for (int d = 0; d < D; ++d) a += (double)t->data[(size_t)o * D + d] * (double)wout[(size_t)d * c.codebook_dim + j];
+        mat[(size_t)o * c.codebook_dim + j] = (float)(s3 * a);
+      }
+      double a = u->data[o];
+      for (int d = 0; d < D; ++d) a += (double)t->data[(size_t)o * D + d] * (double)bout->data[d];
+      vec[o] = (float)(s3 * a);
+    }
+    SC_TRY(upload(h, mat, &h->vq_mat));
+    SC_TRY(upload(h, vec, &h->vq_vec));
+  }
+
+  // ---- speaker: FSQ project_out, project, stacked AdaLN scale/shift Linears ----
+  {
+    std::vector<int> lv(c.fsq_levels, c.fsq_levels + c.fsq_num_levels);
+    SC_TRY(upload(h, lv, &h->fsq_levels));
+  }
+  SC_TRY(get(h, "speaker_encoder.quantizer.project_out.weight", &t, {c.latent_dim, c.fsq_num_levels}));
+  SC_TRY(upload(h, t->data, &h->fsq_wpo));
+  SC_TRY(get(h, "speaker_encoder.quantizer.project_out.bias", &t, {c.latent_dim}));
+  SC_TRY(upload(h, t->data, &h->fsq_bpo));
+  SC_TRY(get(h, "speaker_encoder.project.weight", &t, {D, (int64_t)c.latent_dim * c.token_num}));
+  SC_TRY(upload(h, t->data, &h->spk_w));
+  SC_TRY(get(h, "speaker_encoder.project.bias", &t, {D}));
+  SC_TRY(upload(h, t->data, &h->spk_b));
+  {
+    // AdaLayerNorm i: rows [ (2i)*C, (2i+1)*C ) = scale, [ (2i+1)*C, (2i+2)*C ) = shift; i = 0 is the
+    // backbone norm, i = 1.. the ConvNeXt norms (vocos.py:100-110, 293-306)
+    h->n_ada = 1 + c.vocos_num_layers;
+    std::vector<float> w((size_t)h->n_ada * 2 * C * D), b((size_t)h->n_ada * 2 * C);
+    for (int i = 0; i < h->n_ada; ++i) {
+      const std::string p = i == 0 ? std::string("prenet.vocos_backbone.norm")
+                                   : "prenet.vocos_backbone.convnext." + std::to_string(i - 1) + ".norm";
+      const char* names[2] = {".scale", ".shift"};
+      for (int q = 0; q < 2; ++q) {
+        SC_TRY(get(h, p + names[q] + ".weight", &t, {C, D}));
+        SC_TRY(get(h, p + names[q] + ".bias", &u, {C}));
+        memcpy(&w[((size_t)i * 2 + q) * C * D], t->data.data(), (size_t)C * D * sizeof(float));
+        memcpy(&b[((size_t)i * 2 + q) * C], u->data.data(), (size_t)C * sizeof(float));
+      }
+    }
+    SC_TRY(upload(h, w, &h->ada_w));
+    SC_TRY(upload(h, b, &h->ada_b));
+  }
+
+  // ---- prenet backbones ----
+  h->backbones.resize(c.num_downsample + 1);
+  for (int i = 0; i < c.num_downsample; ++i)
+    SC_TRY(build_backbone(h, "prenet.downsample." + std::to_string(i) + ".1", c.downsample_layers, false,
+                          i + 1 < c.num_downsample ? 3.0f : 1.0f, &h->backbones[i]));
+  SC_TRY(build_backbone(h, "prenet.vocos_backbone", c.vocos_num_layers, true, 1.0f, &h->backbones[c.num_downsample]));
+  SC_TRY(build_conv1d(h, "prenet.linear", D, C, 1, 1, true, nullptr, &h->linear));
+
+  // ---- wave generator ----
+  const int ch = c.dec_channels;
+  SC_TRY(build_conv1d(h, "decoder.model.0", ch, D, 7, 1, false, nullptr, &h->conv_in));
+  h->ups.resize(c.num_upsample);
+  int cin = ch;
+  h->hop = 1;
+  for (int i = 0; i < c.num_upsample; ++i) {
+    UpBlock& ub = h->ups[i];
+    const int k = c.kernel_sizes[i], s = c.rates[i], cout = ch >> (i + 1);
+    if ((k - s) % 2 != 0 || k < s) {
+      set_error("upsample %d: kernel %d / stride %d must satisfy (k - s) even and k >= s", i, k, s);
+      return SPARKCODEC_EINVAL;
+    }
+    if (s > kMaxPhases || (k + s - 1) / s > kMaxTaps) {
+      set_error("upsample %d: stride %d / kernel %d outside the supported polyphase range", i, s, k);
+      return SPARKCODEC_EINVAL;
+    }
+    ub.stride = s; ub.c_in = cin; ub.c_out = cout;
+    h->hop *= s;
+    const std::string p = "decoder.model." + std::to_string(i + 1) + ".block";
+    SnakeParams* s_in = i == 0 ? &h->s_conv_in : &h->ups[i - 1].ru[2].s_next;
+    SC_TRY(upload_snake(h, p + ".0.alpha", cin, 1, s_in));
+    std::vector<float> w;
+    SC_TRY(conv_weight(h, p + ".1", {cin, cout, k}, &w));
+    SC_TRY(get(h, p + ".1.bias", &t, {cout}));
+    PackedGemm pk;
+    pack_conv_transpose1d(w.data(), cin, cout, k, s, t->data.data(), pk);
+    SC_TRY(upload_gemm(h, pk, &ub.convt));
+    const int dil[3] = {1, 3, 9};
+    for (int j = 0; j < 3; ++j) {
+      const std::string q = p + "." + std::to_string(j + 2) + ".block";
+      SnakeParams* s1 = j == 0 ? &ub.s_after : &ub.ru[j - 1].s_next;
+      SC_TRY(upload_snake(h, q + ".0.alpha", cout, j == 0 ? s : 1, s1));
+      SC_TRY(build_conv1d(h, q + ".1", cout, cout, 7, dil[j], false, nullptr, &ub.ru[j].c7));
+      SC_TRY(upload_snake(h, q + ".2.alpha", cout, 1, &ub.ru[j].s_mid));
+      SC_TRY(build_conv1d(h, q + ".3", cout, cout, 1, 1, false, nullptr, &ub.ru[j].c1));
+    }
+    cin = cout;
+  }
+  {
+    const int n = c.num_upsample;
+    SC_TRY(upload_snake(h, "decoder.model." + std::to_string(n + 1) + ".alpha", cin, 1, &h->s_head));
+    std::vector<float> w;
+    SC_TRY(conv_weight(h, "decoder.model." + std::to_string(n + 2), {1, cin, 7}, &w));
+    std::vector<float> wt((size_t)7 * cin);
+    for (int ci = 0; ci < cin; ++ci)
+      for (int j = 0; j < 7; ++j) wt[(size_t)j * cin + ci] = w[(size_t)ci * 7 + j];
+    SC_TRY(upload(h, wt, &h->head_w));
+    SC_TRY(get(h, "decoder.model." + std::to_string(n + 2) + ".bias", &t, {1}));
+    h->head_bias = t->data[0];
+    h->head_c = cin;
+  }
+  h->host.clear();
+  h->finalized = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ workspace
+struct Arena {
+  char* base; size_t off = 0, cap;
+  bool overflow = false;
+  void* take(size_t bytes) {
+    off = (off + 1023) & ~(size_t)1023;
+    void* p = base ? base + off : nullptr;
+    off += bytes;
+    if (off > cap) overflow = true;
+    return p;
+  }
+  float* f32(size_t n) { return static_cast<float*>(take(n * 4)); }
+  OpBuf op(size_t n) {
+    OpBuf o;
+    o.hi = static_cast<__nv_bfloat16*>(take(n * 2));
+    o.lo = static_cast<__nv_bfloat16*>(take(n * 2));
+    return o;
+  }
+};
+
+struct Workspace {
+  float *d, *flat, *ada, *px, *py, *x;
+  OpBuf pa, ph, w_in, w_c0, op1[2], op2;
+};
+
+static size_t max_cl(const sparkcodec_handle* h) {   // max over up-blocks of (channels * rows per frame)
+  size_t m = 0, rate = 1;
+  for (auto& ub : h->ups) {
+    rate *= ub.stride;
+    m = std::max(m, (size_t)ub.c_out * rate);
+  }
+  return m;
+}
+
+static void carve(const sparkcodec_handle* h, Arena& a, size_t B, size_t T, Workspace* w) {
+  const sparkcodec_config& c = h->cfg;
+  const size_t F = B * T, C = c.vocos_dim, D = c.d_model;
+  w->d = a.f32(B * D);
+  w->flat = a.f32(B * (size_t)c.latent_dim * c.token_num);
+  w->ada = a.f32(B * (size_t)h->n_ada * 2 * C);
+  w->px = a.f32(F * C);
+  w->py = a.f32(F * C);
+  w->pa = a.op(F * C);
+  w->ph = a.op(F * c.vocos_intermediate_dim);
+  w->w_in = a.op(F * D);
+  w->w_c0 = a.op(F * c.dec_channels);
+  const size_t m = max_cl(h);
+  w->x = a.f32(F * m);
+  w->op1[0] = a.op(F * m);
+  w->op1[1] = a.op(F * m);
+  w->op2 = a.op(F * m);
+}
+
+static size_t workspace_needed(const sparkcodec_handle* h, size_t B, size_t T) {
+  Arena a{nullptr, 0, ~(size_t)0};
+  Workspace w;
+  carve(h, a, B, T, &w);
+  return a.off + 1024;
+}
+
+// ------------------------------------------------------------------------------------ schedule
+struct TapReq {
+  const char* name = nullptr;
+  float* out = nullptr;
+  size_t cap = 0;
+  int64_t* shape = nullptr;
+  size_t b0 = 0;   // first utterance of the current pass
+  bool hit = false;
+};
+
+struct Pass {
+  sparkcodec_handle* h;
+  int B, T, prec;
+  cudaStream_t st;
+  TapReq* tap;
+
+  int gemm(const GemmWeights& w, const OpBuf& a, int L, const Epilogue& ep) {
+    if (h->impl == SPARKCODEC_IMPL_SIMT) return launch_conv_gemm_simt(w, a, B, L, ep, prec, st);
+    return launch_conv_gemm_tc(w, a, B, L, ep, prec, h->num_sms, st);
+  }
+  bool want(const char* name) const { return tap && tap->name && strcmp(tap->name, name) == 0; }
+  int tap_check(size_t rows, size_t ch) {
+    const size_t n = (size_t)B * rows * ch;
+    if ((tap->b0 * rows * ch + n) > tap->cap) {
+      set_error("tap buffer too small for '%s' (%zu floats needed)", tap->name, tap->b0 * rows * ch + n);
+      return SPARKCODEC_ENOMEM;
+    }
+    if (tap->shape) { tap->shape[0] = (int64_t)rows; tap->shape[1] = (int64_t)ch; }
+    tap->hit = true;
+    return 0;
+  }
+  int tap_f32(const char* name, const float* src, size_t rows, size_t ch) {
+    if (!want(name)) return 0;
+    SC_TRY(tap_check(rows, ch));
+    SC_CUDA(cudaMemcpyAsync(tap->out + tap->b0 * rows * ch, src, (size_t)B * rows * ch * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
+  int tap_op(const char* name, const OpBuf& src, size_t rows, size_t ch) {
+    if (!want(name)) return 0;
+    SC_TRY(tap_check(rows, ch));
+    OpBuf s = src;
+    if (prec != SPARKCODEC_PREC_FP32) s.lo = nullptr;
+    return launch_merge(s, tap->out + tap->b0 * rows * ch, (size_t)B * rows * ch, st);
+  }
+};
+
+static OpBuf mode_op(OpBuf o, int prec) {
+  if (prec != SPARKCODEC_PREC_FP32) o.lo = nullptr;
+  return o;
+}
+
+// One pass over B utterances of T frames.  x_in != null: skip the token stages + prenet and start the
+// wave generator from x_in (B,T,D) fp32.  x_out != null: stop after prenet(+d) and write it as fp32.
+static int run_pass(Pass& P, const void* sem, int sem_dt, const void* glob, int glob_dt, Workspace& W,
+                    const float* x_in, float* x_out, float* wav_out) {
+  sparkcodec_handle* h = P.h;
+  const sparkcodec_config& c = h->cfg;
+  const int B = P.B, T = P.T, prec = P.prec;
+  const int C = c.vocos_dim, D = c.d_model;
+  cudaStream_t st = P.st;
+  const OpBuf pa = mode_op(W.pa, prec), ph = mode_op(W.ph, prec), w_in = mode_op(W.w_in, prec),
+              w_c0 = mode_op(W.w_c0, prec), op2 = mode_op(W.op2, prec);
+  const OpBuf op1[2] = {mode_op(W.op1[0], prec), mode_op(W.op1[1], prec)};
+
+  if (!x_in) {
+    // ---- speaker tokens -> d_vector, AdaLN scale/shift for all 1 + vocos_num_layers norms ----
+    SC_TRY(launch_fsq_project(glob, glob_dt, B, c.token_num, c.fsq_num_levels, h->fsq_levels, h->fsq_wpo, h->fsq_bpo,
+                              c.latent_dim, W.flat, h->err_flag, st));
+    SC_TRY(launch_small_linear(W.flat, h->spk_w, h->spk_b, W.d, B, c.latent_dim * c.token_num, D, st));
+    SC_TRY(P.tap_f32("d_vector", W.d, 1, D));
+    const int ada_n = h->n_ada * 2 * C;
+    SC_TRY(launch_small_linear(W.d, h->ada_w, h->ada_b, W.ada, B, D, ada_n, st));
+    // ---- semantic tokens -> 3 * linear_pre(out_project(codebook[idx])) as operand planes ----
+    if (P.want("z_q")) {
+      SC_TRY(P.tap_check(T, D));
+      SC_TRY(launch_vq_zq(sem, sem_dt, B * T, c.codebook_size, c.codebook_dim, h->codebook, h->vq_w, h->vq_b, D,
+                          P.tap->out + P.tap->b0 * (size_t)T * D, st));
+    }
+    SC_TRY(launch_vq_embed(sem, sem_dt, B, T, 0, T, c.codebook_size, c.codebook_dim, h->codebook, h->vq_mat,
+                           h->vq_vec, C, pa, h->err_flag, st));
+    // ---- prenet: 2 x VocosBackbone(2 layers) + VocosBackbone(12 layers, AdaLN) ----
+    for (size_t bi = 0; bi < h->backbones.size(); ++bi) {
+      Backbone& bb = h->backbones[bi];
+      const std::string name = bb.ada ? std::string("prenet.vocos_backbone")
+                                      : "prenet.downsample." + std::to_string(bi) + ".1";
+      Epilogue e;
+      e.out_f32 = W.py;
+      SC_TRY(P.gemm(bb.embed, pa, T, e));                                           // embed conv k7 -> py
+      const float* sc = bb.ada ? W.ada : bb.norm_w;
+      const float* sh = bb.ada ? W.ada + C : bb.norm_b;
+      SC_TRY(launch_dwconv_ln(W.py, B, T, C, nullptr, nullptr, sc, sh, bb.ada ? ada_n : 0, 1e-6f, W.px, OpBuf(), st));
+      SC_TRY(P.tap_f32((name + ".norm").c_str(), W.px, T, C));
+      for (size_t i = 0; i < bb.blocks.size(); ++i) {
+        ConvNeXt& blk = bb.blocks[i];
+        sc = bb.ada ? W.ada + (size_t)(i + 1) * 2 * C : blk.ln_w;
+        sh = bb.ada ? W.ada + (size_t)(i + 1) * 2 * C + C : blk.ln_b;
+        SC_TRY(launch_dwconv_ln(W.px, B, T, C, blk.dw_w, blk.dw_b, sc, sh, bb.ada ? ada_n : 0, 1e-6f, nullptr, pa, st));
+        Epilogue e1;
+        e1.act = ACT_GELU;
+        e1.out_op = ph;
+        SC_TRY(P.gemm(blk.pw1, pa, T, e1));                                          // 384 -> 2048, GELU
+        Epilogue e2;
+        e2.residual = W.px;
+        e2.out_f32 = W.px;
+        SC_TRY(P.gemm(blk.pw2, ph, T, e2));                                          // 2048 -> 384, gamma, + x
+        SC_TRY(P.tap_f32((name + ".convnext." + std::to_string(i)).c_str(), W.px, T, C));
+      }
+      SC_TRY(launch_dwconv_ln(W.px, B, T, C, nullptr, nullptr, bb.final_w, bb.final_b, 0, 1e-6f, nullptr, pa, st));
+      // oracle tap names; NOTE the x3 of the following SamplingBlock is already folded in for downsample.0
+      const std::string out_name = bb.ada ? std::string("prenet.vocos_backbone") : "prenet.downsample." + std::to_string(bi);
+      SC_TRY(P.tap_op(out_name.c_str(), pa, T, C));
+    }
+    // ---- linear 384 -> 1024, + d_vector broadcast over time (bicodec.py:186) ----
+    Epilogue el;
+    el.rowbias = W.d;
+    if (x_out) el.out_f32 = x_out; else el.out_op = w_in;
+    if (P.want("prenet_plus_d") && !x_out) el.out_f32 = W.x;   // W.x is free until the first up-block
+    SC_TRY(P.gemm(h->linear, pa, T, el));
+    if (!x_out) SC_TRY(P.tap_f32("prenet_plus_d", W.x, T, D));
+    if (x_out) return 0;
+  } else {
+    SC_TRY(launch_split(x_in, w_in, (size_t)B * T * D, st));
+  }
+
+  // ---- WaveGenerator ----
+  {
+    Epilogue e;
+    e.act = ACT_SNAKE; e.alpha = h->s_conv_in.alpha; e.inv_alpha = h->s_conv_in.inv;
+    e.out_op = w_c0;
+    if (P.want("decoder.model.0")) e.out_f32 = W.x;
+    SC_TRY(P.gemm(h->conv_in, w_in, T, e));
+    SC_TRY(P.tap_f32("decoder.model.0", W.x, T, c.dec_channels));
+  }
+  OpBuf cur = w_c0;   // snake'd operand feeding the next transposed conv
+  int L = T, pp = 0;
+  for (size_t i = 0; i < h->ups.size(); ++i) {
+    UpBlock& ub = h->ups[i];
+    const std::string name = "decoder.model." + std::to_string(i + 1) + ".block";
+    {
+      Epilogue e;
+      e.out_f32 = W.x;
+      e.act = ACT_SNAKE; e.alpha = ub.s_after.alpha; e.inv_alpha = ub.s_after.inv;
+      e.out_op = op1[pp];
+      SC_TRY(P.gemm(ub.convt, cur, L, e));   // rows L, n_total = s*C_out  ==  (B, s*L, C_out)
+    }
+    L *= ub.stride;
+    SC_TRY(P.tap_f32((name + ".1").c_str(), W.x, L, ub.c_out));
+    for (int j = 0; j < 3; ++j) {
+      ResUnit& ru = ub.ru[j];
+      Epilogue e7;
+      e7.act = ACT_SNAKE; e7.alpha = ru.s_mid.alpha; e7.inv_alpha = ru.s_mid.inv;
+      e7.out_op = op2;
+      SC_TRY(P.gemm(ru.c7, op1[pp], L, e7));
+      Epilogue e1;
+      e1.residual = W.x;
+      e1.out_f32 = W.x;
+      const bool last = (i + 1 == h->ups.size()) && j == 2;
+      if (!last) {
+        e1.act = ACT_SNAKE; e1.alpha = ru.s_next.alpha; e1.inv_alpha = ru.s_next.inv;
+        e1.out_op = op1[pp ^ 1];
+      }
+      SC_TRY(P.gemm(ru.c1, op2, L, e1));
+      pp ^= 1;
+      SC_TRY(P.tap_f32((name + "." + std::to_string(j + 2)).c_str(), W.x, L, ub.c_out));
+    }
+    cur = op1[pp];
+  }
+  SC_TRY(launch_head(W.x, B, L, h->head_c, h->s_head.alpha, h->s_head.inv, h->head_w, h->head_bias, wav_out, 0, L, st));
+  return 0;
+}
+
+static int check_common(sparkcodec_handle* h, int batch, int frames, int precision) {
+  if (!h) { set_error("null handle"); return SPARKCODEC_EINVAL; }
+  if (!h->finalized) { set_error("sparkcodec_finalize has not been called"); return SPARKCODEC_ESTATE; }
+  if (batch < 0 || frames < 0) { set_error("negative batch/frames"); return SPARKCODEC_EINVAL; }
+  if (precision != SPARKCODEC_PREC_FP32 && precision != SPARKCODEC_PREC_BF16) {
+    set_error("unknown precision %d", precision);
+    return SPARKCODEC_EINVAL;
+  }
+  return 0;
+}
+
+// Splits the batch into passes that fit the caller's workspace.
+static int run_all(sparkcodec_handle* h, const void* sem, int sem_dt, const void* glob, int glob_dt, int batch,
+                   int frames, int precision, void* ws, size_t ws_bytes, const float* x_in, float* x_out,
+                   float* wav_out, TapReq* tap, cudaStream_t st) {
+  SC_TRY(check_common(h, batch, frames, precision));
+  if ((sem_dt != SPARKCODEC_I32 && sem_dt != SPARKCODEC_I64) || (glob_dt != SPARKCODEC_I32 && glob_dt != SPARKCODEC_I64)) {
+    set_error("token dtype must be SPARKCODEC_I32 or SPARKCODEC_I64");
+    return SPARKCODEC_EINVAL;
+  }
+  if (batch == 0 || frames == 0) return 0;
+  int per_pass = batch;
+  while (per_pass > 1 && workspace_needed(h, per_pass, frames) > ws_bytes) per_pass = (per_pass + 1) / 2;
+  if (workspace_needed(h, per_pass, frames) > ws_bytes || !ws) {
+    set_error("workspace of %zu bytes cannot hold even one utterance of %d frames (%zu needed)", ws_bytes, frames,
+              workspace_needed(h, 1, frames));
+    return SPARKCODEC_ENOMEM;
+  }
+  SC_CUDA(cudaSetDevice(h->device));
+  g_launch_counter = &h->launches;
+  const sparkcodec_config& c = h->cfg;
+  const size_t sem_sz = sem_dt == SPARKCODEC_I64 ? 8 : 4, glob_sz = glob_dt == SPARKCODEC_I64 ? 8 : 4;
+  for (int b0 = 0; b0 < batch; b0 += per_pass) {
+    const int B = std::min(per_pass, batch - b0);
+    Arena a{static_cast<char*>(ws), 0, ws_bytes};
+    Workspace W;
+    carve(h, a, B, frames, &W);
+    Pass P{h, B, frames, precision, st, tap};
+    if (tap) tap->b0 = b0;
+    const char* semp = sem ? static_cast<const char*>(sem) + (size_t)b0 * frames * sem_sz : nullptr;
+    const char* globp = glob ? static_cast<const char*>(glob) + (size_t)b0 * c.token_num * glob_sz : nullptr;
+    SC_TRY(run_pass(P, semp, sem_dt, globp, glob_dt, W,
+                    x_in ? x_in + (size_t)b0 * frames * c.d_model : nullptr,
+                    x_out ? x_out + (size_t)b0 * frames * c.d_model : nullptr,
+                    wav_out ? wav_out + (size_t)b0 * frames * h->hop : nullptr));
+  }
+  if (tap && tap->name && !tap->hit) {
+    set_error("unknown tap '%s'", tap->name);
+    return SPARKCODEC_EINVAL;
+  }
+  return 0;
+}
+
+}  // namespace sparkcodec
+
+// ================================================================================== extern "C"
+extern "C" {
+
+const char* sparkcodec_last_error(void) { return g_err; }
+int sparkcodec_abi_version(void) { return SPARKCODEC_ABI_VERSION; }
+
+int sparkcodec_create(const sparkcodec_config* cfg, int device, sparkcodec_handle** out) {
+  if (!cfg || !out) { set_error("null argument"); return SPARKCODEC_EINVAL; }
+  if (cfg->fsq_num_levels < 1 || cfg->fsq_num_levels > 8 || cfg->num_upsample < 1 || cfg->num_upsample > 8 ||
+      cfg->num_downsample < 0 || cfg->num_downsample > 4) {
+    set_error("config out of range (fsq_num_levels %d, num_upsample %d, num_downsample %d)", cfg->fsq_num_levels,
+              cfg->num_upsample, cfg->num_downsample);
+    return SPARKCODEC_EINVAL;
+  }
+  if (cfg->vocos_dim % 128 || cfg->d_model % 64 || cfg->vocos_intermediate_dim % 64 ||
+      (cfg->dec_channels >> cfg->num_upsample) % 32 || (cfg->dec_channels >> cfg->num_upsample) > 128) {
+    set_error("unsupported widths: vocos_dim %% 128, d_model/intermediate %% 64, final decoder width in {32,64,96,128}");
+    return SPARKCODEC_EINVAL;
+  }
+  int ndev = 0;
+  SC_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) { set_error("device %d out of range (%d devices)", device, ndev); return SPARKCODEC_EINVAL; }
+  SC_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  SC_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("libsparkcodec is built for sm_100a (B200); device %d is sm_%d%d", device, prop.major, prop.minor);
+    return SPARKCODEC_ECUDA;
+  }
+  auto* h = new sparkcodec_handle();
+  h->cfg = *cfg;
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  *out = h;
+  return 0;
+}
+
+int sparkcodec_destroy(sparkcodec_handle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  for (void* p : h->allocs) cudaFree(p);
+  if (g_launch_counter == &h->launches) g_launch_counter = nullptr;
+  delete h;
+  return 0;
+}
+
+int sparkcodec_set_tensor(sparkcodec_handle* h, const char* key, const float* data, const int64_t* shape, int ndim) {
+  if (!h || !key || !data || (!shape && ndim > 0) || ndim < 0 || ndim > 4) { set_error("bad argument"); return SPARKCODEC_EINVAL; }
+  if (h->finalized) { set_error("weights are already finalized"); return SPARKCODEC_ESTATE; }
+  const std::string k(key);
+  static const char* used[] = {"quantizer.codebook.", "quantizer.out_project.", "speaker_encoder.quantizer.project_out.",
+                               "speaker_encoder.project.", "prenet.", "decoder."};
+  bool keep = false;
+  for (const char* p : used) keep |= k.rfind(p, 0) == 0;
+  if (!keep) return 0;   // encode-side / training-only tensor
+  HostTensor t;
+  t.shape.assign(shape, shape + ndim);
+  const int64_t n = t.numel();
+  if (n < 0 || n > (int64_t)1 << 31) { set_error("tensor '%s' too large", key); return SPARKCODEC_EINVAL; }
+  t.data.assign(data, data + n);
+  h->host[k] = std::move(t);
+  return 0;
+}
+
+int sparkcodec_finalize(sparkcodec_handle* h) {
+  if (!h) { set_error("null handle"); return SPARKCODEC_EINVAL; }
+  if (h->finalized) return 0;
+  SC_CUDA(cudaSetDevice(h->device));
+  return do_finalize(h);
+}
+
+int sparkcodec_workspace_bytes(sparkcodec_handle* h, int batch, int frames, size_t* bytes) {
+  if (!bytes) { set_error("null argument"); return SPARKCODEC_EINVAL; }
+  SC_TRY(check_common(h, batch, frames, SPARKCODEC_PREC_FP32));
+  *bytes = workspace_needed(h, (size_t)std::max(batch, 1), (size_t)std::max(frames, 1));
+  return 0;
+}
+
+int sparkcodec_detokenize(sparkcodec_handle* h, const void* semantic, int sem_dtype, const void* global_tokens,
+                          int glob_dtype, int batch, int frames, int precision, void* workspace,
+                          size_t workspace_bytes, float* wav_out, void* stream) {
+  if (batch > 0 && frames > 0 && (!semantic || !global_tokens || !wav_out)) { set_error("null tensor pointer"); return SPARKCODEC_EINVAL; }
+  return run_all(h, semantic, sem_dtype, global_tokens, glob_dtype, batch, frames, precision, workspace,
+                 workspace_bytes, nullptr, nullptr, wav_out, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int sparkcodec_prenet(sparkcodec_handle* h, const void* semantic, int sem_dtype, const void* global_tokens,
+                      int glob_dtype, int batch, int frames, int precision, void* workspace, size_t workspace_bytes,
+                      float* x_out, void* stream) {
+  if (batch > 0 && frames > 0 && (!semantic || !global_tokens || !x_out)) { set_error("null tensor pointer"); return SPARKCODEC_EINVAL; }
+  return run_all(h, semantic, sem_dtype, global_tokens, glob_dtype, batch, frames, precision, workspace,
+                 workspace_bytes, nullptr, x_out, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int sparkcodec_wavegen(sparkcodec_handle* h, const float* x_in, int batch, int frames, int precision, void* workspace,
+                       size_t workspace_bytes, float* wav_out, void* stream) {
+  if (batch > 0 && frames > 0 && (!x_in || !wav_out)) { set_error("null tensor pointer"); return SPARKCODEC_EINVAL; }
+  return run_all(h, nullptr, SPARKCODEC_I32, nullptr, SPARKCODEC_I32, batch, frames, precision, workspace,
+                 workspace_bytes, x_in, nullptr, wav_out, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int sparkcodec_halo_frames(sparkcodec_handle* h, int* prenet_halo, int* wavegen_halo) {
+  if (!h || !prenet_halo || !wavegen_halo) { set_error("null argument"); return SPARKCODEC_EINVAL; }
+  if (!h->finalized) { set_error("sparkcodec_finalize has not been called"); return SPARKCODEC_ESTATE; }
+  const sparkcodec_config& c = h->cfg;
+  // prenet: every backbone = embed conv (3) + layers x depthwise conv (3 each), all at frame rate
+  int pre = 0;
+  for (int i = 0; i < c.num_downsample; ++i) pre += 3 + 3 * c.downsample_layers;
+  pre += 3 + 3 * c.vocos_num_layers;
+  // wave generator: conv_in (3 frames), then per up-block the transposed conv's reach in input rows
+  // (max |tap shift|) and three residual units (k7, dilation 1/3/9 -> 39 rows) at the block's rate
+  double halo_frames = 3.0, rate = 1.0;
+  for (auto& ub : h->ups) {
+    int reach = 0;
+    for (int r = 0; r < ub.convt.taps.n_phase; ++r)
+      for (int m = 0; m < ub.convt.taps.ntaps[r]; ++m) reach = std::max(reach, std::abs(ub.convt.taps.shift[r][m]));
+    halo_frames += reach / rate;
+    rate *= ub.stride;
+    halo_frames += 3.0 * (1 + 3 + 9) / rate;
+  }
+  halo_frames += 3.0 / rate;   // head conv k7
+  *prenet_halo = pre;
+  *wavegen_halo = (int)std::ceil(halo_frames);
+  return 0;
+}
+
+int sparkcodec_check_tokens(sparkcodec_handle* h, void* stream) {
+  if (!h || !h->finalized) { set_error("handle not ready"); return SPARKCODEC_ESTATE; }
+  int e[4];
+  SC_CUDA(cudaMemcpyAsync(e, h->err_flag, sizeof(e), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+  SC_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  if (e[0] == 0) return 0;
+  SC_CUDA(cudaMemsetAsync(h->err_flag, 0, sizeof(e), static_cast<cudaStream_t>(stream)));
+  const long long v = ((long long)e[3] << 32) | (unsigned int)e[2];
+  set_error("%s token id %lld at flat position %d is out of range", e[0] == 1 ? "semantic" : "global", v, e[1]);
+  return SPARKCODEC_EINDEX;
+}
+
+int sparkcodec_set_impl(sparkcodec_handle* h, int impl) {
+  if (!h || (impl != SPARKCODEC_IMPL_TC && impl != SPARKCODEC_IMPL_SIMT)) { set_error("bad impl"); return SPARKCODEC_EINVAL; }
+  h->impl = impl;
+  return 0;
+}
+
+int sparkcodec_detokenize_tap(sparkcodec_handle* h, const void* semantic, int sem_dtype, const void* global_tokens,
+                              int glob_dtype, int batch, int frames, int precision, void* workspace,
+                              size_t workspace_bytes, float* wav_out, const char* tap, float* tap_out,
+                              size_t tap_capacity, int64_t* tap_shape, void* stream) {
+  if (!semantic || !global_tokens || !wav_out || !tap || !tap_out) { set_error("null argument"); return SPARKCODEC_EINVAL; }
+  TapReq t;
+  t.name = tap; t.out = tap_out; t.cap = tap_capacity; t.shape = tap_shape;
+  return run_all(h, semantic, sem_dtype, global_tokens, glob_dtype, batch, frames, precision, workspace,
+                 workspace_bytes, nullptr, nullptr, wav_out, &t, static_cast<cudaStream_t>(stream));
+}
+
+int sparkcodec_launch_count(sparkcodec_handle* h, int64_t* count) {
+  if (!h || !count) { set_error("null argument"); return SPARKCODEC_EINVAL; }
+  *count = h->launches;
+  return 0;
+}
+
+int sparkcodec_pack_conv(int kind, const float* w_host, const int64_t* wshape, int param, uint16_t* w_hi,
+                         uint16_t* w_lo, size_t w_capacity, int32_t* shifts, int32_t* ntaps, int32_t* kt,
+                         int32_t* n_phase, int32_t* n_total) {
+  if (!w_host || !wshape || !kt || !n_phase || !n_total) { set_error("null argument"); return SPARKCODEC_EINVAL; }
+  PackedGemm pk;
+  if (kind == 0) pack_conv1d(w_host, (int)wshape[0], (int)wshape[1], (int)wshape[2], param, nullptr, nullptr, pk);
+  else if (kind == 1) pack_conv_transpose1d(w_host, (int)wshape[0], (int)wshape[1], (int)wshape[2], param, nullptr, pk);
+  else { set_error("kind must be 0 (Conv1d) or 1 (ConvTranspose1d)"); return SPARKCODEC_EINVAL; }
+  *kt = pk.kt; *n_phase = pk.taps.n_phase; *n_total = pk.n_total;
+  if (w_hi && w_lo) {
+    if (pk.w_hi.size() > w_capacity) { set_error("w buffers too small (%zu needed)", pk.w_hi.size()); return SPARKCODEC_ENOMEM; }
+    memcpy(w_hi, pk.w_hi.data(), pk.w_hi.size() * 2);
+    memcpy(w_lo, pk.w_lo.data(), pk.w_lo.size() * 2);
+  }
+  if (ntaps) for (int r = 0; r < pk.taps.n_phase; ++r) ntaps[r] = pk.taps.ntaps[r];
+  if (shifts)
+    for (int r = 0; r < pk.taps.n_phase; ++r)
+      for (int m = 0; m < pk.kt; ++m) shifts[r * pk.kt + m] = m < pk.taps.ntaps[r] ? pk.taps.shift[r][m] : INT32_MIN;
+  return 0;
+}
+
+int sparkcodec_op_conv(int device, int kind, const float* w_host, const int64_t* wshape, const float* bias_host,
+                       int param, int batch, int L, const float* x_dev, float* y_dev, const float* residual_dev,
+                       int act, const float* alpha_host, int precision, int impl, void* stream) {
+  if (!w_host || !wshape || !x_dev || !y_dev) { set_error("null argument"); return SPARKCODEC_EINVAL; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SC_CUDA(cudaSetDevice(device));
+  sparkcodec_handle tmp;   // only used as an allocation list
+  tmp.device = device;
+  cudaDeviceProp prop;
+  SC_CUDA(cudaGetDeviceProperties(&prop, device));
+  g_launch_counter = nullptr;
+  PackedGemm pk;
+  int c_in, c_out;
+  if (kind == 0) {
+    c_out = (int)wshape[0]; c_in = (int)wshape[1];
+    pack_conv1d(w_host, c_out, c_in, (int)wshape[2], param, bias_host, nullptr, pk);
+  } else if (kind == 1) {
+    c_in = (int)wshape[0]; c_out = (int)wshape[1];
+    pack_conv_transpose1d(w_host, c_in, c_out, (int)wshape[2], param, bias_host, pk);
+  } else { set_error("kind must be 0 or 1"); return SPARKCODEC_EINVAL; }
+  int rc = 0;
+  auto cleanup = [&]() { cudaStreamSynchronize(st); for (void* p : tmp.allocs) cudaFree(p); };
+  GemmWeights g;
+  OpBuf a, o;
+  SnakeParams sp;
+  void* p;
+  const size_t n_in = (size_t)batch * L * c_in, n_out = (size_t)batch * L * pk.n_total;
+  do {
+    if ((rc = upload_gemm(&tmp, pk, &g))) break;
+    if ((rc = dev_alloc(&tmp, n_in * 2, &p))) break; a.hi = (__nv_bfloat16*)p;
+    if ((rc = dev_alloc(&tmp, n_in * 2, &p))) break; a.lo = (__nv_bfloat16*)p;
+    if ((rc = launch_split(x_dev, a, n_in, st))) break;
+    Epilogue e;
+    e.residual = residual_dev;
+    if (act == ACT_NONE) {
+      e.out_f32 = y_dev;
+    } else {
+      if ((rc = dev_alloc(&tmp, n_out * 2, &p))) break; o.hi = (__nv_bfloat16*)p;
+      if ((rc = dev_alloc(&tmp, n_out * 2, &p))) break; o.lo = (__nv_bfloat16*)p;
+      e.act = act;
+      e.out_op = o;
+      if (act == ACT_SNAKE) {
+        if (!alpha_host) { set_error("snake needs alpha"); rc = SPARKCODEC_EINVAL; break; }
+        const int rep = pk.n_total / c_out;
+        std::vector<float> al((size_t)pk.n_total), inv((size_t)pk.n_total);
+        for (int r = 0; r < rep; ++r)
+          for (int i = 0; i < c_out; ++i) {
+            al[(size_t)r * c_out + i] = alpha_host[i];
+            inv[(size_t)r * c_out + i] = 1.0f / (alpha_host[i] + 1e-9f);
+          }
+        if ((rc = upload(&tmp, al, &sp.alpha))) break;
+        if ((rc = upload(&tmp, inv, &sp.inv))) break;
+        e.alpha = sp.alpha; e.inv_alpha = sp.inv;
+      }
+    }
+    if (precision != SPARKCODEC_PREC_FP32) { a.lo = nullptr; }
+    if (impl == SPARKCODEC_IMPL_SIMT) rc = launch_conv_gemm_simt(g, a, batch, L, e, precision, st);
+    else rc = launch_conv_gemm_tc(g, a, batch, L, e, precision, prop.multiProcessorCount, st);
+    if (rc) break;
+    if (act != ACT_NONE) {
+      OpBuf m = o;
+      if (precision != SPARKCODEC_PREC_FP32) m.lo = nullptr;
+      if ((rc = launch_merge(m, y_dev, n_out, st))) break;
+    }
+    cudaError_t ce = cudaStreamSynchronize(st);
+    if (ce != cudaSuccess) { set_error("op_conv: %s", cudaGetErrorString(ce)); rc = SPARKCODEC_ECUDA; }
+  } while (0);
+  cleanup();
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,133 @@
+// Shared declarations for libsparkcodec (B200 / sm_100a BiCodec detokenize path).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/sparkcodec.h"
+
+namespace sparkcodec {
+
+// ---- error plumbing --------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern thread_local int64_t* g_launch_counter;   // points at the active handle's counter (or null)
+
+#define SC_CUDA(expr)                                                                      \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      ::sparkcodec::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr,           \
+                              cudaGetErrorString(_e));                                     \
+      return SPARKCODEC_ECUDA;                                                             \
+    }                                                                                      \
+  } while (0)
+
+#define SC_TRY(expr)                                                                       \
+  do {                                                                                     \
+    int _r = (expr);                                                                       \
+    if (_r != 0) return _r;                                                                \
+  } while (0)
+
+#define SC_LAUNCH_CHECK()                                                                  \
+  do {                                                                                     \
+    if (::sparkcodec::g_launch_counter) ++*::sparkcodec::g_launch_counter;                 \
+    SC_CUDA(cudaGetLastError());                                                           \
+  } while (0)
+
+// ---- activations -------------------------------------------------------------------------------
+// All activations are channels-last (batch, rows, channels).  A dense-contraction operand is stored
+// as two bf16 planes hi = bf16(x), lo = bf16(x - hi) (the "OP" format); the fp32-precision mode
+// multiplies hi*Whi + lo*Whi + hi*Wlo on the tensor cores, the bf16 mode only hi*Whi.
+struct OpBuf {
+  __nv_bfloat16* hi = nullptr;
+  __nv_bfloat16* lo = nullptr;   // null in bf16 mode
+};
+
+constexpr int kMaxPhases = 8;   // polyphase branches of a transposed conv (= stride)
+constexpr int kMaxTaps = 7;     // taps per branch (k=7 convs; <=3 for the transposed convs)
+constexpr int kBlockM = 128;    // rows of one accumulator tile (UMMA M)
+
+// Tap table of one dense contraction seen as D[b,l,n] = sum_j sum_c A[b, l+shift[ph][j], c] * W[n, j*C_in + c]
+struct TapTable {
+  int n_phase = 1;
+  int cols_per_phase = 0;                  // N_total / n_phase (= C_out)
+  int ntaps[kMaxPhases] = {0};
+  int shift[kMaxPhases][kMaxTaps] = {{0}};
+};
+
+// Device-resident packed weights of one dense contraction.
+struct GemmWeights {
+  int c_in = 0, n_total = 0, kt = 0;       // W is (n_total, kt*c_in) K-major
+  TapTable taps;
+  __nv_bfloat16* w_hi = nullptr;
+  __nv_bfloat16* w_lo = nullptr;
+  float* bias = nullptr;                   // (n_total) (phase-replicated for transposed convs)
+  int block_n = 0, bk = 0;                 // tile shape chosen for the tcgen05 kernel
+  CUtensorMap tmap_hi, tmap_lo;            // (K, N) boxes (bk, block_n)
+};
+
+enum Act { ACT_NONE = 0, ACT_GELU = 1, ACT_SNAKE = 2 };
+
+struct Epilogue {
+  const float* rowbias = nullptr;    // (batch, n_total) added per utterance (d_vector), optional
+  const float* residual = nullptr;   // (batch, L, n_total) fp32, optional (may alias out_f32)
+  int act = ACT_NONE;
+  const float* alpha = nullptr;      // (n_total) snake alpha of the NEXT layer's input snake
+  const float* inv_alpha = nullptr;  // (n_total) 1/(alpha+1e-9)
+  float* out_f32 = nullptr;          // pre-activation value (residual stream), optional
+  OpBuf out_op;                      // post-activation operand planes, optional
+};
+
+// ---- kernels / launchers (defined in the .cu files) --------------------------------------------
+int tma_init();   // resolves cuTensorMapEncodeTiled through the runtime (no link-time libcuda dep)
+int make_weight_tmaps(GemmWeights& w);
+
+// D = conv(A) with fused epilogue.  A: (batch, L, c_in) operand planes.
+int launch_conv_gemm_tc(const GemmWeights& w, const OpBuf& a, int batch, int L, const Epilogue& ep,
+                        int precision, int num_sms, cudaStream_t stream);
+int launch_conv_gemm_simt(const GemmWeights& w, const OpBuf& a, int batch, int L, const Epilogue& ep,
+                          int precision, cudaStream_t stream);
+
+// streaming / token kernels
+int launch_split(const float* x, OpBuf out, size_t n, cudaStream_t s);                 // fp32 -> hi/lo
+int launch_merge(const OpBuf& in, float* out, size_t n, cudaStream_t s);               // hi(+lo) -> fp32
+int launch_vq_embed(const void* sem, int sem_dtype, int batch, int frames, int t0, int rows,
+                    int codebook_size, int codebook_dim, const float* codebook, const float* mat,
+                    const float* vec, int c_out, OpBuf out, int* err_flag, cudaStream_t s);
+int launch_vq_zq(const void* sem, int sem_dtype, int n_tok, int codebook_size, int codebook_dim,
+                 const float* codebook, const float* w, const float* bias, int d_model, float* out,
+                 cudaStream_t s);
+int launch_fsq_project(const void* glob, int glob_dtype, int batch, int token_num, int n_levels,
+                       const int* levels, const float* w_po, const float* b_po, int latent,
+                       float* flat_out, int* err_flag, cudaStream_t s);
+int launch_small_linear(const float* x, const float* w, const float* bias, float* y, int batch, int k,
+                        int n, cudaStream_t s);
+// (depthwise k=7 conv +) LayerNorm over channels, affine per utterance (scale/shift with batch stride)
+int launch_dwconv_ln(const float* x, int batch, int rows, int c, const float* dw_w, const float* dw_b,
+                     const float* scale, const float* shift, int ss_batch_stride, float eps,
+                     float* out_f32, OpBuf out_op, cudaStream_t s);
+int launch_head(const float* x, int batch, int rows, int c, const float* alpha, const float* inv_alpha,
+                const float* w, float bias, float* wav, int crop_begin, int crop_rows, cudaStream_t s);
+
+// ---- small host helpers ------------------------------------------------------------------------
+inline uint16_t f32_to_bf16_rn(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);   // NaN
+  uint32_t r = u + 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(r >> 16);
+}
+inline float bf16_to_f32(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+}  // namespace sparkcodec

@@ -1,0 +1,421 @@
+// HBM-streaming and token kernels of the BiCodec detokenize path (sm_100a):
+//   * split / merge            fp32 <-> bf16 hi/lo operand planes
+//   * vq_embed / vq_zq         FactorizedVectorQuantize.detokenize (+ folded linear_pre, x3)
+//   * fsq_project              FSQ index -> level codes -> project_out -> (c*N + n) flattening
+//   * small_linear             tiny per-utterance Linear layers (speaker project, AdaLN scale/shift)
+//   * dwconv_ln                depthwise k=7 conv + LayerNorm / AdaLayerNorm, smem halo staging
+//   * head                     Snake -> Conv1d(C->1, k=7) -> tanh, warp-shuffle channel reduction
+#include "common.cuh"
+#include "gemm_params.cuh"
+
+namespace sparkcodec {
+namespace {
+
+__device__ __forceinline__ void store_op4(const OpBuf& o, size_t idx, float4 v) {
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+  uint2 hp;
+  hp.x = *reinterpret_cast<uint32_t*>(&h0);
+  hp.y = *reinterpret_cast<uint32_t*>(&h1);
+  *reinterpret_cast<uint2*>(o.hi + idx) = hp;
+  if (o.lo) {
+    float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+    __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y);
+    __nv_bfloat162 l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
+    uint2 lp;
+    lp.x = *reinterpret_cast<uint32_t*>(&l0);
+    lp.y = *reinterpret_cast<uint32_t*>(&l1);
+    *reinterpret_cast<uint2*>(o.lo + idx) = lp;
+  }
+}
+
+// ------------------------------------------------------------------------------- split / merge
+__global__ void split_kernel(const float4* __restrict__ x, OpBuf out, size_t n4) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
+    store_op4(out, i * 4, __ldg(x + i));
+}
+__global__ void merge_kernel(OpBuf in, float* __restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float v = __bfloat162float(in.hi[i]);
+    if (in.lo) v += __bfloat162float(in.lo[i]);
+    out[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------ tokens
+__device__ __forceinline__ long long load_token(const void* p, int dtype, size_t i) {
+  return dtype == SPARKCODEC_I64 ? static_cast<const long long*>(p)[i]
+                                 : (long long)static_cast<const int*>(p)[i];
+}
+// err[0] = 1 + which (0 semantic, 1 global), err[1] = flat position, err[2..3] = value
+__device__ __forceinline__ void report_bad_token(int* err, int which, size_t pos, long long v) {
+  if (atomicCAS(err, 0, 1 + which) == 0) {
+    err[1] = (int)pos;
+    err[2] = (int)(v & 0xffffffffll);
+    err[3] = (int)(v >> 32);
+  }
+}
+
+// x0[tok, c] = mat[c, :] . codebook[idx[tok], :] + vec[c]   (mat/vec fold out_project, linear_pre and
+// the first SamplingBlock's x3: a purely linear chain, factorized_vector_quantize.py:157 ->
+// feat_decoder.py:87 -> samper.py:98).  One thread per (token, 4 channels).
+__global__ void vq_embed_kernel(const void* __restrict__ sem, int sem_dtype, size_t n_tok, int codebook_size,
+                                int cdim, const float* __restrict__ codebook, const float* __restrict__ mat,
+                                const float* __restrict__ vec, int c_out, OpBuf out, int* err) {
+  const int groups = c_out / 4;
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n_tok * groups) return;
+  const size_t tok = i / groups;
+  const int c = (int)(i % groups) * 4;
+  long long id = load_token(sem, sem_dtype, tok);
+  if (id < 0 || id >= codebook_size) {
+    if (c == 0) report_bad_token(err, 0, tok, id);
+    id = 0;
+  }
+  const float* e = codebook + (size_t)id * cdim;
+  float acc[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float a = __ldg(vec + c + q);
+    for (int j = 0; j < cdim; ++j) a = fmaf(__ldg(mat + (size_t)(c + q) * cdim + j), __ldg(e + j), a);
+    acc[q] = a;
+  }
+  store_op4(out, tok * c_out + c, make_float4(acc[0], acc[1], acc[2], acc[3]));
+}
+
+// z_q[tok, :] = W_out . codebook[idx] + b_out (test tap; factorized_vector_quantize.py:154-158)
+__global__ void vq_zq_kernel(const void* __restrict__ sem, int sem_dtype, size_t n_tok, int codebook_size, int cdim,
+                             const float* __restrict__ codebook, const float* __restrict__ w,
+                             const float* __restrict__ bias, int d_model, float* __restrict__ out) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n_tok * d_model) return;
+  const size_t tok = i / d_model;
+  const int c = (int)(i % d_model);
+  long long id = load_token(sem, sem_dtype, tok);
+  if (id < 0 || id >= codebook_size) id = 0;
+  const float* e = codebook + (size_t)id * cdim;
+  // same association order as a 1x1 conv over 8 input channels: bias added last
+  float a = 0.f;
+  for (int j = 0; j < cdim; ++j) a = fmaf(__ldg(w + (size_t)c * cdim + j), __ldg(e + j), a);
+  out[i] = a + __ldg(bias + c);
+}
+
+// FSQ: level_j = (idx / basis_j) % L_j, code_j = (level_j - L_j/2) / (L_j/2)   (exact in fp32)
+// z[c] = W_po[c,:] . code + b_po[c];  flat[b, c*N + n] = z[c]   (finite_scalar_quantization.py:143-162,
+// residual_fsq.py:191-199, speaker_encoder.py:107-111).  One block per (b, n), one thread per c.
+__global__ void fsq_project_kernel(const void* __restrict__ glob, int glob_dtype, int token_num, int n_levels,
+                                   const int* __restrict__ levels, const float* __restrict__ w_po,
+                                   const float* __restrict__ b_po, int latent, float* __restrict__ flat, int* err) {
+  const int bn = blockIdx.x, b = bn / token_num, n = bn % token_num;
+  long long id = load_token(glob, glob_dtype, (size_t)bn);
+  long long total = 1;
+  for (int j = 0; j < n_levels; ++j) total *= levels[j];
+  if (id < 0 || id >= total) {
+    if (threadIdx.x == 0) report_bad_token(err, 1, (size_t)bn, id);
+    id = 0;
+  }
+  float code[8];
+  long long basis = 1;
+  for (int j = 0; j < n_levels; ++j) {
+    const int L = levels[j], half = L / 2;
+    const int level = (int)((id / basis) % L);
+    code[j] = (float)(level - half) / (float)half;
+    basis *= L;
+  }
+  for (int c = threadIdx.x; c < latent; c += blockDim.x) {
+    float a = 0.f;
+    for (int j = 0; j < n_levels; ++j) a = fmaf(__ldg(w_po + c * n_levels + j), code[j], a);
+    flat[(size_t)b * latent * token_num + (size_t)c * token_num + n] = a + __ldg(b_po + c);
+  }
+}
+
+// y[b, n] = x[b, :] . w[n, :] + bias[n].  One warp per output column n, 8 utterances per pass, so W is
+// streamed from HBM once per launch (the batch re-reads of its 4-16 KB row hit L1).
+__global__ void small_linear_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                    const float* __restrict__ bias, float* __restrict__ y, int batch, int k, int n) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const float4* wr = reinterpret_cast<const float4*>(w + (size_t)warp * k);
+  const int k4 = k / 4;
+  for (int b0 = 0; b0 < batch; b0 += 8) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int i = lane; i < k4; i += 32) {
+      const float4 wv = __ldg(wr + i);
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (b0 + q < batch) {
+          const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (size_t)(b0 + q) * k) + i);
+          acc[q] = fmaf(wv.x, xv.x, fmaf(wv.y, xv.y, fmaf(wv.z, xv.z, fmaf(wv.w, xv.w, acc[q]))));
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float v = acc[q];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && b0 + q < batch) y[(size_t)(b0 + q) * n + warp] = v + __ldg(bias + warp);
+    }
+  }
+}
+
+// ------------------------------------------------------------------- depthwise conv + LayerNorm
+// x (batch, rows, C) fp32 -> [dwconv k=7 pad 3 over rows] -> LayerNorm over C (biased variance, eps)
+// -> * scale[b] + shift[b] -> fp32 and/or operand planes.
+// (vocos.py:69-75 ConvNeXtBlock head, :105-110 AdaLayerNorm, :328-334 backbone norms.)
+// One CTA stages TR + 6 rows of one utterance in shared memory with coalesced 128-bit loads (halo rows
+// outside the utterance are the conv's zero padding); each warp then owns whole rows: a lane holds
+// C/32 channels as float4s, so the row statistics are two warp-shuffle reductions.
+constexpr int kLnRows = 16;
+
+template <int NV, bool DW>
+__global__ void __launch_bounds__(256)
+dwconv_ln_kernel(const float* __restrict__ x, int rows, const float* __restrict__ dw_w /* [7][C] */,
+                 const float* __restrict__ dw_b, const float* __restrict__ scale, const float* __restrict__ shift,
+                 int ss_stride, float eps, float* __restrict__ out_f32, OpBuf out_op, int tiles_per_utt) {
+  constexpr int C = NV * 128;
+  constexpr int HALO = DW ? 3 : 0;
+  extern __shared__ __align__(16) float s_x[];   // [(kLnRows + 2*HALO)][C]
+  const int b = blockIdx.x / tiles_per_utt;
+  const int r0 = (blockIdx.x % tiles_per_utt) * kLnRows;
+  const float* xb = x + (size_t)b * rows * C;
+
+  constexpr int C4 = C / 4;
+  for (int i = threadIdx.x; i < (kLnRows + 2 * HALO) * C4; i += blockDim.x) {
+    const int rr = i / C4, c4 = i % C4;
+    const int r = r0 + rr - HALO;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r >= 0 && r < rows) v = __ldg(reinterpret_cast<const float4*>(xb + (size_t)r * C) + c4);
+    reinterpret_cast<float4*>(s_x)[i] = v;
+  }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int rr = warp; rr < kLnRows; rr += 8) {
+    const int r = r0 + rr;
+    if (r >= rows) break;
+    float4 y[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int c = v * 128 + lane * 4;
+      if (DW) {
+        float4 a = __ldg(reinterpret_cast<const float4*>(dw_b + c));
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(dw_w + j * C + c));
+          const float4 s = *reinterpret_cast<const float4*>(s_x + (rr + j) * C + c);
+          a.x = fmaf(w.x, s.x, a.x); a.y = fmaf(w.y, s.y, a.y);
+          a.z = fmaf(w.z, s.z, a.z); a.w = fmaf(w.w, s.w, a.w);
+        }
+        y[v] = a;
+      } else {
+        y[v] = *reinterpret_cast<const float4*>(s_x + rr * C + c);
+      }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) sum += (y[v].x + y[v].y) + (y[v].z + y[v].w);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * (1.0f / C);
+    float sq = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      y[v].x -= mean; y[v].y -= mean; y[v].z -= mean; y[v].w -= mean;
+      sq += (y[v].x * y[v].x + y[v].y * y[v].y) + (y[v].z * y[v].z + y[v].w * y[v].w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq * (1.0f / C) + eps);
+    const size_t row_off = ((size_t)b * rows + r) * C;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int c = v * 128 + lane * 4;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(scale + (size_t)b * ss_stride + c));
+      const float4 h = __ldg(reinterpret_cast<const float4*>(shift + (size_t)b * ss_stride + c));
+      float4 o;
+      o.x = fmaf(y[v].x * rstd, g.x, h.x); o.y = fmaf(y[v].y * rstd, g.y, h.y);
+      o.z = fmaf(y[v].z * rstd, g.z, h.z); o.w = fmaf(y[v].w * rstd, g.w, h.w);
+      if (out_f32) *reinterpret_cast<float4*>(out_f32 + row_off + c) = o;
+      if (out_op.hi) store_op4(out_op, row_off + c, o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ waveform head
+// wav[b, l] = tanh(bias + sum_j sum_c w[j, c] * snake(x[b, l + j - 3, c]))     (wave_generator.py:77-81)
+// A warp walks a run of kHeadRun consecutive samples of one utterance: every lane owns C/32 channels,
+// streams the rows straight from HBM with coalesced loads (each element is read and Snake'd once per
+// run, 6 halo rows per run), keeps the 7-row window in registers and reduces the C partial products
+// of every sample with warp shuffles.  Results are written back as coalesced 128 B lines.
+constexpr int kHeadRun = 128;
+
+template <int NCH>
+__global__ void __launch_bounds__(256)
+head_kernel(const float* __restrict__ x, int rows, const float* __restrict__ alpha,
+            const float* __restrict__ inv_alpha, const float* __restrict__ w /* [7][C] */, float bias,
+            float* __restrict__ wav, int runs_per_utt, int total_runs) {
+  constexpr int C = NCH * 32;
+  const int run = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (run >= total_runs) return;
+  const int b = run / runs_per_utt;
+  const int l0 = (run % runs_per_utt) * kHeadRun;
+  const float* xb = x + (size_t)b * rows * C;
+  float a[NCH], ia[NCH], wt[7][NCH];
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    a[k] = __ldg(alpha + lane + 32 * k);
+    ia[k] = __ldg(inv_alpha + lane + 32 * k);
+#pragma unroll
+    for (int j = 0; j < 7; ++j) wt[j][k] = __ldg(w + j * C + lane + 32 * k);
+  }
+  auto load_row = [&](int r, float (&dst)[NCH]) {
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) dst[k] = (r >= 0 && r < rows) ? __ldg(xb + (size_t)r * C + lane + 32 * k) : 0.f;
+  };
+  auto act_row = [&](int r, float (&v)[NCH]) {
+    // zero padding applies to the Snake OUTPUT (the conv pads its input, which is snake(x))
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) v[k] = (r >= 0 && r < rows) ? snake_f(v[k], a[k], ia[k]) : 0.f;
+  };
+  float win[7][NCH];   // win[j] = snake(x[l + j - 3])
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    load_row(l0 + j - 3, win[j + 1]);
+    act_row(l0 + j - 3, win[j + 1]);
+  }
+  float keep = 0.f;
+  const int l_end = min(l0 + kHeadRun, rows);
+  for (int l = l0; l < l_end; l += 4) {
+    float nxt[4][NCH];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) load_row(l + u + 3, nxt[u]);   // 4 rows of loads in flight
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      act_row(l + u + 3, nxt[u]);
+#pragma unroll
+      for (int j = 0; j < 6; ++j)
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) win[j][k] = win[j + 1][k];
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) win[6][k] = nxt[u][k];
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 7; ++j)
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) s = fmaf(wt[j][k], win[j][k], s);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const int ll = l + u;
+      if (lane == (ll & 31)) keep = s;
+      if ((ll & 31) == 31 || ll == l_end - 1) {
+        const int base = ll & ~31;
+        if (base + lane <= ll && base + lane < rows) wav[(size_t)b * rows + base + lane] = tanhf(keep + bias);
+      }
+    }
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------ launchers
+int launch_split(const float* x, OpBuf out, size_t n, cudaStream_t s) {
+  if (n % 4) { set_error("split: element count must be a multiple of 4"); return SPARKCODEC_EINVAL; }
+  const size_t n4 = n / 4;
+  const int grid = (int)std::min<size_t>((n4 + 255) / 256, 148 * 16);
+  split_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(x), out, n4);
+  SC_LAUNCH_CHECK();
+  return 0;
+}
+int launch_merge(const OpBuf& in, float* out, size_t n, cudaStream_t s) {
+  const int grid = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
+  merge_kernel<<<grid, 256, 0, s>>>(in, out, n);
+  SC_LAUNCH_CHECK();
+  return 0;
+}
+int launch_vq_embed(const void* sem, int sem_dtype, int batch, int frames, int, int, int codebook_size,
+                    int codebook_dim, const float* codebook, const float* mat, const float* vec, int c_out,
+                    OpBuf out, int* err_flag, cudaStream_t s) {
+  const size_t n_tok = (size_t)batch * frames, n = n_tok * (c_out / 4);
+  vq_embed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(sem, sem_dtype, n_tok, codebook_size, codebook_dim,
+                                                             codebook, mat, vec, c_out, out, err_flag);
+  SC_LAUNCH_CHECK();
+  return 0;
+}
+int launch_vq_zq(const void* sem, int sem_dtype, int n_tok, int codebook_size, int codebook_dim,
+                 const float* codebook, const float* w, const float* bias, int d_model, float* out, cudaStream_t s) {
+  const size_t n = (size_t)n_tok * d_model;
+  vq_zq_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(sem, sem_dtype, (size_t)n_tok, codebook_size, codebook_dim,
+                                                          codebook, w, bias, d_model, out);
+  SC_LAUNCH_CHECK();
+  return 0;
+}
+int launch_fsq_project(const void* glob, int glob_dtype, int batch, int token_num, int n_levels, const int* levels,
+                       const float* w_po, const float* b_po, int latent, float* flat_out, int* err_flag,
+                       cudaStream_t s) {
+  fsq_project_kernel<<<batch * token_num, 128, 0, s>>>(glob, glob_dtype, token_num, n_levels, levels, w_po, b_po,
+                                                      latent, flat_out, err_flag);
+  SC_LAUNCH_CHECK();
+  return 0;
+}
+int launch_small_linear(const float* x, const float* w, const float* bias, float* y, int batch, int k, int n,
+                        cudaStream_t s) {
+  if (k % 4) { set_error("small_linear: K must be a multiple of 4"); return SPARKCODEC_EINVAL; }
+  small_linear_kernel<<<(n + 7) / 8, 256, 0, s>>>(x, w, bias, y, batch, k, n);
+  SC_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int NV>
+static int launch_dwconv_ln_t(const float* x, int batch, int rows, const float* dw_w, const float* dw_b,
+                              const float* scale, const float* shift, int ss, float eps, float* out_f32,
+                              OpBuf out_op, cudaStream_t s) {
+  const int tiles = (rows + kLnRows - 1) / kLnRows;
+  const bool dw = dw_w != nullptr;
+  const size_t smem = (size_t)(kLnRows + (dw ? 6 : 0)) * NV * 128 * sizeof(float);
+  if (dw) {
+    static bool done = false;
+    if (!done) {
+      SC_CUDA(cudaFuncSetAttribute(dwconv_ln_kernel<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      done = true;
+    }
+    dwconv_ln_kernel<NV, true><<<batch * tiles, 256, smem, s>>>(x, rows, dw_w, dw_b, scale, shift, ss, eps, out_f32,
+                                                               out_op, tiles);
+  } else {
+    static bool done = false;
+    if (!done) {
+      SC_CUDA(cudaFuncSetAttribute(dwconv_ln_kernel<NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      done = true;
+    }
+    dwconv_ln_kernel<NV, false><<<batch * tiles, 256, smem, s>>>(x, rows, dw_w, dw_b, scale, shift, ss, eps, out_f32,
+                                                                out_op, tiles);
+  }
+  SC_LAUNCH_CHECK();
+  return 0;
+}
+int launch_dwconv_ln(const float* x, int batch, int rows, int c, const float* dw_w, const float* dw_b,
+                     const float* scale, const float* shift, int ss_batch_stride, float eps, float* out_f32,
+                     OpBuf out_op, cudaStream_t s) {
+  switch (c) {
+    case 128: return launch_dwconv_ln_t<1>(x, batch, rows, dw_w, dw_b, scale, shift, ss_batch_stride, eps, out_f32, out_op, s);
+    case 256: return launch_dwconv_ln_t<2>(x, batch, rows, dw_w, dw_b, scale, shift, ss_batch_stride, eps, out_f32, out_op, s);
+    case 384: return launch_dwconv_ln_t<3>(x, batch, rows, dw_w, dw_b, scale, shift, ss_batch_stride, eps, out_f32, out_op, s);
+    case 512: return launch_dwconv_ln_t<4>(x, batch, rows, dw_w, dw_b, scale, shift, ss_batch_stride, eps, out_f32, out_op, s);
+    default: set_error("dwconv_ln: unsupported channel count %d (128/256/384/512)", c); return SPARKCODEC_EINVAL;
+  }
+}
+
+int launch_head(const float* x, int batch, int rows, int c, const float* alpha, const float* inv_alpha,
+                const float* w, float bias, float* wav, int, int, cudaStream_t s) {
+  const int runs = (rows + kHeadRun - 1) / kHeadRun, total = batch * runs;
+  const int grid = (total + 7) / 8;
+  switch (c) {
+    case 32: head_kernel<1><<<grid, 256, 0, s>>>(x, rows, alpha, inv_alpha, w, bias, wav, runs, total); break;
+    case 64: head_kernel<2><<<grid, 256, 0, s>>>(x, rows, alpha, inv_alpha, w, bias, wav, runs, total); break;
+    case 96: head_kernel<3><<<grid, 256, 0, s>>>(x, rows, alpha, inv_alpha, w, bias, wav, runs, total); break;
+    case 128: head_kernel<4><<<grid, 256, 0, s>>>(x, rows, alpha, inv_alpha, w, bias, wav, runs, total); break;
+    default: set_error("head: unsupported channel count %d (32/64/96/128)", c); return SPARKCODEC_EINVAL;
+  }
+  SC_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace sparkcodec

@@ -1,0 +1,432 @@
+// tcgen05 implicit-GEMM convolution for sm_100a.
+//
+//   D[b, l, n] = sum_{tap j} sum_{c} A[b, l + shift_j, c] * W[n, j*C_in + c]        (+ fused epilogue)
+//
+// covers every dense contraction of the BiCodec detokenize path: k=7 (dilated) Conv1d, the 1x1 convs
+// / Linear layers (one tap) and the ConvTranspose1d up-samplers (stride polyphase branches selected
+// per N tile).  Activations are channels-last bf16 planes, so a tap shift is a row offset of the TMA
+// box and TMA out-of-bounds zero fill IS the convolution's zero padding (3-D map C x L x batch:
+// rows never bleed across utterances).
+//
+// Structure (persistent, warp specialised, one CTA per SM):
+//   warp 0 / lane 0 : TMA producer  -> smem ring of {A_hi, A_lo, W_hi, W_lo} stages (mbarrier full/empty)
+//   warp 1 / lane 0 : tcgen05.mma issuer, accumulators in TMEM (2 stages of BLOCK_N columns)
+//   warps 2..5      : epilogue: tcgen05.ld -> bias / residual / Snake / GELU -> fp32 + bf16 hi/lo stores,
+//                     overlapped with the next tile's MMAs through the second TMEM stage.
+// Precision modes: NTERMS == 1 : A_hi*W_hi (bf16);  NTERMS == 3 : A_hi*W_hi + A_lo*W_hi + A_hi*W_lo
+// (error-compensated split, ~2^-16 relative per product, fp32 accumulate) = the "fp32" mode.
+#include "gemm_params.cuh"
+
+namespace sparkcodec {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trapped kernel, not as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {   // ~2 s
+      printf("sparkcodec: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
+             threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(NCOLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, issued by ONE thread for the CTA.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives when all tcgen05 ops previously issued by this thread have completed.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile in smem, rows of BK bf16 (= the TMA swizzle span), 8-row swizzle atoms stacked
+// along M/N: SBO = 8 * BK * 2 bytes, LBO unused.  Fields per cute/arch/mma_sm100_desc.hpp.
+template <int BK>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  constexpr uint64_t layout = (BK == 64) ? 2ull /*SWIZZLE_128B*/ : 4ull /*SWIZZLE_64B*/;
+  constexpr uint64_t sbo = (8ull * BK * 2) >> 4;
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = BLOCK_N.
+template <int BLOCK_N>
+__device__ __forceinline__ constexpr uint32_t make_idesc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+}
+
+template <int BLOCK_N, int BK, int NTERMS>
+struct TileCfg {
+  static constexpr int kPlanes = (NTERMS == 3) ? 2 : 1;
+  static constexpr int kABytes = kBlockM * BK * 2;
+  static constexpr int kWBytes = BLOCK_N * BK * 2;
+  static constexpr int kStageBytes = kPlanes * (kABytes + kWBytes);
+  static constexpr int kBudget = 200 * 1024;
+  static constexpr int kStagesRaw = kBudget / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
+                                   : (2 * BLOCK_N <= 256) ? 256 : 512;
+  static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024 /* manual 1024 B alignment */;
+  static_assert(kStages >= 2, "need at least a double-buffered smem ring");
+  static_assert(2 * BLOCK_N <= 512, "two accumulator stages must fit TMEM");
+  static_assert(kABytes % 1024 == 0 && kWBytes % 1024 == 0, "swizzled tiles must stay 1024 B aligned");
+};
+
+constexpr int kNumThreads = 192;   // warp 0 producer, warp 1 MMA, warps 2..5 epilogue
+
+template <int BLOCK_N, int BK, int NTERMS>
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                    const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+                    const ConvGemmParams p) {
+  using Cfg = TileCfg<BLOCK_N, BK, NTERMS>;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + S * Cfg::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * S + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 4);
+  uint32_t* tmem_slot_ptr =
+      reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int k_chunks = p.c_in / BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_a_hi);
+    prefetch_tmap(&tm_w_hi);
+    if (NTERMS == 3) {
+      prefetch_tmap(&tm_a_lo);
+      prefetch_tmap(&tm_w_lo);
+    }
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;
+        const int b = m_tile / p.m_tiles_per_utt;
+        const int l0 = (m_tile % p.m_tiles_per_utt) * kBlockM;
+        const int n0 = n_tile * BLOCK_N;
+        const int ph = n0 / p.taps.cols_per_phase;
+        const int ntaps = p.taps.ntaps[ph];
+        for (int j = 0; j < ntaps; ++j) {
+          const int row = l0 + p.taps.shift[ph][j];
+          for (int kc = 0; kc < k_chunks; ++kc) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+            const uint32_t sw = sa + Cfg::kPlanes * Cfg::kABytes;
+            mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+            tma_load_3d(sa, &tm_a_hi, full_bar(stage), kc * BK, row, b);
+            tma_load_2d(sw, &tm_w_hi, full_bar(stage), j * p.c_in + kc * BK, n0);
+            if (NTERMS == 3) {
+              tma_load_3d(sa + Cfg::kABytes, &tm_a_lo, full_bar(stage), kc * BK, row, b);
+              tma_load_2d(sw + Cfg::kWBytes, &tm_w_lo, full_bar(stage), j * p.c_in + kc * BK, n0);
+            }
+            if (++stage == S) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc<BLOCK_N>();
+      uint32_t stage = 0, phase = 0, iter = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+        const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
+        const int ph = n0 / p.taps.cols_per_phase;
+        const int n_k = p.taps.ntaps[ph] * k_chunks;
+        const uint32_t acc = iter & 1u, acc_phase = (iter >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);   // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int ki = 0; ki < n_k; ++ki) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          const uint32_t sw = sa + Cfg::kPlanes * Cfg::kABytes;
+          const uint64_t a_hi = make_smem_desc<BK>(sa), w_hi = make_smem_desc<BK>(sw);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)   // +32 B (=2 in >>4 units) per 16-element K step inside the swizzle row
+            umma_bf16(d_tmem, a_hi + 2 * k, w_hi + 2 * k, idesc, (ki | k) != 0);
+          if (NTERMS == 3) {
+            const uint64_t a_lo = make_smem_desc<BK>(sa + Cfg::kABytes);
+            const uint64_t w_lo = make_smem_desc<BK>(sw + Cfg::kWBytes);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, a_lo + 2 * k, w_hi + 2 * k, idesc, 1u);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, a_hi + 2 * k, w_lo + 2 * k, idesc, 1u);
+          }
+          umma_commit(empty_bar(stage));                    // smem slot free once these MMAs retire
+          if (ki == n_k - 1) umma_commit(tfull_bar(acc));   // accumulator complete -> epilogue
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ================================ epilogue warps ================================
+    const int group = warp & 3;                 // TMEM lane quarter this warp may read
+    const int row_in_tile = group * 32 + lane;
+    uint32_t iter = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+      const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;
+      const int b = m_tile / p.m_tiles_per_utt;
+      const int l = (m_tile % p.m_tiles_per_utt) * kBlockM + row_in_tile;
+      const int n0 = n_tile * BLOCK_N;
+      const bool valid = l < p.L;
+      const size_t row_off = ((size_t)b * p.L + (valid ? l : 0)) * (size_t)p.n_total;
+      const uint32_t acc = iter & 1u, acc_phase = (iter >> 1) & 1u;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(group * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t r[32];
+        tmem_ld_x32(t_row + c, r);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[q * 8 + i]);
+            epilogue_store8(p, v, b, row_off, n0 + c + q * 8);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                        CUtensorMapFloatOOBfill);
+PFN_tmapEncodeTiled g_encode = nullptr;
+
+int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+               const uint32_t* box, int bk, bool weights) {
+  cuuint64_t gdim[3], gstr[2];
+  cuuint32_t bx[3], es[3] = {1, 1, 1};
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; }
+  for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr,
+                        bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                        weights ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu box %u,%u)", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    return SPARKCODEC_ECUDA;
+  }
+  return 0;
+}
+
+template <int BLOCK_N, int BK, int NTERMS>
+int launch_inst(const GemmWeights& w, const OpBuf& a, int batch, int L, const ConvGemmParams& p, int num_sms,
+                cudaStream_t stream) {
+  using Cfg = TileCfg<BLOCK_N, BK, NTERMS>;
+  CUtensorMap ta_hi, ta_lo;
+  const uint64_t dims[3] = {(uint64_t)w.c_in, (uint64_t)L, (uint64_t)batch};
+  const uint64_t strides[2] = {(uint64_t)w.c_in * 2, (uint64_t)L * w.c_in * 2};
+  const uint32_t box[3] = {(uint32_t)BK, (uint32_t)kBlockM, 1u};
+  SC_TRY(encode_map(&ta_hi, a.hi, 3, dims, strides, box, BK, false));
+  if (NTERMS == 3) SC_TRY(encode_map(&ta_lo, a.lo, 3, dims, strides, box, BK, false));
+  else ta_lo = ta_hi;
+  auto kern = conv_gemm_tc_kernel<BLOCK_N, BK, NTERMS>;
+  static bool attr_done = false;   // per instantiation
+  if (!attr_done) {
+    SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  kern<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta_hi, ta_lo, w.tmap_hi, NTERMS == 3 ? w.tmap_lo : w.tmap_hi, p);
+  SC_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+int tma_init() {
+  if (g_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  SC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return SPARKCODEC_ECUDA;
+  }
+  g_encode = reinterpret_cast<PFN_tmapEncodeTiled>(fn);
+  return 0;
+}
+
+// Tile shape per layer: BLOCK_N must divide the per-phase width so an N tile never straddles two
+// polyphase branches; BK = 64 (128 B swizzle rows) unless C_in is only a multiple of 32.
+int choose_tile(int c_in, int cols_per_phase, int* block_n, int* bk) {
+  if (c_in % 64 == 0) *bk = 64;
+  else if (c_in % 32 == 0) *bk = 32;
+  else { set_error("C_in=%d is not a multiple of 32", c_in); return SPARKCODEC_EINVAL; }
+  const int cand[] = {256, 192, 128, 96, 64};
+  for (int c : cand)
+    if (cols_per_phase % c == 0) { *block_n = c; return 0; }
+  set_error("no tile width divides C_out=%d (need a multiple of 64)", cols_per_phase);
+  return SPARKCODEC_EINVAL;
+}
+
+int make_weight_tmaps(GemmWeights& w) {
+  SC_TRY(tma_init());
+  SC_TRY(choose_tile(w.c_in, w.taps.cols_per_phase, &w.block_n, &w.bk));
+  const uint64_t dims[2] = {(uint64_t)w.kt * w.c_in, (uint64_t)w.n_total};
+  const uint64_t strides[1] = {(uint64_t)w.kt * w.c_in * 2};
+  const uint32_t box[2] = {(uint32_t)w.bk, (uint32_t)w.block_n};
+  SC_TRY(encode_map(&w.tmap_hi, w.w_hi, 2, dims, strides, box, w.bk, true));
+  SC_TRY(encode_map(&w.tmap_lo, w.w_lo, 2, dims, strides, box, w.bk, true));
+  return 0;
+}
+
+int fill_params(const GemmWeights& w, int batch, int L, const Epilogue& ep, int precision, ConvGemmParams* p) {
+  if ((ep.out_op.hi != nullptr) && precision == SPARKCODEC_PREC_FP32 && ep.out_op.lo == nullptr) {
+    set_error("fp32 mode needs both operand planes");
+    return SPARKCODEC_EINVAL;
+  }
+  p->batch = batch; p->L = L; p->n_total = w.n_total; p->c_in = w.c_in;
+  p->taps = w.taps;
+  p->m_tiles_per_utt = (L + kBlockM - 1) / kBlockM;
+  p->num_m_tiles = batch * p->m_tiles_per_utt;
+  p->num_n_tiles = w.n_total / w.block_n;
+  p->bias = w.bias; p->rowbias = ep.rowbias; p->residual = ep.residual;
+  p->alpha = ep.alpha; p->inv_alpha = ep.inv_alpha; p->act = ep.act;
+  p->out_f32 = ep.out_f32; p->out_hi = ep.out_op.hi;
+  p->out_lo = (precision == SPARKCODEC_PREC_FP32) ? ep.out_op.lo : nullptr;
+  return 0;
+}
+
+int launch_conv_gemm_tc(const GemmWeights& w, const OpBuf& a, int batch, int L, const Epilogue& ep, int precision,
+                        int num_sms, cudaStream_t stream) {
+  ConvGemmParams p;
+  SC_TRY(fill_params(w, batch, L, ep, precision, &p));
+  const bool f32 = precision == SPARKCODEC_PREC_FP32;
+#define SC_INST(BN, BKK)                                                                        \
+  if (w.block_n == BN && w.bk == BKK)                                                           \
+    return f32 ? launch_inst<BN, BKK, 3>(w, a, batch, L, p, num_sms, stream)                    \
+               : launch_inst<BN, BKK, 1>(w, a, batch, L, p, num_sms, stream);
+  SC_INST(256, 64) SC_INST(192, 64) SC_INST(128, 64) SC_INST(96, 64) SC_INST(64, 64)
+  SC_INST(256, 32) SC_INST(192, 32) SC_INST(128, 32) SC_INST(96, 32) SC_INST(64, 32)
+#undef SC_INST
+  set_error("no tcgen05 instantiation for block_n=%d bk=%d", w.block_n, w.bk);
+  return SPARKCODEC_EINVAL;
+}
+
+}  // namespace sparkcodec

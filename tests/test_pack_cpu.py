@@ -1,0 +1,94 @@
+"""CPU (no GPU): the C-ABI library loads, exports every declared symbol, and its host-side weight
+re-layout (tap tables + K-major bf16 hi/lo planes) reproduces torch's Conv1d / ConvTranspose1d."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from spark_tts_b200 import _lib, ops
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "sparkcodec.h")).read()
+    declared = set(re.findall(r"SPARKCODEC_API\s+(?:int|const char\*)\s+(sparkcodec_\w+)\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.sparkcodec_abi_version() == 1
+
+
+def _bf16_bits_to_f32(a: np.ndarray) -> np.ndarray:
+    return (a.astype(np.uint32) << 16).view(np.float32)
+
+
+def _emulate(x: torch.Tensor, pk: dict, c_out: int) -> torch.Tensor:
+    """x (B, L, C_in) -> (B, L*n_phase, C_out) using only the packed weights + tap table."""
+    w = torch.from_numpy(_bf16_bits_to_f32(pk["w_hi"]) + _bf16_bits_to_f32(pk["w_lo"])).double()
+    B, L, c_in = x.shape
+    out = torch.zeros(B, L, pk["n_total"], dtype=torch.float64)
+    xd = x.double()
+    for r in range(pk["n_phase"]):
+        rows = slice(r * c_out, (r + 1) * c_out)
+        for m in range(int(pk["ntaps"][r])):
+            sh = int(pk["shifts"][r, m])
+            xs = torch.zeros_like(xd)
+            lo, hi = max(0, -sh), min(L, L - sh)
+            if hi > lo:
+                xs[:, lo:hi] = xd[:, lo + sh:hi + sh]
+            out[:, :, rows] += xs @ w[rows, m * c_in:(m + 1) * c_in].T
+    return out.reshape(B, L * pk["n_phase"], c_out)
+
+
+@pytest.mark.parametrize("k,dil", [(7, 1), (7, 3), (7, 9), (1, 1)])
+def test_pack_conv1d_matches_torch(k, dil):
+    g = torch.Generator().manual_seed(k * 10 + dil)
+    w = torch.randn(24, 16, k, generator=g)
+    x = torch.randn(2, 40, 16, generator=g)
+    pk = ops.pack_conv(w, transposed=False, param=dil)
+    assert pk["n_phase"] == 1 and pk["kt"] == k and pk["n_total"] == 24
+    ref = F.conv1d(x.transpose(1, 2).double(), w.double(), dilation=dil, padding=(k - 1) // 2 * dil).transpose(1, 2)
+    got = _emulate(x, pk, 24)
+    # hi+lo planes keep ~16 mantissa bits of every weight
+    assert (got - ref).abs().max().item() < 2e-4 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("k,s", [(16, 8), (11, 5), (8, 4), (4, 2)])
+def test_pack_conv_transpose1d_matches_torch(k, s):
+    g = torch.Generator().manual_seed(k * 10 + s)
+    w = torch.randn(16, 8, k, generator=g)           # (C_in, C_out, k)
+    x = torch.randn(2, 23, 16, generator=g)
+    pk = ops.pack_conv(w, transposed=True, param=s)
+    assert pk["n_phase"] == s and pk["n_total"] == s * 8
+    ref = F.conv_transpose1d(x.transpose(1, 2).double(), w.double(), stride=s, padding=(k - s) // 2).transpose(1, 2)
+    got = _emulate(x, pk, 8)
+    assert got.shape == ref.shape
+    assert (got - ref).abs().max().item() < 2e-4 * ref.abs().max().item()
+
+
+def test_split_planes_are_error_compensated():
+    w = torch.randn(32, 32, 1, generator=torch.Generator().manual_seed(3))
+    pk = ops.pack_conv(w, transposed=False, param=1)
+    hi, lo = _bf16_bits_to_f32(pk["w_hi"]), _bf16_bits_to_f32(pk["w_lo"])
+    ref = w[:, :, 0].numpy()
+    assert np.abs(hi - ref).max() > 1e-4                      # bf16 alone is coarse ...
+    assert np.abs(hi + lo - ref).max() <= np.abs(ref).max() * 2.0 ** -16   # ... hi+lo is not
+
+
+def test_product_path_has_no_cpu_fallback(cfg, state_dict):
+    from spark_tts_b200 import BiCodec
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    m = BiCodec.from_state_dict(cfg, state_dict)
+    sem = torch.zeros(1, 4, dtype=torch.int64)
+    glob = torch.zeros(1, 1, cfg.token_num, dtype=torch.int32)
+    with pytest.raises(RuntimeError):
+        m.detokenize(sem, glob)
+    with pytest.raises(RuntimeError):
+        m.to("cpu")
