@@ -164,6 +164,13 @@ SPARKCODEC_API int sparkcodec_pack_conv(int kind, const float* w_host, const int
                          uint16_t* w_hi, uint16_t* w_lo, size_t w_capacity, int32_t* shifts,
                          int32_t* ntaps, int32_t* kt, int32_t* n_phase, int32_t* n_total);
 
+/* Profile mode: records a CUDA-event pair around every kernel launch of subsequent calls (adds launch
+ * gaps; never on while a throughput number is taken).  sparkcodec_profile_read synchronises and writes
+ * one line per launch: "name\tms\talgorithmic_flops\talgorithmic_bytes\n" (buf may be NULL to query
+ * the size).  Enabling/disabling clears the records. */
+SPARKCODEC_API int sparkcodec_profile(sparkcodec_handle* h, int enable);
+SPARKCODEC_API int sparkcodec_profile_read(sparkcodec_handle* h, char* buf, size_t cap, size_t* needed);
+
 /* Number of this library's kernel launches issued since the handle was created (bench.py's
  * `gpu_launches`). */
 SPARKCODEC_API int sparkcodec_launch_count(sparkcodec_handle* h, int64_t* count);

@@ -263,3 +263,19 @@ class BiCodec:
         n = C.c_int64()
         _lib.check(_lib.load().sparkcodec_launch_count(self._handle, C.byref(n)))
         return n.value
+
+    def profile(self, enable: bool) -> None:
+        """Per-launch CUDA-event timing for the roofline pass of bench.py (never on during a timed run)."""
+        _lib.check(_lib.load().sparkcodec_profile(self._handle, 1 if enable else 0))
+
+    def profile_read(self):
+        """-> list of dict(name, ms, flops, bytes), one per kernel launch since profile(True)."""
+        need = C.c_size_t()
+        _lib.check(_lib.load().sparkcodec_profile_read(self._handle, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        _lib.check(_lib.load().sparkcodec_profile_read(self._handle, buf, need.value, C.byref(need)))
+        rows = []
+        for line in buf.value.decode().splitlines():
+            name, ms, fl, by = line.split("\t")
+            rows.append(dict(name=name, ms=float(ms), flops=float(fl), bytes=float(by)))
+        return rows

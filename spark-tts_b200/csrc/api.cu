@@ -71,6 +71,9 @@ struct sparkcodec_handle {
   std::map<std::string, HostTensor> host;
   std::vector<void*> allocs;
   int* err_flag = nullptr;   // device int[4]
+  bool profile = false;      // record a CUDA-event pair around every launch (bench.py roofline pass)
+  struct ProfRec { std::string name; double flops, bytes; cudaEvent_t e0, e1; };
+  std::vector<ProfRec> prof;
 
   // token stages
   float *codebook = nullptr, *vq_mat = nullptr, *vq_vec = nullptr, *vq_w = nullptr, *vq_b = nullptr;
@@ -447,9 +450,43 @@ struct Pass {
   cudaStream_t st;
   TapReq* tap;
 
+  // ---- optional per-launch CUDA-event timing (profile mode only) ----
+  int prof_begin(const std::string& name, double flops, double bytes) {
+    if (!h->profile) return 0;
+    sparkcodec_handle::ProfRec r{name, flops, bytes, nullptr, nullptr};
+    SC_CUDA(cudaEventCreate(&r.e0));
+    SC_CUDA(cudaEventCreate(&r.e1));
+    SC_CUDA(cudaEventRecord(r.e0, st));
+    h->prof.push_back(r);
+    return 0;
+  }
+  int prof_end() {
+    if (!h->profile) return 0;
+    SC_CUDA(cudaEventRecord(h->prof.back().e1, st));
+    return 0;
+  }
   int gemm(const GemmWeights& w, const OpBuf& a, int L, const Epilogue& ep) {
-    if (h->impl == SPARKCODEC_IMPL_SIMT) return launch_conv_gemm_simt(w, a, B, L, ep, prec, st);
-    return launch_conv_gemm_tc(w, a, B, L, ep, prec, h->num_sms, st);
+    if (h->profile) {
+      double macs = 0;
+      int tmax = 0;
+      for (int r = 0; r < w.taps.n_phase; ++r) {
+        macs += (double)w.taps.ntaps[r] * w.c_in * w.taps.cols_per_phase;
+        tmax = std::max(tmax, w.taps.ntaps[r]);
+      }
+      const double planes = prec == SPARKCODEC_PREC_FP32 ? 4.0 : 2.0;   // bytes per operand element
+      double bytes = (double)B * L * w.c_in * planes + (double)w.n_total * w.kt * w.c_in * planes;
+      if (ep.residual) bytes += (double)B * L * w.n_total * 4;
+      if (ep.out_f32) bytes += (double)B * L * w.n_total * 4;
+      if (ep.out_op.hi) bytes += (double)B * L * w.n_total * planes;
+      char nm[160];
+      snprintf(nm, sizeof(nm), "conv_gemm_tc cin=%d n=%d phases=%d taps=%d L=%d bn=%d bk=%d act=%d", w.c_in, w.n_total,
+               w.taps.n_phase, tmax, L, w.block_n, w.bk, ep.act);
+      SC_TRY(prof_begin(nm, 2.0 * B * L * macs, bytes));
+    }
+    int rc = h->impl == SPARKCODEC_IMPL_SIMT ? launch_conv_gemm_simt(w, a, B, L, ep, prec, st)
+                                             : launch_conv_gemm_tc(w, a, B, L, ep, prec, h->num_sms, st);
+    if (rc) return rc;
+    return prof_end();
   }
   bool want(const char* name) const { return tap && tap->name && strcmp(tap->name, name) == 0; }
   int tap_check(size_t rows, size_t ch) {
@@ -521,13 +558,17 @@ static int run_pass(Pass& P, const void* sem, int sem_dt, const void* glob, int 
       SC_TRY(P.gemm(bb.embed, pa, T, e));                                           // embed conv k7 -> py
       const float* sc = bb.ada ? W.ada : bb.norm_w;
       const float* sh = bb.ada ? W.ada + C : bb.norm_b;
+      SC_TRY(P.prof_begin("ln", 0, (double)B * T * C * 8));
       SC_TRY(launch_dwconv_ln(W.py, B, T, C, nullptr, nullptr, sc, sh, bb.ada ? ada_n : 0, 1e-6f, W.px, OpBuf(), st));
+      SC_TRY(P.prof_end());
       SC_TRY(P.tap_f32((name + ".norm").c_str(), W.px, T, C));
       for (size_t i = 0; i < bb.blocks.size(); ++i) {
         ConvNeXt& blk = bb.blocks[i];
         sc = bb.ada ? W.ada + (size_t)(i + 1) * 2 * C : blk.ln_w;
         sh = bb.ada ? W.ada + (size_t)(i + 1) * 2 * C + C : blk.ln_b;
+        SC_TRY(P.prof_begin("dwconv_ln", 0, (double)B * T * C * (4 + (prec == SPARKCODEC_PREC_FP32 ? 4 : 2))));
         SC_TRY(launch_dwconv_ln(W.px, B, T, C, blk.dw_w, blk.dw_b, sc, sh, bb.ada ? ada_n : 0, 1e-6f, nullptr, pa, st));
+        SC_TRY(P.prof_end());
         Epilogue e1;
         e1.act = ACT_GELU;
         e1.out_op = ph;
@@ -570,6 +611,7 @@ static int run_pass(Pass& P, const void* sem, int sem_dt, const void* glob, int 
     UpBlock& ub = h->ups[i];
     const std::string name = "decoder.model." + std::to_string(i + 1) + ".block";
     {
+      if (cur.hi == op1[pp].hi) pp ^= 1;   // the transposed conv must not write over its own input
       Epilogue e;
       e.out_f32 = W.x;
       e.act = ACT_SNAKE; e.alpha = ub.s_after.alpha; e.inv_alpha = ub.s_after.inv;
@@ -598,7 +640,9 @@ static int run_pass(Pass& P, const void* sem, int sem_dt, const void* glob, int 
     }
     cur = op1[pp];
   }
+  SC_TRY(P.prof_begin("head", 0, (double)B * L * (h->head_c * 4 + 4)));
   SC_TRY(launch_head(W.x, B, L, h->head_c, h->s_head.alpha, h->s_head.inv, h->head_w, h->head_bias, wav_out, 0, L, st));
+  SC_TRY(P.prof_end());
   return 0;
 }
 
@@ -810,6 +854,31 @@ int sparkcodec_detokenize_tap(sparkcodec_handle* h, const void* semantic, int se
   t.name = tap; t.out = tap_out; t.cap = tap_capacity; t.shape = tap_shape;
   return run_all(h, semantic, sem_dtype, global_tokens, glob_dtype, batch, frames, precision, workspace,
                  workspace_bytes, nullptr, nullptr, wav_out, &t, static_cast<cudaStream_t>(stream));
+}
+
+int sparkcodec_profile(sparkcodec_handle* h, int enable) {
+  if (!h) { set_error("null handle"); return SPARKCODEC_EINVAL; }
+  for (auto& r : h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  h->prof.clear();
+  h->profile = enable != 0;
+  return 0;
+}
+
+int sparkcodec_profile_read(sparkcodec_handle* h, char* buf, size_t cap, size_t* needed) {
+  if (!h || !needed) { set_error("null argument"); return SPARKCODEC_EINVAL; }
+  SC_CUDA(cudaSetDevice(h->device));
+  std::string out;
+  for (auto& r : h->prof) {
+    SC_CUDA(cudaEventSynchronize(r.e1));
+    float ms = 0.f;
+    SC_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    char line[320];
+    snprintf(line, sizeof(line), "%s\t%.6f\t%.6e\t%.6e\n", r.name.c_str(), ms, r.flops, r.bytes);
+    out += line;
+  }
+  *needed = out.size() + 1;
+  if (buf && cap >= out.size() + 1) memcpy(buf, out.c_str(), out.size() + 1);
+  return 0;
 }
 
 int sparkcodec_launch_count(sparkcodec_handle* h, int64_t* count) {
