@@ -68,8 +68,9 @@ struct GemmWeights {
   __nv_bfloat16* w_hi = nullptr;
   __nv_bfloat16* w_lo = nullptr;
   float* bias = nullptr;                   // (n_total) (phase-replicated for transposed convs)
-  int block_n = 0, bk = 0;                 // tile shape chosen for the tcgen05 kernel
-  CUtensorMap tmap_hi, tmap_lo;            // (K, N) boxes (bk, block_n)
+  int block_n = 0;                         // N tile of the tcgen05 kernel (divides cols_per_phase)
+  CUtensorMap tmap_hi[2], tmap_lo[2];      // (K, N) boxes (bk, block_n) for bk = 64 ([0]) and 32 ([1])
+  bool has_bk64 = false;                   // c_in % 64 == 0
 };
 
 enum Act { ACT_NONE = 0, ACT_GELU = 1, ACT_SNAKE = 2 };

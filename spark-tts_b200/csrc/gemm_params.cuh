@@ -24,7 +24,8 @@ struct ConvGemmParams {
 };
 
 int fill_params(const GemmWeights& w, int batch, int L, const Epilogue& ep, int precision, ConvGemmParams* p);
-int choose_tile(int c_in, int cols_per_phase, int* block_n, int* bk);
+int choose_block_n(int cols_per_phase, int* block_n);
+int choose_bk(int c_in, int block_n, int precision);
 
 // snake(x) = x + sin(alpha x)^2 / (alpha + 1e-9)   (reference sparktts/modules/blocks/layers.py:32-39)
 // sin: two-constant Cody-Waite reduction to [-pi, pi], then the SFU sine (abs err ~2^-21 there).
@@ -45,57 +46,66 @@ __device__ __forceinline__ float gelu_erf(float v) {   // nn.GELU() default (voc
   return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
 }
 
-// Finishes 8 consecutive output columns [n, n+8) of one output row: bias (+rowbias)(+residual),
-// optional fp32 store, activation, optional bf16 hi/lo operand store.  acc[] holds the accumulators.
-__device__ __forceinline__ void epilogue_store8(const ConvGemmParams& p, float (&acc)[8], int b,
-                                                size_t row_off /* (b*L + l) * n_total */, int n) {
-  const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-  const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-  acc[0] += b0.x; acc[1] += b0.y; acc[2] += b0.z; acc[3] += b0.w;
-  acc[4] += b1.x; acc[5] += b1.y; acc[6] += b1.z; acc[7] += b1.w;
+// Finishes 4 consecutive output columns [n, n+4) of one output row: bias (+rowbias)(+residual),
+// optional fp32 store, activation, optional bf16 hi/lo operand store.  bias/alpha/inv are the per-column
+// parameters of those 4 columns (loaded once by the caller when it keeps the same columns across rows).
+__device__ __forceinline__ void epilogue_store4(const ConvGemmParams& p, float4 acc, int b, size_t row_off, int n,
+                                                const float4& bias, const float4& alpha, const float4& inv,
+                                                bool add_residual = true) {
+  acc.x += bias.x; acc.y += bias.y; acc.z += bias.z; acc.w += bias.w;
   if (p.rowbias) {
-    const float4 r0 = __ldg(reinterpret_cast<const float4*>(p.rowbias + (size_t)b * p.n_total + n));
-    const float4 r1 = __ldg(reinterpret_cast<const float4*>(p.rowbias + (size_t)b * p.n_total + n + 4));
-    acc[0] += r0.x; acc[1] += r0.y; acc[2] += r0.z; acc[3] += r0.w;
-    acc[4] += r1.x; acc[5] += r1.y; acc[6] += r1.z; acc[7] += r1.w;
+    const float4 r = __ldg(reinterpret_cast<const float4*>(p.rowbias + (size_t)b * p.n_total + n));
+    acc.x += r.x; acc.y += r.y; acc.z += r.z; acc.w += r.w;
   }
-  if (p.residual) {
-    const float4 r0 = *reinterpret_cast<const float4*>(p.residual + row_off + n);
-    const float4 r1 = *reinterpret_cast<const float4*>(p.residual + row_off + n + 4);
-    acc[0] += r0.x; acc[1] += r0.y; acc[2] += r0.z; acc[3] += r0.w;
-    acc[4] += r1.x; acc[5] += r1.y; acc[6] += r1.z; acc[7] += r1.w;
+  if (add_residual && p.residual) {
+    const float4 r = *reinterpret_cast<const float4*>(p.residual + row_off + n);
+    acc.x += r.x; acc.y += r.y; acc.z += r.z; acc.w += r.w;
   }
-  if (p.out_f32) {
-    *reinterpret_cast<float4*>(p.out_f32 + row_off + n) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    *reinterpret_cast<float4*>(p.out_f32 + row_off + n + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-  }
+  if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + row_off + n) = acc;
   if (p.out_hi) {
     if (p.act == ACT_SNAKE) {
-      const float4 a0 = __ldg(reinterpret_cast<const float4*>(p.alpha + n));
-      const float4 a1 = __ldg(reinterpret_cast<const float4*>(p.alpha + n + 4));
-      const float4 i0 = __ldg(reinterpret_cast<const float4*>(p.inv_alpha + n));
-      const float4 i1 = __ldg(reinterpret_cast<const float4*>(p.inv_alpha + n + 4));
-      acc[0] = snake_f(acc[0], a0.x, i0.x); acc[1] = snake_f(acc[1], a0.y, i0.y);
-      acc[2] = snake_f(acc[2], a0.z, i0.z); acc[3] = snake_f(acc[3], a0.w, i0.w);
-      acc[4] = snake_f(acc[4], a1.x, i1.x); acc[5] = snake_f(acc[5], a1.y, i1.y);
-      acc[6] = snake_f(acc[6], a1.z, i1.z); acc[7] = snake_f(acc[7], a1.w, i1.w);
+      acc.x = snake_f(acc.x, alpha.x, inv.x); acc.y = snake_f(acc.y, alpha.y, inv.y);
+      acc.z = snake_f(acc.z, alpha.z, inv.z); acc.w = snake_f(acc.w, alpha.w, inv.w);
     } else if (p.act == ACT_GELU) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = gelu_erf(acc[i]);
+      acc.x = gelu_erf(acc.x); acc.y = gelu_erf(acc.y); acc.z = gelu_erf(acc.z); acc.w = gelu_erf(acc.w);
     }
-    __nv_bfloat162 h[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(acc[2 * i], acc[2 * i + 1]);
-    *reinterpret_cast<uint4*>(p.out_hi + row_off + n) = *reinterpret_cast<uint4*>(h);
+    const __nv_bfloat162 h0 = __floats2bfloat162_rn(acc.x, acc.y), h1 = __floats2bfloat162_rn(acc.z, acc.w);
+    uint2 hp;
+    hp.x = *reinterpret_cast<const uint32_t*>(&h0);
+    hp.y = *reinterpret_cast<const uint32_t*>(&h1);
+    *reinterpret_cast<uint2*>(p.out_hi + row_off + n) = hp;
     if (p.out_lo) {
-      __nv_bfloat162 l[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float2 hf = __bfloat1622float2(h[i]);
-        l[i] = __floats2bfloat162_rn(acc[2 * i] - hf.x, acc[2 * i + 1] - hf.y);
-      }
-      *reinterpret_cast<uint4*>(p.out_lo + row_off + n) = *reinterpret_cast<uint4*>(l);
+      const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+      const __nv_bfloat162 l0 = __floats2bfloat162_rn(acc.x - f0.x, acc.y - f0.y);
+      const __nv_bfloat162 l1 = __floats2bfloat162_rn(acc.z - f1.x, acc.w - f1.y);
+      uint2 lp;
+      lp.x = *reinterpret_cast<const uint32_t*>(&l0);
+      lp.y = *reinterpret_cast<const uint32_t*>(&l1);
+      *reinterpret_cast<uint2*>(p.out_lo + row_off + n) = lp;
     }
+  }
+}
+
+__device__ __forceinline__ void load_col_params4(const ConvGemmParams& p, int n, float4& bias, float4& alpha,
+                                                 float4& inv) {
+  bias = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+  alpha = make_float4(0.f, 0.f, 0.f, 0.f);
+  inv = alpha;
+  if (p.out_hi && p.act == ACT_SNAKE) {
+    alpha = __ldg(reinterpret_cast<const float4*>(p.alpha + n));
+    inv = __ldg(reinterpret_cast<const float4*>(p.inv_alpha + n));
+  }
+}
+
+// 8-column convenience wrapper (CUDA-core verification kernel).
+__device__ __forceinline__ void epilogue_store8(const ConvGemmParams& p, float (&acc)[8], int b,
+                                                size_t row_off /* (b*L + l) * n_total */, int n) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    float4 bias, alpha, inv;
+    load_col_params4(p, n + 4 * h, bias, alpha, inv);
+    epilogue_store4(p, make_float4(acc[4 * h], acc[4 * h + 1], acc[4 * h + 2], acc[4 * h + 3]), b, row_off,
+                    n + 4 * h, bias, alpha, inv);
   }
 }
 

@@ -138,13 +138,16 @@ struct TileCfg {
   static constexpr int kABytes = kBlockM * BK * 2;
   static constexpr int kWBytes = BLOCK_N * BK * 2;
   static constexpr int kStageBytes = kPlanes * (kABytes + kWBytes);
-  static constexpr int kBudget = 200 * 1024;
+  static constexpr int kSlabBytes = kBlockM * 128;   // epilogue transpose slab: 128 rows x 32 fp32, 128B-swizzled
+  static constexpr int kBudget = 192 * 1024;         // smem ring budget (227 KB - 2 slabs - barriers - alignment)
   static constexpr int kStagesRaw = kBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
                                    : (2 * BLOCK_N <= 256) ? 256 : 512;
   static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024 /* manual 1024 B alignment */;
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + 2 * kSlabBytes + kBarBytes + 1024 /* manual 1024 B alignment */;
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
   static_assert(kStages >= 2, "need at least a double-buffered smem ring");
   static_assert(2 * BLOCK_N <= 512, "two accumulator stages must fit TMEM");
   static_assert(kABytes % 1024 == 0 && kWBytes % 1024 == 0, "swizzled tiles must stay 1024 B aligned");
@@ -161,7 +164,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + S * Cfg::kStageBytes;
+  const uint32_t slab_base = smem_base + S * Cfg::kStageBytes;   // 2 epilogue slabs, 1024 B aligned
+  const uint32_t bar_base = slab_base + 2 * Cfg::kSlabBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * S + a); };
@@ -265,37 +269,80 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     }
   } else {
     // ================================ epilogue warps ================================
+    // Two phases per 32-column chunk so that every global access is coalesced:
+    //  (1) tcgen05.ld hands each thread 32 columns of ITS row (TMEM lane); the thread parks them in a
+    //      128B-swizzled smem slab (row r, 16 B chunk j -> chunk j ^ (r & 7): conflict-free both ways);
+    //  (2) after a 128-thread named barrier the slab is read back transposed: 8 lanes cover the 32
+    //      columns of one row (float4 each), a warp covers 4 rows per access, so residual loads and
+    //      fp32 / bf16 stores are full 128 B / 64 B row segments.  Per-column parameters (bias, Snake
+    //      alpha) are fixed per lane and loaded once per chunk.
     const int group = warp & 3;                 // TMEM lane quarter this warp may read
     const int row_in_tile = group * 32 + lane;
-    uint32_t iter = 0;
+    const int ew = warp - 2;                    // 0..3
+    const int q4 = lane & 7, rsub = lane >> 3;  // phase-2 mapping: column quad, row within a 4-row group
+    uint32_t iter = 0, chunk_ctr = 0;
+    // The residual (fp32, may alias out_f32: every element is read and later written by the same thread)
+    // is prefetched one chunk ahead into registers so its HBM latency hides behind the previous chunk /
+    // the wait for the accumulator instead of serialising the 8 row groups of a chunk.
+    float4 res_nxt[8];
+    auto prefetch_residual = [&](int b_, int l0_, int n_) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int l = l0_ + ew * 32 + i * 4 + rsub;
+        res_nxt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (l < p.L)
+          res_nxt[i] = *reinterpret_cast<const float4*>(p.residual + ((size_t)b_ * p.L + l) * (size_t)p.n_total + n_);
+      }
+    };
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
       const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;
       const int b = m_tile / p.m_tiles_per_utt;
-      const int l = (m_tile % p.m_tiles_per_utt) * kBlockM + row_in_tile;
+      const int l0 = (m_tile % p.m_tiles_per_utt) * kBlockM;
       const int n0 = n_tile * BLOCK_N;
-      const bool valid = l < p.L;
-      const size_t row_off = ((size_t)b * p.L + (valid ? l : 0)) * (size_t)p.n_total;
       const uint32_t acc = iter & 1u, acc_phase = (iter >> 1) & 1u;
+      if (p.residual) prefetch_residual(b, l0, n0 + q4 * 4);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(group * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
-        uint32_t r[32];
-        tmem_ld_x32(t_row + c, r);
-        tmem_ld_wait();
-        if (valid) {
+      for (int c = 0; c < BLOCK_N; c += 32, ++chunk_ctr) {
+        const uint32_t slab = slab_base + (chunk_ctr & 1u) * Cfg::kSlabBytes;
+        {
+          uint32_t r[32];
+          tmem_ld_x32(t_row + c, r);
+          tmem_ld_wait();
+          const uint32_t row_addr = slab + row_in_tile * 128;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float v[8];
+          for (int j = 0; j < 8; ++j)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + ((j ^ (row_in_tile & 7)) << 4)),
+                         "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
+                         : "memory");
+        }
+        if (c + 32 >= BLOCK_N) {   // accumulator fully drained: hand the TMEM stage back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(tempty_bar(acc));
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int n = n0 + c + q4 * 4;
+        float4 bias4, alpha4, inv4;
+        load_col_params4(p, n, bias4, alpha4, inv4);
+        float4 res[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[q * 8 + i]);
-            epilogue_store8(p, v, b, row_off, n0 + c + q * 8);
-          }
+        for (int i = 0; i < 8; ++i) res[i] = res_nxt[i];
+        if (p.residual && c + 32 < BLOCK_N) prefetch_residual(b, l0, n + 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = ew * 32 + i * 4 + rsub;
+          const int l = l0 + r;
+          float4 v;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                       : "r"(slab + r * 128 + ((q4 ^ (r & 7)) << 4)));
+          if (p.residual) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
+          if (l < p.L) epilogue_store4(p, v, b, ((size_t)b * p.L + l) * (size_t)p.n_total, n, bias4, alpha4, inv4,
+                                          /*add_residual=*/false);
         }
       }
-      tc_fence_before();
-      mbar_arrive(tempty_bar(acc));
     }
   }
 
@@ -352,7 +399,9 @@ int launch_inst(const GemmWeights& w, const OpBuf& a, int batch, int L, const Co
   }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta_hi, ta_lo, w.tmap_hi, NTERMS == 3 ? w.tmap_lo : w.tmap_hi, p);
+  constexpr int mi = BK == 64 ? 0 : 1;
+  kern<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta_hi, ta_lo, w.tmap_hi[mi],
+                                                        NTERMS == 3 ? w.tmap_lo[mi] : w.tmap_hi[mi], p);
   SC_LAUNCH_CHECK();
   return 0;
 }
@@ -372,27 +421,39 @@ int tma_init() {
   return 0;
 }
 
-// Tile shape per layer: BLOCK_N must divide the per-phase width so an N tile never straddles two
-// polyphase branches; BK = 64 (128 B swizzle rows) unless C_in is only a multiple of 32.
-int choose_tile(int c_in, int cols_per_phase, int* block_n, int* bk) {
-  if (c_in % 64 == 0) *bk = 64;
-  else if (c_in % 32 == 0) *bk = 32;
-  else { set_error("C_in=%d is not a multiple of 32", c_in); return SPARKCODEC_EINVAL; }
+// N tile per layer: BLOCK_N must divide the per-phase width so an N tile never straddles two polyphase
+// branches.
+int choose_block_n(int cols_per_phase, int* block_n) {
   const int cand[] = {256, 192, 128, 96, 64};
   for (int c : cand)
     if (cols_per_phase % c == 0) { *block_n = c; return 0; }
-  set_error("no tile width divides C_out=%d (need a multiple of 64)", cols_per_phase);
+  set_error("no tile width divides C_out=%d (need a multiple of 64 or 96)", cols_per_phase);
   return SPARKCODEC_EINVAL;
+}
+
+// K chunk per (layer, precision): 64 bf16 (128 B swizzle rows) when C_in allows it and the smem ring
+// still gets >= 3 stages, else 32 (64 B swizzle rows).
+int choose_bk(int c_in, int block_n, int precision) {
+  if (c_in % 64 != 0) return 32;
+  const int planes = precision == SPARKCODEC_PREC_FP32 ? 2 : 1;
+  const int stage64 = planes * (kBlockM * 64 * 2 + block_n * 64 * 2);
+  return (192 * 1024) / stage64 >= 3 ? 64 : 32;
 }
 
 int make_weight_tmaps(GemmWeights& w) {
   SC_TRY(tma_init());
-  SC_TRY(choose_tile(w.c_in, w.taps.cols_per_phase, &w.block_n, &w.bk));
+  if (w.c_in % 32 != 0) { set_error("C_in=%d is not a multiple of 32", w.c_in); return SPARKCODEC_EINVAL; }
+  SC_TRY(choose_block_n(w.taps.cols_per_phase, &w.block_n));
+  w.has_bk64 = w.c_in % 64 == 0;
   const uint64_t dims[2] = {(uint64_t)w.kt * w.c_in, (uint64_t)w.n_total};
   const uint64_t strides[1] = {(uint64_t)w.kt * w.c_in * 2};
-  const uint32_t box[2] = {(uint32_t)w.bk, (uint32_t)w.block_n};
-  SC_TRY(encode_map(&w.tmap_hi, w.w_hi, 2, dims, strides, box, w.bk, true));
-  SC_TRY(encode_map(&w.tmap_lo, w.w_lo, 2, dims, strides, box, w.bk, true));
+  for (int mi = 0; mi < 2; ++mi) {
+    const int bk = mi == 0 ? 64 : 32;
+    if (mi == 0 && !w.has_bk64) continue;
+    const uint32_t box[2] = {(uint32_t)bk, (uint32_t)w.block_n};
+    SC_TRY(encode_map(&w.tmap_hi[mi], w.w_hi, 2, dims, strides, box, bk, true));
+    SC_TRY(encode_map(&w.tmap_lo[mi], w.w_lo, 2, dims, strides, box, bk, true));
+  }
   return 0;
 }
 
@@ -418,14 +479,15 @@ int launch_conv_gemm_tc(const GemmWeights& w, const OpBuf& a, int batch, int L, 
   ConvGemmParams p;
   SC_TRY(fill_params(w, batch, L, ep, precision, &p));
   const bool f32 = precision == SPARKCODEC_PREC_FP32;
+  const int bk = choose_bk(w.c_in, w.block_n, precision);
 #define SC_INST(BN, BKK)                                                                        \
-  if (w.block_n == BN && w.bk == BKK)                                                           \
+  if (w.block_n == BN && bk == BKK)                                                             \
     return f32 ? launch_inst<BN, BKK, 3>(w, a, batch, L, p, num_sms, stream)                    \
                : launch_inst<BN, BKK, 1>(w, a, batch, L, p, num_sms, stream);
   SC_INST(256, 64) SC_INST(192, 64) SC_INST(128, 64) SC_INST(96, 64) SC_INST(64, 64)
   SC_INST(256, 32) SC_INST(192, 32) SC_INST(128, 32) SC_INST(96, 32) SC_INST(64, 32)
 #undef SC_INST
-  set_error("no tcgen05 instantiation for block_n=%d bk=%d", w.block_n, w.bk);
+  set_error("no tcgen05 instantiation for block_n=%d bk=%d", w.block_n, bk);
   return SPARKCODEC_EINVAL;
 }
 
