@@ -25,7 +25,7 @@ struct ConvGemmParams {
 
 int fill_params(const GemmWeights& w, int batch, int L, const Epilogue& ep, int precision, ConvGemmParams* p);
 int choose_block_n(int cols_per_phase, int* block_n);
-int choose_bk(int c_in, int block_n, int precision);
+int choose_bk(int c_in, int block_n, int precision, bool residual);
 
 // snake(x) = x + sin(alpha x)^2 / (alpha + 1e-9)   (reference sparktts/modules/blocks/layers.py:32-39)
 // sin: two-constant Cody-Waite reduction to [-pi, pi], then the SFU sine (abs err ~2^-21 there).

@@ -116,6 +116,15 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major operand tile in smem, rows of BK bf16 (= the TMA swizzle span), 8-row swizzle atoms stacked
@@ -132,45 +141,57 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
 }
 
-template <int BLOCK_N, int BK, int NTERMS>
+constexpr int kResSlots = 4;   // residual slabs in flight (TMA, 16 KB each)
+
+template <int BLOCK_N, int BK, int NTERMS, bool RES>
 struct TileCfg {
   static constexpr int kPlanes = (NTERMS == 3) ? 2 : 1;
   static constexpr int kABytes = kBlockM * BK * 2;
   static constexpr int kWBytes = BLOCK_N * BK * 2;
   static constexpr int kStageBytes = kPlanes * (kABytes + kWBytes);
   static constexpr int kSlabBytes = kBlockM * 128;   // epilogue transpose slab: 128 rows x 32 fp32, 128B-swizzled
-  static constexpr int kBudget = 192 * 1024;         // smem ring budget (227 KB - 2 slabs - barriers - alignment)
+  static constexpr int kResBytes = RES ? kResSlots * kSlabBytes : 0;   // residual slabs (same swizzled format)
+  // smem ring budget: 227 KB - 2 slabs - residual ring - barriers - alignment slack
+  static constexpr int kBudget = 192 * 1024 - kResBytes;
   static constexpr int kStagesRaw = kBudget / kStageBytes;
-  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : (kStagesRaw < 1 ? 1 : kStagesRaw);
   static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
                                    : (2 * BLOCK_N <= 256) ? 256 : 512;
-  static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
+  static constexpr int kBarBytes = (2 * kStages + 4 + 2 * kResSlots) * 8 + 16;
   static constexpr int kSmemBytes =
-      kStages * kStageBytes + 2 * kSlabBytes + kBarBytes + 1024 /* manual 1024 B alignment */;
-  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
-  static_assert(kStages >= 2, "need at least a double-buffered smem ring");
+      kStages * kStageBytes + 2 * kSlabBytes + kResBytes + kBarBytes + 1024 /* manual 1024 B alignment */;
+  static_assert(!(kStagesRaw >= 2) || kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
+  static constexpr bool kValid = kStages >= 2;   // need at least a double-buffered smem ring
   static_assert(2 * BLOCK_N <= 512, "two accumulator stages must fit TMEM");
   static_assert(kABytes % 1024 == 0 && kWBytes % 1024 == 0, "swizzled tiles must stay 1024 B aligned");
 };
 
-constexpr int kNumThreads = 192;   // warp 0 producer, warp 1 MMA, warps 2..5 epilogue
+// warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue (two warps per TMEM lane quarter, each
+// draining half of a 32-column chunk), warp 10 residual TMA producer
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kResWarp = 2 + kEpiWarps;
+constexpr int kNumThreads = (3 + kEpiWarps) * 32;
 
-template <int BLOCK_N, int BK, int NTERMS>
+template <int BLOCK_N, int BK, int NTERMS, bool RES>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                     const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
-                    const ConvGemmParams p) {
-  using Cfg = TileCfg<BLOCK_N, BK, NTERMS>;
+                    const __grid_constant__ CUtensorMap tm_res, const ConvGemmParams p) {
+  using Cfg = TileCfg<BLOCK_N, BK, NTERMS, RES>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t slab_base = smem_base + S * Cfg::kStageBytes;   // 2 epilogue slabs, 1024 B aligned
-  const uint32_t bar_base = slab_base + 2 * Cfg::kSlabBytes;
+  const uint32_t res_base = slab_base + 2 * Cfg::kSlabBytes;      // kResSlots residual slabs (RES only)
+  const uint32_t bar_base = res_base + Cfg::kResBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * S + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * S + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 4);
+  auto rfull_bar = [&](int r) { return bar_base + 8u * (2 * S + 4 + r); };
+  auto rempty_bar = [&](int r) { return bar_base + 8u * (2 * S + 4 + kResSlots + r); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 4 + 2 * kResSlots);
   uint32_t* tmem_slot_ptr =
       reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -192,7 +213,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 128);
+      mbar_init(tempty_bar(a), kEpiThreads);
+    }
+    for (int r = 0; r < kResSlots; ++r) {
+      mbar_init(rfull_bar(r), 1);
+      mbar_init(rempty_bar(r), kEpiThreads);
     }
     fence_barrier_init();
   }
@@ -267,6 +292,26 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
         }
       }
     }
+  } else if (warp == kResWarp) {
+    // ================================ residual TMA producer ================================
+    // Streams the fp32 residual tile (B, L, N) as 128-row x 32-column boxes into a ring of slabs that
+    // have exactly the epilogue's swizzled slab format (SWIZZLE_128B), kResSlots boxes in flight.
+    if (RES && lane == 0) {
+      prefetch_tmap(&tm_res);
+      uint32_t rs = 0, rphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;
+        const int b = m_tile / p.m_tiles_per_utt;
+        const int l0 = (m_tile % p.m_tiles_per_utt) * kBlockM;
+        const int n0 = n_tile * BLOCK_N;
+        for (int c = 0; c < BLOCK_N; c += 32) {
+          mbar_wait(rempty_bar(rs), rphase ^ 1u);
+          mbar_expect_tx(rfull_bar(rs), Cfg::kSlabBytes);
+          tma_load_3d(res_base + rs * Cfg::kSlabBytes, &tm_res, rfull_bar(rs), n0 + c, l0, b);
+          if (++rs == kResSlots) { rs = 0; rphase ^= 1u; }
+        }
+      }
+    }
   } else {
     // ================================ epilogue warps ================================
     // Two phases per 32-column chunk so that every global access is coalesced:
@@ -278,29 +323,19 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     //      alpha) are fixed per lane and loaded once per chunk.
     const int group = warp & 3;                 // TMEM lane quarter this warp may read
     const int row_in_tile = group * 32 + lane;
-    const int ew = warp - 2;                    // 0..3
+    const int ew = warp - 2;                    // 0..7
+    const int half = ew >> 2;                   // which 16 of a chunk's 32 columns this warp drains from TMEM
     const int q4 = lane & 7, rsub = lane >> 3;  // phase-2 mapping: column quad, row within a 4-row group
     uint32_t iter = 0, chunk_ctr = 0;
-    // The residual (fp32, may alias out_f32: every element is read and later written by the same thread)
-    // is prefetched one chunk ahead into registers so its HBM latency hides behind the previous chunk /
-    // the wait for the accumulator instead of serialising the 8 row groups of a chunk.
-    float4 res_nxt[8];
-    auto prefetch_residual = [&](int b_, int l0_, int n_) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int l = l0_ + ew * 32 + i * 4 + rsub;
-        res_nxt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (l < p.L)
-          res_nxt[i] = *reinterpret_cast<const float4*>(p.residual + ((size_t)b_ * p.L + l) * (size_t)p.n_total + n_);
-      }
-    };
+    // The residual (fp32, may alias out_f32: every element is read by TMA before the thread that
+    // owns it stores the sum) arrives through the slab ring filled by warp 6.
+    uint32_t rs = 0, rphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
       const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;
       const int b = m_tile / p.m_tiles_per_utt;
       const int l0 = (m_tile % p.m_tiles_per_utt) * kBlockM;
       const int n0 = n_tile * BLOCK_N;
       const uint32_t acc = iter & 1u, acc_phase = (iter >> 1) & 1u;
-      if (p.residual) prefetch_residual(b, l0, n0 + q4 * 4);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(group * 32) << 16) + acc * BLOCK_N;
@@ -308,13 +343,13 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       for (int c = 0; c < BLOCK_N; c += 32, ++chunk_ctr) {
         const uint32_t slab = slab_base + (chunk_ctr & 1u) * Cfg::kSlabBytes;
         {
-          uint32_t r[32];
-          tmem_ld_x32(t_row + c, r);
+          uint32_t r[16];
+          tmem_ld_x16(t_row + c + 16 * half, r);
           tmem_ld_wait();
           const uint32_t row_addr = slab + row_in_tile * 128;
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + ((j ^ (row_in_tile & 7)) << 4)),
+          for (int j = 0; j < 4; ++j)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + (((4 * half + j) ^ (row_in_tile & 7)) << 4)),
                          "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
                          : "memory");
         }
@@ -322,25 +357,37 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
           tc_fence_before();
           mbar_arrive(tempty_bar(acc));
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         const int n = n0 + c + q4 * 4;
         float4 bias4, alpha4, inv4;
         load_col_params4(p, n, bias4, alpha4, inv4);
-        float4 res[8];
+        uint32_t rslab = 0;
+        if (RES) {
+          rslab = res_base + rs * Cfg::kSlabBytes;
+          mbar_wait(rfull_bar(rs), rphase);
+        }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) res[i] = res_nxt[i];
-        if (p.residual && c + 32 < BLOCK_N) prefetch_residual(b, l0, n + 32);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = ew * 32 + i * 4 + rsub;
+        for (int i = 0; i < 4; ++i) {
+          const int r = ew * 16 + i * 4 + rsub;
           const int l = l0 + r;
+          const uint32_t off = r * 128 + ((q4 ^ (r & 7)) << 4);
           float4 v;
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                        : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                       : "r"(slab + r * 128 + ((q4 ^ (r & 7)) << 4)));
-          if (p.residual) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
+                       : "r"(slab + off));
+          if (RES) {
+            float4 rr;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(rr.x), "=f"(rr.y), "=f"(rr.z), "=f"(rr.w)
+                         : "r"(rslab + off));
+            v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+          }
           if (l < p.L) epilogue_store4(p, v, b, ((size_t)b * p.L + l) * (size_t)p.n_total, n, bias4, alpha4, inv4,
                                           /*add_residual=*/false);
+        }
+        if (RES) {
+          mbar_arrive(rempty_bar(rs));
+          if (++rs == kResSlots) { rs = 0; rphase ^= 1u; }
         }
       }
     }
@@ -362,12 +409,12 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
 PFN_tmapEncodeTiled g_encode = nullptr;
 
 int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-               const uint32_t* box, int bk, bool weights) {
+               const uint32_t* box, int bk, bool weights, bool fp32 = false) {
   cuuint64_t gdim[3], gstr[2];
   cuuint32_t bx[3], es[3] = {1, 1, 1};
   for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; }
   for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_bytes[i];
-  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr,
+  CUresult r = g_encode(map, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr,
                         bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                         weights ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -380,10 +427,14 @@ int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dim
   return 0;
 }
 
-template <int BLOCK_N, int BK, int NTERMS>
+template <int BLOCK_N, int BK, int NTERMS, bool RES>
 int launch_inst(const GemmWeights& w, const OpBuf& a, int batch, int L, const ConvGemmParams& p, int num_sms,
                 cudaStream_t stream) {
-  using Cfg = TileCfg<BLOCK_N, BK, NTERMS>;
+  using Cfg = TileCfg<BLOCK_N, BK, NTERMS, RES>;
+  if constexpr (!Cfg::kValid) {
+    set_error("tile %dx%d (terms %d, residual %d) does not fit shared memory", BLOCK_N, BK, NTERMS, (int)RES);
+    return SPARKCODEC_EINVAL;
+  } else {
   CUtensorMap ta_hi, ta_lo;
   const uint64_t dims[3] = {(uint64_t)w.c_in, (uint64_t)L, (uint64_t)batch};
   const uint64_t strides[2] = {(uint64_t)w.c_in * 2, (uint64_t)L * w.c_in * 2};
@@ -391,7 +442,14 @@ int launch_inst(const GemmWeights& w, const OpBuf& a, int batch, int L, const Co
   SC_TRY(encode_map(&ta_hi, a.hi, 3, dims, strides, box, BK, false));
   if (NTERMS == 3) SC_TRY(encode_map(&ta_lo, a.lo, 3, dims, strides, box, BK, false));
   else ta_lo = ta_hi;
-  auto kern = conv_gemm_tc_kernel<BLOCK_N, BK, NTERMS>;
+  CUtensorMap t_res = ta_hi;
+  if (RES) {
+    const uint64_t rdims[3] = {(uint64_t)w.n_total, (uint64_t)L, (uint64_t)batch};
+    const uint64_t rstr[2] = {(uint64_t)w.n_total * 4, (uint64_t)L * w.n_total * 4};
+    const uint32_t rbox[3] = {32u, (uint32_t)kBlockM, 1u};
+    SC_TRY(encode_map(&t_res, p.residual, 3, rdims, rstr, rbox, 64, false, /*fp32=*/true));
+  }
+  auto kern = conv_gemm_tc_kernel<BLOCK_N, BK, NTERMS, RES>;
   static bool attr_done = false;   // per instantiation
   if (!attr_done) {
     SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -401,9 +459,10 @@ int launch_inst(const GemmWeights& w, const OpBuf& a, int batch, int L, const Co
   const int grid = tiles < num_sms ? tiles : num_sms;
   constexpr int mi = BK == 64 ? 0 : 1;
   kern<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta_hi, ta_lo, w.tmap_hi[mi],
-                                                        NTERMS == 3 ? w.tmap_lo[mi] : w.tmap_hi[mi], p);
+                                                        NTERMS == 3 ? w.tmap_lo[mi] : w.tmap_hi[mi], t_res, p);
   SC_LAUNCH_CHECK();
   return 0;
+  }
 }
 
 }  // namespace
@@ -433,11 +492,12 @@ int choose_block_n(int cols_per_phase, int* block_n) {
 
 // K chunk per (layer, precision): 64 bf16 (128 B swizzle rows) when C_in allows it and the smem ring
 // still gets >= 3 stages, else 32 (64 B swizzle rows).
-int choose_bk(int c_in, int block_n, int precision) {
+int choose_bk(int c_in, int block_n, int precision, bool residual) {
   if (c_in % 64 != 0) return 32;
   const int planes = precision == SPARKCODEC_PREC_FP32 ? 2 : 1;
   const int stage64 = planes * (kBlockM * 64 * 2 + block_n * 64 * 2);
-  return (192 * 1024) / stage64 >= 3 ? 64 : 32;
+  const int budget = 192 * 1024 - (residual ? kResSlots * kBlockM * 128 : 0);
+  return budget / stage64 >= 3 ? 64 : 32;
 }
 
 int make_weight_tmaps(GemmWeights& w) {
@@ -479,11 +539,14 @@ int launch_conv_gemm_tc(const GemmWeights& w, const OpBuf& a, int batch, int L, 
   ConvGemmParams p;
   SC_TRY(fill_params(w, batch, L, ep, precision, &p));
   const bool f32 = precision == SPARKCODEC_PREC_FP32;
-  const int bk = choose_bk(w.c_in, w.block_n, precision);
+  const bool res = ep.residual != nullptr;
+  const int bk = choose_bk(w.c_in, w.block_n, precision, res);
 #define SC_INST(BN, BKK)                                                                        \
   if (w.block_n == BN && bk == BKK)                                                             \
-    return f32 ? launch_inst<BN, BKK, 3>(w, a, batch, L, p, num_sms, stream)                    \
-               : launch_inst<BN, BKK, 1>(w, a, batch, L, p, num_sms, stream);
+    return res ? (f32 ? launch_inst<BN, BKK, 3, true>(w, a, batch, L, p, num_sms, stream)       \
+                      : launch_inst<BN, BKK, 1, true>(w, a, batch, L, p, num_sms, stream))      \
+               : (f32 ? launch_inst<BN, BKK, 3, false>(w, a, batch, L, p, num_sms, stream)      \
+                      : launch_inst<BN, BKK, 1, false>(w, a, batch, L, p, num_sms, stream));
   SC_INST(256, 64) SC_INST(192, 64) SC_INST(128, 64) SC_INST(96, 64) SC_INST(64, 64)
   SC_INST(256, 32) SC_INST(192, 32) SC_INST(128, 32) SC_INST(96, 32) SC_INST(64, 32)
 #undef SC_INST
