@@ -11,6 +11,8 @@ struct ConvGemmParams {
   int m_tiles_per_utt;   // ceil(L / 128)
   int num_m_tiles;       // batch * m_tiles_per_utt
   int num_n_tiles;       // n_total / BLOCK_N
+  int halo_rows;         // halo mainloop: rows of the A box (128 + tap span, multiple of 8)
+  int halo_bo_mode;      // halo mainloop: descriptor base-offset convention (see tc_gemm.cu)
   // epilogue
   const float* bias;
   const float* rowbias;

@@ -19,6 +19,8 @@
 
 namespace sparkcodec {
 
+int choose_bk_halo(int c_in, int block_n, int precision);
+
 namespace {
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -56,6 +58,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       __trap();
     }
   }
+}
+// One elected lane of a fully converged warp.  Code under this predicate is known by the compiler to run
+// in exactly one thread, so TMA / tcgen05 operands can live in uniform registers without the per-lane
+// "waterfall" loops that a plain `lane == 0` test forces around every such instruction.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -135,6 +149,15 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   constexpr uint64_t sbo = (8ull * BK * 2) >> 4;
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
+// Descriptor for a tile that starts at an arbitrary ROW of a swizzled buffer (halo reuse).  The swizzle
+// XOR is a function of the absolute smem address; bo_mode 1 additionally records the start row's phase
+// inside the 8-row swizzle atom in the descriptor's base-offset field (bits 49..51).
+template <int BK>
+__device__ __forceinline__ uint64_t make_smem_desc_rows(uint32_t smem_addr, int bo_mode) {
+  uint64_t d = make_smem_desc<BK>(smem_addr);
+  if (bo_mode == 1) d |= (uint64_t)((smem_addr >> 7) & 7u) << 49;
+  return d;
+}
 // kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = BLOCK_N.
 template <int BLOCK_N>
 __device__ __forceinline__ constexpr uint32_t make_idesc() {
@@ -142,26 +165,40 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
 }
 
 constexpr int kResSlots = 4;   // residual slabs in flight (TMA, 16 KB each)
+constexpr int kHaloRowsMax = 184;   // 128 + 6 * 9 (k=7, dilation 9) rounded up to 8
 
-template <int BLOCK_N, int BK, int NTERMS, bool RES>
+constexpr int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+// Two mainloop flavours share the kernel:
+//  * plain  : one smem ring; a stage = {A_hi, A_lo, W_hi, W_lo} for one (tap, K-chunk); A is re-fetched per tap
+//  * HALO   : (k>1 convs) ring 1 holds A tiles with the conv halo (128 + (k-1)*dilation rows) for one
+//             K-chunk, fetched ONCE and used by all taps through row-offset smem descriptors; ring 2 holds
+//             the per-(tap, K-chunk) W tiles.  Cuts the L2->smem operand traffic by 26-45 %.
+template <int BLOCK_N, int BK, int NTERMS, bool RES, bool HALO>
 struct TileCfg {
   static constexpr int kPlanes = (NTERMS == 3) ? 2 : 1;
   static constexpr int kABytes = kBlockM * BK * 2;
   static constexpr int kWBytes = BLOCK_N * BK * 2;
-  static constexpr int kStageBytes = kPlanes * (kABytes + kWBytes);
   static constexpr int kSlabBytes = kBlockM * 128;   // epilogue transpose slab: 128 rows x 32 fp32, 128B-swizzled
   static constexpr int kResBytes = RES ? kResSlots * kSlabBytes : 0;   // residual slabs (same swizzled format)
   // smem ring budget: 227 KB - 2 slabs - residual ring - barriers - alignment slack
   static constexpr int kBudget = 192 * 1024 - kResBytes;
-  static constexpr int kStagesRaw = kBudget / kStageBytes;
-  static constexpr int kStages = kStagesRaw > 8 ? 8 : (kStagesRaw < 1 ? 1 : kStagesRaw);
+  // ring 1
+  static constexpr int kAHaloBytes = align_up(kHaloRowsMax * BK * 2, 1024);            // per plane
+  static constexpr int kStage1Bytes = HALO ? kPlanes * kAHaloBytes : kPlanes * (kABytes + kWBytes);
+  static constexpr int kS1Raw = HALO ? 3 : kBudget / kStage1Bytes;
+  static constexpr int kS1 = kS1Raw > 8 ? 8 : (kS1Raw < 1 ? 1 : kS1Raw);
+  // ring 2 (HALO only)
+  static constexpr int kStage2Bytes = kPlanes * kWBytes;
+  static constexpr int kS2Raw = HALO ? (kBudget - kS1 * kStage1Bytes) / kStage2Bytes : 0;
+  static constexpr int kS2 = kS2Raw > 8 ? 8 : (kS2Raw < 0 ? 0 : kS2Raw);
+  static constexpr int kRingBytes = kS1 * kStage1Bytes + kS2 * kStage2Bytes;
   static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
                                    : (2 * BLOCK_N <= 256) ? 256 : 512;
-  static constexpr int kBarBytes = (2 * kStages + 4 + 2 * kResSlots) * 8 + 16;
-  static constexpr int kSmemBytes =
-      kStages * kStageBytes + 2 * kSlabBytes + kResBytes + kBarBytes + 1024 /* manual 1024 B alignment */;
-  static_assert(!(kStagesRaw >= 2) || kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
-  static constexpr bool kValid = kStages >= 2;   // need at least a double-buffered smem ring
+  static constexpr int kBarBytes = (2 * kS1 + 2 * kS2 + 4 + 2 * kResSlots) * 8 + 16;
+  static constexpr int kSmemBytes = kRingBytes + 2 * kSlabBytes + kResBytes + kBarBytes + 1024 /* alignment */;
+  static constexpr bool kValid = HALO ? (kS2 >= 3) : (kS1Raw >= 2);
+  static_assert(!kValid || kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
   static_assert(2 * BLOCK_N <= 512, "two accumulator stages must fit TMEM");
   static_assert(kABytes % 1024 == 0 && kWBytes % 1024 == 0, "swizzled tiles must stay 1024 B aligned");
 };
@@ -173,17 +210,18 @@ constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kResWarp = 2 + kEpiWarps;
 constexpr int kNumThreads = (3 + kEpiWarps) * 32;
 
-template <int BLOCK_N, int BK, int NTERMS, bool RES>
+template <int BLOCK_N, int BK, int NTERMS, bool RES, bool HALO>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                     const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                     const __grid_constant__ CUtensorMap tm_res, const ConvGemmParams p) {
-  using Cfg = TileCfg<BLOCK_N, BK, NTERMS, RES>;
-  constexpr int S = Cfg::kStages;
+  using Cfg = TileCfg<BLOCK_N, BK, NTERMS, RES, HALO>;
+  constexpr int S = Cfg::kS1, S2 = Cfg::kS2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t slab_base = smem_base + S * Cfg::kStageBytes;   // 2 epilogue slabs, 1024 B aligned
-  const uint32_t res_base = slab_base + 2 * Cfg::kSlabBytes;      // kResSlots residual slabs (RES only)
+  const uint32_t ring2_base = smem_base + S * Cfg::kStage1Bytes;
+  const uint32_t slab_base = smem_base + Cfg::kRingBytes;          // 2 epilogue slabs, 1024 B aligned
+  const uint32_t res_base = slab_base + 2 * Cfg::kSlabBytes;       // kResSlots residual slabs (RES only)
   const uint32_t bar_base = res_base + Cfg::kResBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
@@ -191,7 +229,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * S + 2 + a); };
   auto rfull_bar = [&](int r) { return bar_base + 8u * (2 * S + 4 + r); };
   auto rempty_bar = [&](int r) { return bar_base + 8u * (2 * S + 4 + kResSlots + r); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 4 + 2 * kResSlots);
+  auto wfull_bar = [&](int s) { return bar_base + 8u * (2 * S + 4 + 2 * kResSlots + s); };
+  auto wempty_bar = [&](int s) { return bar_base + 8u * (2 * S + 4 + 2 * kResSlots + S2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 4 + 2 * kResSlots + 2 * S2);
   uint32_t* tmem_slot_ptr =
       reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -211,6 +251,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
+    for (int s = 0; s < S2; ++s) {
+      mbar_init(wfull_bar(s), 1);
+      mbar_init(wempty_bar(s), 1);
+    }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), kEpiThreads);
@@ -229,8 +273,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
+    if (elect_one()) {
+      uint32_t stage = 0, phase = 0, ws = 0, wphase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;
         const int b = m_tile / p.m_tiles_per_utt;
@@ -238,57 +282,110 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
         const int n0 = n_tile * BLOCK_N;
         const int ph = n0 / p.taps.cols_per_phase;
         const int ntaps = p.taps.ntaps[ph];
-        for (int j = 0; j < ntaps; ++j) {
-          const int row = l0 + p.taps.shift[ph][j];
+        if (HALO) {
+          const uint32_t a_tx = Cfg::kPlanes * p.halo_rows * BK * 2;
           for (int kc = 0; kc < k_chunks; ++kc) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-            const uint32_t sw = sa + Cfg::kPlanes * Cfg::kABytes;
-            mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-            tma_load_3d(sa, &tm_a_hi, full_bar(stage), kc * BK, row, b);
-            tma_load_2d(sw, &tm_w_hi, full_bar(stage), j * p.c_in + kc * BK, n0);
-            if (NTERMS == 3) {
-              tma_load_3d(sa + Cfg::kABytes, &tm_a_lo, full_bar(stage), kc * BK, row, b);
-              tma_load_2d(sw + Cfg::kWBytes, &tm_w_lo, full_bar(stage), j * p.c_in + kc * BK, n0);
-            }
+            const uint32_t sa = smem_base + stage * Cfg::kStage1Bytes;
+            mbar_expect_tx(full_bar(stage), a_tx);
+            tma_load_3d(sa, &tm_a_hi, full_bar(stage), kc * BK, l0 + p.taps.shift[0][0], b);
+            if (NTERMS == 3)
+              tma_load_3d(sa + Cfg::kAHaloBytes, &tm_a_lo, full_bar(stage), kc * BK, l0 + p.taps.shift[0][0], b);
             if (++stage == S) { stage = 0; phase ^= 1u; }
+            for (int j = 0; j < ntaps; ++j) {
+              mbar_wait(wempty_bar(ws), wphase ^ 1u);
+              const uint32_t sw = ring2_base + ws * Cfg::kStage2Bytes;
+              mbar_expect_tx(wfull_bar(ws), Cfg::kStage2Bytes);
+              tma_load_2d(sw, &tm_w_hi, wfull_bar(ws), j * p.c_in + kc * BK, n0);
+              if (NTERMS == 3) tma_load_2d(sw + Cfg::kWBytes, &tm_w_lo, wfull_bar(ws), j * p.c_in + kc * BK, n0);
+              if (++ws == S2) { ws = 0; wphase ^= 1u; }
+            }
+          }
+        } else {
+          for (int j = 0; j < ntaps; ++j) {
+            const int row = l0 + p.taps.shift[ph][j];
+            for (int kc = 0; kc < k_chunks; ++kc) {
+              mbar_wait(empty_bar(stage), phase ^ 1u);
+              const uint32_t sa = smem_base + stage * Cfg::kStage1Bytes;
+              const uint32_t sw = sa + Cfg::kPlanes * Cfg::kABytes;
+              mbar_expect_tx(full_bar(stage), Cfg::kStage1Bytes);
+              tma_load_3d(sa, &tm_a_hi, full_bar(stage), kc * BK, row, b);
+              tma_load_2d(sw, &tm_w_hi, full_bar(stage), j * p.c_in + kc * BK, n0);
+              if (NTERMS == 3) {
+                tma_load_3d(sa + Cfg::kABytes, &tm_a_lo, full_bar(stage), kc * BK, row, b);
+                tma_load_2d(sw + Cfg::kWBytes, &tm_w_lo, full_bar(stage), j * p.c_in + kc * BK, n0);
+              }
+              if (++stage == S) { stage = 0; phase ^= 1u; }
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc<BLOCK_N>();
-      uint32_t stage = 0, phase = 0, iter = 0;
+      uint32_t stage = 0, phase = 0, iter = 0, ws = 0, wphase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
         const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
         const int ph = n0 / p.taps.cols_per_phase;
-        const int n_k = p.taps.ntaps[ph] * k_chunks;
+        const int ntaps = p.taps.ntaps[ph];
         const uint32_t acc = iter & 1u, acc_phase = (iter >> 1) & 1u;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);   // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int ki = 0; ki < n_k; ++ki) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-          const uint32_t sw = sa + Cfg::kPlanes * Cfg::kABytes;
-          const uint64_t a_hi = make_smem_desc<BK>(sa), w_hi = make_smem_desc<BK>(sw);
+        if (HALO) {
+          for (int kc = 0; kc < k_chunks; ++kc) {
+            mbar_wait(full_bar(stage), phase);
+            const uint32_t sa = smem_base + stage * Cfg::kStage1Bytes;
+            for (int j = 0; j < ntaps; ++j) {
+              mbar_wait(wfull_bar(ws), wphase);
+              tc_fence_after();
+              const uint32_t sw = ring2_base + ws * Cfg::kStage2Bytes;
+              // tap j reads the SAME halo tile, starting (shift_j - shift_0) rows further down
+              const uint32_t a_off = (uint32_t)(p.taps.shift[0][j] - p.taps.shift[0][0]) * (BK * 2);
+              const uint64_t a_hi = make_smem_desc_rows<BK>(sa + a_off, p.halo_bo_mode);
+              const uint64_t w_hi = make_smem_desc<BK>(sw);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)   // +32 B (=2 in >>4 units) per 16-element K step inside the swizzle row
-            umma_bf16(d_tmem, a_hi + 2 * k, w_hi + 2 * k, idesc, (ki | k) != 0);
-          if (NTERMS == 3) {
-            const uint64_t a_lo = make_smem_desc<BK>(sa + Cfg::kABytes);
-            const uint64_t w_lo = make_smem_desc<BK>(sw + Cfg::kWBytes);
+              for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, a_hi + 2 * k, w_hi + 2 * k, idesc, (kc | j | k) != 0);
+              if (NTERMS == 3) {
+                const uint64_t a_lo = make_smem_desc_rows<BK>(sa + Cfg::kAHaloBytes + a_off, p.halo_bo_mode);
+                const uint64_t w_lo = make_smem_desc<BK>(sw + Cfg::kWBytes);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, a_lo + 2 * k, w_hi + 2 * k, idesc, 1u);
+                for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, a_lo + 2 * k, w_hi + 2 * k, idesc, 1u);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, a_hi + 2 * k, w_lo + 2 * k, idesc, 1u);
+                for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, a_hi + 2 * k, w_lo + 2 * k, idesc, 1u);
+              }
+              umma_commit(wempty_bar(ws));
+              if (++ws == S2) { ws = 0; wphase ^= 1u; }
+            }
+            umma_commit(empty_bar(stage));                        // halo tile free once all its taps retired
+            if (kc == k_chunks - 1) umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+            if (++stage == S) { stage = 0; phase ^= 1u; }
           }
-          umma_commit(empty_bar(stage));                    // smem slot free once these MMAs retire
-          if (ki == n_k - 1) umma_commit(tfull_bar(acc));   // accumulator complete -> epilogue
-          if (++stage == S) { stage = 0; phase ^= 1u; }
+        } else {
+          const int n_k = ntaps * k_chunks;
+          for (int ki = 0; ki < n_k; ++ki) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t sa = smem_base + stage * Cfg::kStage1Bytes;
+            const uint32_t sw = sa + Cfg::kPlanes * Cfg::kABytes;
+            const uint64_t a_hi = make_smem_desc<BK>(sa), w_hi = make_smem_desc<BK>(sw);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)   // +32 B (=2 in >>4 units) per 16-element K step inside the swizzle row
+              umma_bf16(d_tmem, a_hi + 2 * k, w_hi + 2 * k, idesc, (ki | k) != 0);
+            if (NTERMS == 3) {
+              const uint64_t a_lo = make_smem_desc<BK>(sa + Cfg::kABytes);
+              const uint64_t w_lo = make_smem_desc<BK>(sw + Cfg::kWBytes);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, a_lo + 2 * k, w_hi + 2 * k, idesc, 1u);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, a_hi + 2 * k, w_lo + 2 * k, idesc, 1u);
+            }
+            umma_commit(empty_bar(stage));                    // smem slot free once these MMAs retire
+            if (ki == n_k - 1) umma_commit(tfull_bar(acc));   // accumulator complete -> epilogue
+            if (++stage == S) { stage = 0; phase ^= 1u; }
+          }
         }
       }
     }
@@ -296,7 +393,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     // ================================ residual TMA producer ================================
     // Streams the fp32 residual tile (B, L, N) as 128-row x 32-column boxes into a ring of slabs that
     // have exactly the epilogue's swizzled slab format (SWIZZLE_128B), kResSlots boxes in flight.
-    if (RES && lane == 0) {
+    if (RES && elect_one()) {
       prefetch_tmap(&tm_res);
       uint32_t rs = 0, rphase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -407,6 +504,12 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
                                         CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                         CUtensorMapFloatOOBfill);
 PFN_tmapEncodeTiled g_encode = nullptr;
+// 0: halo reuse off; 1: on, descriptor base-offset 0; 2: on, base-offset = start row phase.
+// (env SPARKCODEC_HALO overrides; used to validate the descriptor convention on hardware)
+int g_halo_mode = [] {
+  const char* e = getenv("SPARKCODEC_HALO");
+  return e ? atoi(e) : 1;
+}();
 
 int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                const uint32_t* box, int bk, bool weights, bool fp32 = false) {
@@ -427,18 +530,19 @@ int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dim
   return 0;
 }
 
-template <int BLOCK_N, int BK, int NTERMS, bool RES>
+template <int BLOCK_N, int BK, int NTERMS, bool RES, bool HALO>
 int launch_inst(const GemmWeights& w, const OpBuf& a, int batch, int L, const ConvGemmParams& p, int num_sms,
                 cudaStream_t stream) {
-  using Cfg = TileCfg<BLOCK_N, BK, NTERMS, RES>;
+  using Cfg = TileCfg<BLOCK_N, BK, NTERMS, RES, HALO>;
   if constexpr (!Cfg::kValid) {
-    set_error("tile %dx%d (terms %d, residual %d) does not fit shared memory", BLOCK_N, BK, NTERMS, (int)RES);
+    set_error("tile %dx%d (terms %d, residual %d, halo %d) does not fit shared memory", BLOCK_N, BK, NTERMS,
+              (int)RES, (int)HALO);
     return SPARKCODEC_EINVAL;
   } else {
   CUtensorMap ta_hi, ta_lo;
   const uint64_t dims[3] = {(uint64_t)w.c_in, (uint64_t)L, (uint64_t)batch};
   const uint64_t strides[2] = {(uint64_t)w.c_in * 2, (uint64_t)L * w.c_in * 2};
-  const uint32_t box[3] = {(uint32_t)BK, (uint32_t)kBlockM, 1u};
+  const uint32_t box[3] = {(uint32_t)BK, (uint32_t)(HALO ? p.halo_rows : kBlockM), 1u};
   SC_TRY(encode_map(&ta_hi, a.hi, 3, dims, strides, box, BK, false));
   if (NTERMS == 3) SC_TRY(encode_map(&ta_lo, a.lo, 3, dims, strides, box, BK, false));
   else ta_lo = ta_hi;
@@ -449,7 +553,7 @@ int launch_inst(const GemmWeights& w, const OpBuf& a, int batch, int L, const Co
     const uint32_t rbox[3] = {32u, (uint32_t)kBlockM, 1u};
     SC_TRY(encode_map(&t_res, p.residual, 3, rdims, rstr, rbox, 64, false, /*fp32=*/true));
   }
-  auto kern = conv_gemm_tc_kernel<BLOCK_N, BK, NTERMS, RES>;
+  auto kern = conv_gemm_tc_kernel<BLOCK_N, BK, NTERMS, RES, HALO>;
   static bool attr_done = false;   // per instantiation
   if (!attr_done) {
     SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -500,6 +604,14 @@ int choose_bk(int c_in, int block_n, int precision, bool residual) {
   return budget / stage64 >= 3 ? 64 : 32;
 }
 
+// K chunk for the halo mainloop: the W ring must keep >= 3 stages next to 3 halo tiles.
+int choose_bk_halo(int c_in, int block_n, int precision) {
+  if (c_in % 64 != 0) return 32;
+  const int planes = precision == SPARKCODEC_PREC_FP32 ? 2 : 1;
+  const int a64 = planes * align_up(kHaloRowsMax * 64 * 2, 1024), w64 = planes * block_n * 64 * 2;
+  return (192 * 1024 - 3 * a64) / w64 >= 4 ? 64 : 32;
+}
+
 int make_weight_tmaps(GemmWeights& w) {
   SC_TRY(tma_init());
   if (w.c_in % 32 != 0) { set_error("C_in=%d is not a multiple of 32", w.c_in); return SPARKCODEC_EINVAL; }
@@ -527,6 +639,7 @@ int fill_params(const GemmWeights& w, int batch, int L, const Epilogue& ep, int 
   p->m_tiles_per_utt = (L + kBlockM - 1) / kBlockM;
   p->num_m_tiles = batch * p->m_tiles_per_utt;
   p->num_n_tiles = w.n_total / w.block_n;
+  p->halo_rows = 0; p->halo_bo_mode = 0;
   p->bias = w.bias; p->rowbias = ep.rowbias; p->residual = ep.residual;
   p->alpha = ep.alpha; p->inv_alpha = ep.inv_alpha; p->act = ep.act;
   p->out_f32 = ep.out_f32; p->out_hi = ep.out_op.hi;
@@ -540,13 +653,28 @@ int launch_conv_gemm_tc(const GemmWeights& w, const OpBuf& a, int batch, int L, 
   SC_TRY(fill_params(w, batch, L, ep, precision, &p));
   const bool f32 = precision == SPARKCODEC_PREC_FP32;
   const bool res = ep.residual != nullptr;
-  const int bk = choose_bk(w.c_in, w.block_n, precision, res);
-#define SC_INST(BN, BKK)                                                                        \
-  if (w.block_n == BN && bk == BKK)                                                             \
-    return res ? (f32 ? launch_inst<BN, BKK, 3, true>(w, a, batch, L, p, num_sms, stream)       \
-                      : launch_inst<BN, BKK, 1, true>(w, a, batch, L, p, num_sms, stream))      \
-               : (f32 ? launch_inst<BN, BKK, 3, false>(w, a, batch, L, p, num_sms, stream)      \
-                      : launch_inst<BN, BKK, 1, false>(w, a, batch, L, p, num_sms, stream));
+  // halo reuse: single-phase convs with more than one tap (k=7, the embed convs and conv-in)
+  bool halo = g_halo_mode != 0 && w.taps.n_phase == 1 && w.taps.ntaps[0] > 1 && !res;
+  int bk = choose_bk(w.c_in, w.block_n, precision, res);
+  if (halo) {
+    const int span = w.taps.shift[0][w.taps.ntaps[0] - 1] - w.taps.shift[0][0];
+    p.halo_rows = (kBlockM + span + 7) / 8 * 8;
+    p.halo_bo_mode = g_halo_mode == 2 ? 1 : 0;
+    if (p.halo_rows > kHaloRowsMax) halo = false;
+    for (int j = 1; j < w.taps.ntaps[0]; ++j)
+      if (w.taps.shift[0][j] < w.taps.shift[0][j - 1]) halo = false;
+    if (halo) bk = choose_bk_halo(w.c_in, w.block_n, precision);
+  }
+#define SC_INST(BN, BKK)                                                                          \
+  if (w.block_n == BN && bk == BKK) {                                                             \
+    if (halo)                                                                                     \
+      return f32 ? launch_inst<BN, BKK, 3, false, true>(w, a, batch, L, p, num_sms, stream)       \
+                 : launch_inst<BN, BKK, 1, false, true>(w, a, batch, L, p, num_sms, stream);      \
+    return res ? (f32 ? launch_inst<BN, BKK, 3, true, false>(w, a, batch, L, p, num_sms, stream)  \
+                      : launch_inst<BN, BKK, 1, true, false>(w, a, batch, L, p, num_sms, stream)) \
+               : (f32 ? launch_inst<BN, BKK, 3, false, false>(w, a, batch, L, p, num_sms, stream) \
+                      : launch_inst<BN, BKK, 1, false, false>(w, a, batch, L, p, num_sms, stream)); \
+  }
   SC_INST(256, 64) SC_INST(192, 64) SC_INST(128, 64) SC_INST(96, 64) SC_INST(64, 64)
   SC_INST(256, 32) SC_INST(192, 32) SC_INST(128, 32) SC_INST(96, 32) SC_INST(64, 32)
 #undef SC_INST
