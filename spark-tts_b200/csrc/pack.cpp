@@ -78,9 +78,12 @@ void pack_conv_transpose1d(const float* w, int c_in, int c_out, int k, int strid
   out.w_f32.assign((size_t)out.n_total * kt * c_in, 0.f);
   for (int r = 0; r < s; ++r) {
     int base = (r + p) % s, fl = (r + p) / s;
-    for (int m = 0; m < out.taps.ntaps[r]; ++m) {
-      int kk = base + s * m;
-      out.taps.shift[r][m] = fl - m;
+    const int nt = out.taps.ntaps[r];
+    for (int m = 0; m < nt; ++m) {
+      // taps stored with ASCENDING row shift (slot m holds kernel tap nt-1-m) so that the halo mainloop
+      // can address them as increasing row offsets into one A tile
+      int kk = base + s * (nt - 1 - m);
+      out.taps.shift[r][m] = fl - (nt - 1 - m);
       for (int co = 0; co < c_out; ++co)
         for (int ci = 0; ci < c_in; ++ci)
           out.w_f32[((size_t)(r * c_out + co) * kt + m) * c_in + ci] = w[((size_t)ci * c_out + co) * k + kk];

@@ -288,9 +288,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t sa = smem_base + stage * Cfg::kStage1Bytes;
             mbar_expect_tx(full_bar(stage), a_tx);
-            tma_load_3d(sa, &tm_a_hi, full_bar(stage), kc * BK, l0 + p.taps.shift[0][0], b);
+            tma_load_3d(sa, &tm_a_hi, full_bar(stage), kc * BK, l0 + p.taps.shift[ph][0], b);
             if (NTERMS == 3)
-              tma_load_3d(sa + Cfg::kAHaloBytes, &tm_a_lo, full_bar(stage), kc * BK, l0 + p.taps.shift[0][0], b);
+              tma_load_3d(sa + Cfg::kAHaloBytes, &tm_a_lo, full_bar(stage), kc * BK, l0 + p.taps.shift[ph][0], b);
             if (++stage == S) { stage = 0; phase ^= 1u; }
             for (int j = 0; j < ntaps; ++j) {
               mbar_wait(wempty_bar(ws), wphase ^ 1u);
@@ -343,7 +343,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
               tc_fence_after();
               const uint32_t sw = ring2_base + ws * Cfg::kStage2Bytes;
               // tap j reads the SAME halo tile, starting (shift_j - shift_0) rows further down
-              const uint32_t a_off = (uint32_t)(p.taps.shift[0][j] - p.taps.shift[0][0]) * (BK * 2);
+              const uint32_t a_off = (uint32_t)(p.taps.shift[ph][j] - p.taps.shift[ph][0]) * (BK * 2);
               const uint64_t a_hi = make_smem_desc_rows<BK>(sa + a_off, p.halo_bo_mode);
               const uint64_t w_hi = make_smem_desc<BK>(sw);
 #pragma unroll
@@ -439,6 +439,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N; c += 32, ++chunk_ctr) {
         const uint32_t slab = slab_base + (chunk_ctr & 1u) * Cfg::kSlabBytes;
+        // per-column parameters of this lane's 4 columns: issued first so their latency hides behind the
+        // TMEM load, the slab write and the barrier
+        const int n = n0 + c + q4 * 4;
+        float4 bias4, alpha4, inv4;
+        load_col_params4(p, n, bias4, alpha4, inv4);
         {
           uint32_t r[16];
           tmem_ld_x16(t_row + c + 16 * half, r);
@@ -455,9 +460,6 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
           mbar_arrive(tempty_bar(acc));
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-        const int n = n0 + c + q4 * 4;
-        float4 bias4, alpha4, inv4;
-        load_col_params4(p, n, bias4, alpha4, inv4);
         uint32_t rslab = 0;
         if (RES) {
           rslab = res_base + rs * Cfg::kSlabBytes;
@@ -653,17 +655,22 @@ int launch_conv_gemm_tc(const GemmWeights& w, const OpBuf& a, int batch, int L, 
   SC_TRY(fill_params(w, batch, L, ep, precision, &p));
   const bool f32 = precision == SPARKCODEC_PREC_FP32;
   const bool res = ep.residual != nullptr;
-  // halo reuse: single-phase convs with more than one tap (k=7, the embed convs and conv-in)
-  bool halo = g_halo_mode != 0 && w.taps.n_phase == 1 && w.taps.ntaps[0] > 1 && !res;
+  // halo reuse: every conv with more than one tap (k=7 convs, conv-in, embed convs, polyphase up-samplers)
+  int max_taps = 0, span = 0;
+  bool ascending = true;
+  for (int r = 0; r < w.taps.n_phase; ++r) {
+    const int nt = w.taps.ntaps[r];
+    max_taps = nt > max_taps ? nt : max_taps;
+    if (nt > 0 && w.taps.shift[r][nt - 1] - w.taps.shift[r][0] > span) span = w.taps.shift[r][nt - 1] - w.taps.shift[r][0];
+    for (int j = 1; j < nt; ++j) ascending &= w.taps.shift[r][j] > w.taps.shift[r][j - 1];
+  }
+  bool halo = g_halo_mode != 0 && max_taps > 1 && ascending && !res;
   int bk = choose_bk(w.c_in, w.block_n, precision, res);
   if (halo) {
-    const int span = w.taps.shift[0][w.taps.ntaps[0] - 1] - w.taps.shift[0][0];
     p.halo_rows = (kBlockM + span + 7) / 8 * 8;
-    p.halo_bo_mode = g_halo_mode == 2 ? 1 : 0;
+    p.halo_bo_mode = 0;
     if (p.halo_rows > kHaloRowsMax) halo = false;
-    for (int j = 1; j < w.taps.ntaps[0]; ++j)
-      if (w.taps.shift[0][j] < w.taps.shift[0][j - 1]) halo = false;
-    if (halo) bk = choose_bk_halo(w.c_in, w.block_n, precision);
+    else bk = choose_bk_halo(w.c_in, w.block_n, precision);
   }
 #define SC_INST(BN, BKK)                                                                          \
   if (w.block_n == BN && bk == BKK) {                                                             \
