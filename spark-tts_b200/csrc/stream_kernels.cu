@@ -5,6 +5,8 @@
 //   * small_linear             tiny per-utterance Linear layers (speaker project, AdaLN scale/shift)
 //   * dwconv_ln                depthwise k=7 conv + LayerNorm / AdaLayerNorm, smem halo staging
 //   * head                     Snake -> Conv1d(C->1, k=7) -> tanh, warp-shuffle channel reduction
+#include <algorithm>
+
 #include "common.cuh"
 #include "gemm_params.cuh"
 
@@ -166,77 +168,104 @@ __global__ void small_linear_kernel(const float* __restrict__ x, const float* __
 // C/32 channels as float4s, so the row statistics are two warp-shuffle reductions.
 constexpr int kLnRows = 16;
 
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;   // src-size 0 => 16 zero bytes (the conv's zero padding)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+
+// Persistent CTAs; every CTA walks row tiles with a two-deep cp.async pipeline: tile i+1 streams into
+// the other smem buffer while tile i is normalised.
 template <int NV, bool DW>
 __global__ void __launch_bounds__(256)
 dwconv_ln_kernel(const float* __restrict__ x, int rows, const float* __restrict__ dw_w /* [7][C] */,
                  const float* __restrict__ dw_b, const float* __restrict__ scale, const float* __restrict__ shift,
-                 int ss_stride, float eps, float* __restrict__ out_f32, OpBuf out_op, int tiles_per_utt) {
+                 int ss_stride, float eps, float* __restrict__ out_f32, OpBuf out_op, int tiles_per_utt,
+                 int total_tiles) {
   constexpr int C = NV * 128;
   constexpr int HALO = DW ? 3 : 0;
-  extern __shared__ __align__(16) float s_x[];   // [(kLnRows + 2*HALO)][C]
-  const int b = blockIdx.x / tiles_per_utt;
-  const int r0 = (blockIdx.x % tiles_per_utt) * kLnRows;
-  const float* xb = x + (size_t)b * rows * C;
-
+  constexpr int TROWS = kLnRows + 2 * HALO;
   constexpr int C4 = C / 4;
-  for (int i = threadIdx.x; i < (kLnRows + 2 * HALO) * C4; i += blockDim.x) {
-    const int rr = i / C4, c4 = i % C4;
-    const int r = r0 + rr - HALO;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r >= 0 && r < rows) v = __ldg(reinterpret_cast<const float4*>(xb + (size_t)r * C) + c4);
-    reinterpret_cast<float4*>(s_x)[i] = v;
-  }
-  __syncthreads();
-
+  extern __shared__ __align__(16) float s_buf[];   // [2][TROWS][C]
+  const uint32_t s_base = static_cast<uint32_t>(__cvta_generic_to_shared(s_buf));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int rr = warp; rr < kLnRows; rr += 8) {
-    const int r = r0 + rr;
-    if (r >= rows) break;
-    float4 y[NV];
+
+  auto issue = [&](int tile, int buf) {
+    const int b = tile / tiles_per_utt;
+    const int r0 = (tile % tiles_per_utt) * kLnRows;
+    const float* xb = x + (size_t)b * rows * C;
+    for (int i = threadIdx.x; i < TROWS * C4; i += blockDim.x) {
+      const int rr = i / C4, c4 = i % C4;
+      const int r = r0 + rr - HALO;
+      const bool ok = r >= 0 && r < rows;
+      cp_async16(s_base + (uint32_t)((buf * TROWS * C4 + i) * 16), xb + (size_t)(ok ? r : 0) * C + c4 * 4, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  int tile = blockIdx.x, buf = 0;
+  if (tile < total_tiles) issue(tile, 0);
+  for (; tile < total_tiles; tile += gridDim.x, buf ^= 1) {
+    const int nxt = tile + gridDim.x;
+    if (nxt < total_tiles) {
+      issue(nxt, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const float* s_x = s_buf + buf * TROWS * C;
+    const int b = tile / tiles_per_utt;
+    const int r0 = (tile % tiles_per_utt) * kLnRows;
+    for (int rr = warp; rr < kLnRows; rr += 8) {
+      const int r = r0 + rr;
+      if (r >= rows) break;
+      float4 y[NV];
 #pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      const int c = v * 128 + lane * 4;
-      if (DW) {
-        float4 a = __ldg(reinterpret_cast<const float4*>(dw_b + c));
+      for (int v = 0; v < NV; ++v) {
+        const int c = v * 128 + lane * 4;
+        if (DW) {
+          float4 a = __ldg(reinterpret_cast<const float4*>(dw_b + c));
 #pragma unroll
-        for (int j = 0; j < 7; ++j) {
-          const float4 w = __ldg(reinterpret_cast<const float4*>(dw_w + j * C + c));
-          const float4 s = *reinterpret_cast<const float4*>(s_x + (rr + j) * C + c);
-          a.x = fmaf(w.x, s.x, a.x); a.y = fmaf(w.y, s.y, a.y);
-          a.z = fmaf(w.z, s.z, a.z); a.w = fmaf(w.w, s.w, a.w);
+          for (int j = 0; j < 7; ++j) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(dw_w + j * C + c));
+            const float4 s = *reinterpret_cast<const float4*>(s_x + (rr + j) * C + c);
+            a.x = fmaf(w.x, s.x, a.x); a.y = fmaf(w.y, s.y, a.y);
+            a.z = fmaf(w.z, s.z, a.z); a.w = fmaf(w.w, s.w, a.w);
+          }
+          y[v] = a;
+        } else {
+          y[v] = *reinterpret_cast<const float4*>(s_x + rr * C + c);
         }
-        y[v] = a;
-      } else {
-        y[v] = *reinterpret_cast<const float4*>(s_x + rr * C + c);
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) sum += (y[v].x + y[v].y) + (y[v].z + y[v].w);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float mean = sum * (1.0f / C);
+      float sq = 0.f;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        y[v].x -= mean; y[v].y -= mean; y[v].z -= mean; y[v].w -= mean;
+        sq += (y[v].x * y[v].x + y[v].y * y[v].y) + (y[v].z * y[v].z + y[v].w * y[v].w);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      const float rstd = rsqrtf(sq * (1.0f / C) + eps);
+      const size_t row_off = ((size_t)b * rows + r) * C;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int c = v * 128 + lane * 4;
+        const float4 g = __ldg(reinterpret_cast<const float4*>(scale + (size_t)b * ss_stride + c));
+        const float4 h = __ldg(reinterpret_cast<const float4*>(shift + (size_t)b * ss_stride + c));
+        float4 o;
+        o.x = fmaf(y[v].x * rstd, g.x, h.x); o.y = fmaf(y[v].y * rstd, g.y, h.y);
+        o.z = fmaf(y[v].z * rstd, g.z, h.z); o.w = fmaf(y[v].w * rstd, g.w, h.w);
+        if (out_f32) *reinterpret_cast<float4*>(out_f32 + row_off + c) = o;
+        if (out_op.hi) store_op4(out_op, row_off + c, o);
       }
     }
-    float sum = 0.f;
-#pragma unroll
-    for (int v = 0; v < NV; ++v) sum += (y[v].x + y[v].y) + (y[v].z + y[v].w);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float mean = sum * (1.0f / C);
-    float sq = 0.f;
-#pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      y[v].x -= mean; y[v].y -= mean; y[v].z -= mean; y[v].w -= mean;
-      sq += (y[v].x * y[v].x + y[v].y * y[v].y) + (y[v].z * y[v].z + y[v].w * y[v].w);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    const float rstd = rsqrtf(sq * (1.0f / C) + eps);
-    const size_t row_off = ((size_t)b * rows + r) * C;
-#pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      const int c = v * 128 + lane * 4;
-      const float4 g = __ldg(reinterpret_cast<const float4*>(scale + (size_t)b * ss_stride + c));
-      const float4 h = __ldg(reinterpret_cast<const float4*>(shift + (size_t)b * ss_stride + c));
-      float4 o;
-      o.x = fmaf(y[v].x * rstd, g.x, h.x); o.y = fmaf(y[v].y * rstd, g.y, h.y);
-      o.z = fmaf(y[v].z * rstd, g.z, h.z); o.w = fmaf(y[v].w * rstd, g.w, h.w);
-      if (out_f32) *reinterpret_cast<float4*>(out_f32 + row_off + c) = o;
-      if (out_op.hi) store_op4(out_op, row_off + c, o);
-    }
+    __syncthreads();   // everyone is done with this buffer before the next-but-one tile streams into it
   }
 }
 
@@ -244,12 +273,15 @@ dwconv_ln_kernel(const float* __restrict__ x, int rows, const float* __restrict_
 // wav[b, l] = tanh(bias + sum_j sum_c w[j, c] * snake(x[b, l + j - 3, c]))     (wave_generator.py:77-81)
 // A warp walks a run of kHeadRun consecutive samples of one utterance: every lane owns C/32 channels,
 // streams the rows straight from HBM with coalesced loads (each element is read and Snake'd once per
-// run, 6 halo rows per run), keeps the 7-row window in registers and reduces the C partial products
-// of every sample with warp shuffles.  Results are written back as coalesced 128 B lines.
+// run, 6 halo rows per run, 8 rows of loads in flight per lane) and keeps the 7-row window in registers.
+// The per-lane partial sums of 32 consecutive samples are transposed through a padded per-warp smem
+// tile (one st.shared + one ld.shared per sample instead of a 5-step shuffle tree per sample); lane L
+// ends up with sample L, so the stores are coalesced 128 B lines.
 constexpr int kHeadRun = 128;
+constexpr int kHeadWarps = 4;   // 144 registers/thread: 4-warp CTAs keep 3 CTAs (12 warps) resident per SM
 
 template <int NCH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kHeadWarps * 32)
 head_kernel(const float* __restrict__ x, int rows, const float* __restrict__ alpha,
             const float* __restrict__ inv_alpha, const float* __restrict__ w /* [7][C] */, float bias,
             float* __restrict__ wav, int runs_per_utt, int total_runs) {
@@ -278,38 +310,56 @@ head_kernel(const float* __restrict__ x, int rows, const float* __restrict__ alp
   };
   float win[7][NCH];   // win[j] = snake(x[l + j - 3])
 #pragma unroll
+  for (int k = 0; k < NCH; ++k) win[0][k] = 0.f;
+#pragma unroll
   for (int j = 0; j < 6; ++j) {
     load_row(l0 + j - 3, win[j + 1]);
     act_row(l0 + j - 3, win[j + 1]);
   }
-  float keep = 0.f;
   const int l_end = min(l0 + kHeadRun, rows);
-  for (int l = l0; l < l_end; l += 4) {
-    float nxt[4][NCH];
+  __shared__ float s_part[kHeadWarps][32][33];   // per warp: [sample][lane] partial sums (+1 pad: conflict-free both ways)
+  float(*sp)[33] = s_part[threadIdx.x >> 5];
+  // Software pipeline over groups of 8 rows: while group g is Snake'd and convolved, the 8 rows of group
+  // g+1 are already in flight (two register buffers, loop unrolled by two so no buffer copies).
+  float bufA[8][NCH], bufB[8][NCH];
+  auto load_group = [&](int gi, float (&dst)[8][NCH]) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) load_row(l + u + 3, nxt[u]);   // 4 rows of loads in flight
+    for (int u = 0; u < 8; ++u) load_row(l0 + gi * 8 + u + 3, dst[u]);
+  };
+  auto compute_group = [&](int gi, float (&src)[8][NCH]) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      act_row(l + u + 3, nxt[u]);
+    for (int u = 0; u < 8; ++u) {
+      act_row(l0 + gi * 8 + u + 3, src[u]);
 #pragma unroll
       for (int j = 0; j < 6; ++j)
 #pragma unroll
         for (int k = 0; k < NCH; ++k) win[j][k] = win[j + 1][k];
 #pragma unroll
-      for (int k = 0; k < NCH; ++k) win[6][k] = nxt[u][k];
+      for (int k = 0; k < NCH; ++k) win[6][k] = src[u][k];
       float s = 0.f;
 #pragma unroll
       for (int j = 0; j < 7; ++j)
 #pragma unroll
         for (int k = 0; k < NCH; ++k) s = fmaf(wt[j][k], win[j][k], s);
+      sp[(gi & 3) * 8 + u][lane] = s;
+    }
+  };
+  constexpr int kGroups = kHeadRun / 8;
+  load_group(0, bufA);
+#pragma unroll 1
+  for (int gp = 0; gp < kGroups; gp += 2) {
+    load_group(gp + 1, bufB);
+    compute_group(gp, bufA);
+    if (gp + 2 < kGroups) load_group(gp + 2, bufA);
+    compute_group(gp + 1, bufB);
+    if ((gp & 2) != 0) {   // 32 samples done: transpose-reduce through shared memory, lane L gets sample L
+      __syncwarp();
+      float tot = 0.f;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      const int ll = l + u;
-      if (lane == (ll & 31)) keep = s;
-      if ((ll & 31) == 31 || ll == l_end - 1) {
-        const int base = ll & ~31;
-        if (base + lane <= ll && base + lane < rows) wav[(size_t)b * rows + base + lane] = tanhf(keep + bias);
-      }
+      for (int j = 0; j < 32; ++j) tot += sp[lane][j];
+      __syncwarp();
+      const int l = l0 + (gp - 2) * 8 + lane;
+      if (l < l_end) wav[(size_t)b * rows + l] = tanhf(tot + bias);
     }
   }
 }
@@ -368,25 +418,33 @@ template <int NV>
 static int launch_dwconv_ln_t(const float* x, int batch, int rows, const float* dw_w, const float* dw_b,
                               const float* scale, const float* shift, int ss, float eps, float* out_f32,
                               OpBuf out_op, cudaStream_t s) {
-  const int tiles = (rows + kLnRows - 1) / kLnRows;
+  const int tiles = (rows + kLnRows - 1) / kLnRows, total = batch * tiles;
   const bool dw = dw_w != nullptr;
-  const size_t smem = (size_t)(kLnRows + (dw ? 6 : 0)) * NV * 128 * sizeof(float);
+  const size_t smem = 2 * (size_t)(kLnRows + (dw ? 6 : 0)) * NV * 128 * sizeof(float);
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    SC_CUDA(cudaGetDevice(&dev));
+    SC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / smem));
+  const int grid = std::min(total, num_sms * per_sm);
   if (dw) {
     static bool done = false;
     if (!done) {
-      SC_CUDA(cudaFuncSetAttribute(dwconv_ln_kernel<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      SC_CUDA(cudaFuncSetAttribute(dwconv_ln_kernel<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       done = true;
     }
-    dwconv_ln_kernel<NV, true><<<batch * tiles, 256, smem, s>>>(x, rows, dw_w, dw_b, scale, shift, ss, eps, out_f32,
-                                                               out_op, tiles);
+    dwconv_ln_kernel<NV, true><<<grid, 256, smem, s>>>(x, rows, dw_w, dw_b, scale, shift, ss, eps, out_f32, out_op,
+                                                       tiles, total);
   } else {
     static bool done = false;
     if (!done) {
-      SC_CUDA(cudaFuncSetAttribute(dwconv_ln_kernel<NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      SC_CUDA(cudaFuncSetAttribute(dwconv_ln_kernel<NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       done = true;
     }
-    dwconv_ln_kernel<NV, false><<<batch * tiles, 256, smem, s>>>(x, rows, dw_w, dw_b, scale, shift, ss, eps, out_f32,
-                                                                out_op, tiles);
+    dwconv_ln_kernel<NV, false><<<grid, 256, smem, s>>>(x, rows, dw_w, dw_b, scale, shift, ss, eps, out_f32, out_op,
+                                                        tiles, total);
   }
   SC_LAUNCH_CHECK();
   return 0;
@@ -406,12 +464,12 @@ int launch_dwconv_ln(const float* x, int batch, int rows, int c, const float* dw
 int launch_head(const float* x, int batch, int rows, int c, const float* alpha, const float* inv_alpha,
                 const float* w, float bias, float* wav, int, int, cudaStream_t s) {
   const int runs = (rows + kHeadRun - 1) / kHeadRun, total = batch * runs;
-  const int grid = (total + 7) / 8;
+  const int grid = (total + kHeadWarps - 1) / kHeadWarps, blk = kHeadWarps * 32;
   switch (c) {
-    case 32: head_kernel<1><<<grid, 256, 0, s>>>(x, rows, alpha, inv_alpha, w, bias, wav, runs, total); break;
-    case 64: head_kernel<2><<<grid, 256, 0, s>>>(x, rows, alpha, inv_alpha, w, bias, wav, runs, total); break;
-    case 96: head_kernel<3><<<grid, 256, 0, s>>>(x, rows, alpha, inv_alpha, w, bias, wav, runs, total); break;
-    case 128: head_kernel<4><<<grid, 256, 0, s>>>(x, rows, alpha, inv_alpha, w, bias, wav, runs, total); break;
+    case 32: head_kernel<1><<<grid, blk, 0, s>>>(x, rows, alpha, inv_alpha, w, bias, wav, runs, total); break;
+    case 64: head_kernel<2><<<grid, blk, 0, s>>>(x, rows, alpha, inv_alpha, w, bias, wav, runs, total); break;
+    case 96: head_kernel<3><<<grid, blk, 0, s>>>(x, rows, alpha, inv_alpha, w, bias, wav, runs, total); break;
+    case 128: head_kernel<4><<<grid, blk, 0, s>>>(x, rows, alpha, inv_alpha, w, bias, wav, runs, total); break;
     default: set_error("head: unsupported channel count %d (32/64/96/128)", c); return SPARKCODEC_EINVAL;
   }
   SC_LAUNCH_CHECK();
