@@ -269,8 +269,11 @@ def main():
                         "3 bf16 MMAs per algorithmic MAC (tensor_work_factor)"}
             stream = {}
             for r in rows:
-                if r["name"] in ("head", "dwconv_ln", "ln"):
-                    a = stream.setdefault(r["name"], dict(ms=0.0, bytes=0.0, n=0))
+                key = r["name"] if r["name"] in ("head", "dwconv_ln", "ln") else None
+                if r["name"].startswith("conv_gemm_tc") and " taps=1 " in r["name"] and r["name"].endswith("res=1"):
+                    key = "conv1x1_residual (conv_gemm_tc, HBM-bound class)"
+                if key:
+                    a = stream.setdefault(key, dict(ms=0.0, bytes=0.0, n=0))
                     a["ms"] += r["ms"]; a["bytes"] += r["bytes"]; a["n"] += 1
             line["hbm_kernels"] = {k: {"launches": v["n"], "achieved_gbs": v["bytes"] / (v["ms"] * 1e-3) / 1e9,
                                        "frac": v["bytes"] / (v["ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"],

@@ -479,8 +479,8 @@ struct Pass {
       if (ep.out_f32) bytes += (double)B * L * w.n_total * 4;
       if (ep.out_op.hi) bytes += (double)B * L * w.n_total * planes;
       char nm[160];
-      snprintf(nm, sizeof(nm), "conv_gemm_tc cin=%d n=%d phases=%d taps=%d L=%d bn=%d bk=%d act=%d", w.c_in, w.n_total,
-               w.taps.n_phase, tmax, L, w.block_n, choose_bk(w.c_in, w.block_n, prec, ep.residual != nullptr), ep.act);
+      snprintf(nm, sizeof(nm), "conv_gemm_tc cin=%d n=%d phases=%d taps=%d L=%d bn=%d act=%d res=%d", w.c_in, w.n_total,
+               w.taps.n_phase, tmax, L, w.block_n, ep.act, ep.residual != nullptr ? 1 : 0);
       SC_TRY(prof_begin(nm, 2.0 * B * L * macs, bytes));
     }
     int rc = h->impl == SPARKCODEC_IMPL_SIMT ? launch_conv_gemm_simt(w, a, B, L, ep, prec, st)
