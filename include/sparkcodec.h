@@ -48,9 +48,11 @@ enum { SPARKCODEC_I32 = 0, SPARKCODEC_I64 = 1 };
  *   BF16 : single bf16 product, fp32 accumulate (looser stated bound)            */
 enum { SPARKCODEC_PREC_FP32 = 0, SPARKCODEC_PREC_BF16 = 1 };
 
-/* which implementation of the dense contraction runs: tcgen05 tensor cores (product path) or the
- * CUDA-core verification kernel with the same operands/epilogue (tests only). */
-enum { SPARKCODEC_IMPL_TC = 0, SPARKCODEC_IMPL_SIMT = 1 };
+/* which implementation of the dense contractions runs: tcgen05 tensor cores (product path: one kernel
+ * per conv, the narrow ResidualUnits as ONE fused kernel each), the CUDA-core verification kernel with
+ * the same operands/epilogue (tests only), or tcgen05 with the ResidualUnit fusion switched off
+ * (tests / A-B timing only). */
+enum { SPARKCODEC_IMPL_TC = 0, SPARKCODEC_IMPL_SIMT = 1, SPARKCODEC_IMPL_TC_UNFUSED = 2 };
 
 /* Mirrors the `audio_tokenizer` section of BiCodec/config.yaml consumed by
  * BiCodec.load_from_checkpoint (sparktts/models/bicodec.py:81-88). */

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libsparkcodec.so")
 OK, EINVAL, EINDEX, ECUDA, ESTATE, ENOMEM, EMISSING = 0, -1, -2, -3, -4, -5, -6
 I32, I64 = 0, 1
 PREC_FP32, PREC_BF16 = 0, 1
-IMPL_TC, IMPL_SIMT = 0, 1
+IMPL_TC, IMPL_SIMT, IMPL_TC_UNFUSED = 0, 1, 2
 ACT_NONE, ACT_GELU, ACT_SNAKE = 0, 1, 2
 
 PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16}

@@ -234,12 +234,12 @@ class BiCodec:
     # ------------------------------------------------------------------ test / profiling hooks
     def set_impl(self, impl: str) -> None:
         """'tc' (tcgen05, the product path) or 'simt' (CUDA-core verification kernels, tests only)."""
-        if impl not in ("tc", "simt"):
-            raise ValueError("impl must be 'tc' or 'simt'")
+        if impl not in ("tc", "simt", "tc_unfused"):
+            raise ValueError("impl must be 'tc', 'simt' or 'tc_unfused'")
         self._impl = impl
         if self._handle is not None:
             _lib.check(_lib.load().sparkcodec_set_impl(
-                self._handle, _lib.IMPL_TC if impl == "tc" else _lib.IMPL_SIMT))
+                self._handle, {"tc": _lib.IMPL_TC, "simt": _lib.IMPL_SIMT, "tc_unfused": _lib.IMPL_TC_UNFUSED}[impl]))
 
     @torch.no_grad()
     def detokenize_tap(self, semantic_tokens, global_tokens, tap: str, precision: Optional[str] = None):

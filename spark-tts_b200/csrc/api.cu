@@ -622,6 +622,25 @@ static int run_pass(Pass& P, const void* sem, int sem_dt, const void* glob, int 
     SC_TRY(P.tap_f32((name + ".1").c_str(), W.x, L, ub.c_out));
     for (int j = 0; j < 3; ++j) {
       ResUnit& ru = ub.ru[j];
+      const bool last_unit = (i + 1 == h->ups.size()) && j == 2;
+      int dil = 0;
+      if (h->impl == SPARKCODEC_IMPL_TC && resunit_fusable(ru.c7, ru.c1, &dil)) {
+        // narrow stages: the whole ResidualUnit is one kernel, `mid` never reaches HBM
+        if (h->profile) {
+          const double planes = prec == SPARKCODEC_PREC_FP32 ? 4.0 : 2.0, C = ub.c_out;
+          char nm[160];
+          snprintf(nm, sizeof(nm), "resunit_fused c=%d dil=%d L=%d", ub.c_out, dil, L);
+          SC_TRY(P.prof_begin(nm, 2.0 * B * L * 8.0 * C * C,
+                              (double)B * L * C * (planes + 8.0 + (last_unit ? 0.0 : planes)) + 8.0 * C * C * planes));
+        }
+        SC_TRY(launch_resunit_fused(ru.c7, ru.c1, op1[pp], B, L, ru.s_mid.alpha, ru.s_mid.inv, W.x,
+                                    last_unit ? nullptr : ru.s_next.alpha, last_unit ? nullptr : ru.s_next.inv,
+                                    last_unit ? OpBuf() : op1[pp ^ 1], prec, h->num_sms, st));
+        SC_TRY(P.prof_end());
+        pp ^= 1;
+        SC_TRY(P.tap_f32((name + "." + std::to_string(j + 2)).c_str(), W.x, L, ub.c_out));
+        continue;
+      }
       Epilogue e7;
       e7.act = ACT_SNAKE; e7.alpha = ru.s_mid.alpha; e7.inv_alpha = ru.s_mid.inv;
       e7.out_op = op2;
@@ -840,7 +859,10 @@ int sparkcodec_check_tokens(sparkcodec_handle* h, void* stream) {
 }
 
 int sparkcodec_set_impl(sparkcodec_handle* h, int impl) {
-  if (!h || (impl != SPARKCODEC_IMPL_TC && impl != SPARKCODEC_IMPL_SIMT)) { set_error("bad impl"); return SPARKCODEC_EINVAL; }
+  if (!h || (impl != SPARKCODEC_IMPL_TC && impl != SPARKCODEC_IMPL_SIMT && impl != SPARKCODEC_IMPL_TC_UNFUSED)) {
+    set_error("bad impl");
+    return SPARKCODEC_EINVAL;
+  }
   h->impl = impl;
   return 0;
 }

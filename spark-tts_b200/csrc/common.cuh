@@ -95,6 +95,13 @@ int launch_conv_gemm_tc(const GemmWeights& w, const OpBuf& a, int batch, int L, 
 int launch_conv_gemm_simt(const GemmWeights& w, const OpBuf& a, int batch, int L, const Epilogue& ep,
                           int precision, cudaStream_t stream);
 
+// Fused ResidualUnit (k7 dilated conv -> Snake -> 1x1 conv -> + x -> Snake) for C in {96, 192}; x is updated
+// in place, `out` (optional) receives snake_out(x) as operand planes.  ru_fused.cu
+bool resunit_fusable(const GemmWeights& c7, const GemmWeights& c1, int* dil);
+int launch_resunit_fused(const GemmWeights& c7, const GemmWeights& c1, const OpBuf& a, int batch, int L,
+                         const float* alpha_mid, const float* inv_mid, float* x, const float* alpha_out,
+                         const float* inv_out, OpBuf out, int precision, int num_sms, cudaStream_t stream);
+
 // streaming / token kernels
 int launch_split(const float* x, OpBuf out, size_t n, cudaStream_t s);                 // fp32 -> hi/lo
 int launch_merge(const OpBuf& in, float* out, size_t n, cudaStream_t s);               // hi(+lo) -> fp32
