@@ -10,9 +10,12 @@
 // Un-fused, the k7 conv writes `mid` to HBM and the 1x1 conv reads it back; at C <= 192 the 1x1 conv is
 // purely HBM-bound (16 B per output element).  Here `mid` never leaves the SM:
 //
-//   TMEM acc1 (k7 result) --epilogue warps: +b7, Snake, bf16 hi/lo split--> smem K-major SWIZZLE_64B chunks
-//        --tcgen05.mma (A = mid chunk, B = W1 chunk, split-K over the chunks)--> TMEM acc2
-//        --epilogue warps: + residual slab (TMA) + b1, store x, Snake, store operand planes.
+//   TMEM acc1 (k7 result) --mid warps: tcgen05.ld, +b7, Snake, bf16 hi/lo split, tcgen05.st IN PLACE--> the 32 fp32
+//        columns of a chunk become 16 columns of packed bf16 hi + 16 columns of packed bf16 lo
+//        --tcgen05.mma with the A operand in TENSOR MEMORY (B = W1 chunk from smem, split-K over chunks)--> acc2
+//        --final warps: + residual slab (TMA) + b1, store x, Snake, store operand planes.
+// Keeping `mid` in TMEM leaves the whole shared memory to the operand rings: the weight ring has to cover the
+// ~2k-cycle refill round trip (MMA done -> commit -> producer -> TMA from L2 -> full), see DESIGN.md.
 //
 // Roles (352 threads, one persistent CTA per SM):
 //   warp 0 / one lane : TMA producer: activation halo tiles (one per K group, shared by the 7 taps through
@@ -22,6 +25,10 @@
 //   warp 10 / one lane: residual TMA producer (fp32 128 x 32 slabs, SWIZZLE_128B)
 // C = 96 keeps two acc1 and two acc2 buffers in TMEM and skews the 1x1 conv by one tile (SKEW = 1) so the
 // tensor pipe never waits for the mid stage; C = 192 (acc1 + acc2 = 384 columns) runs un-skewed.
+#include <algorithm>
+#include <cstdlib>
+#include <vector>
+
 #include "gemm_params.cuh"
 #include "tc_ptx.cuh"
 
@@ -30,12 +37,23 @@ namespace {
 
 constexpr int kRuHaloRowsMax = 184;                 // 128 + 6 * 9, multiple of 8
 constexpr int kRuAChunkBytes = 12 * 1024;           // 184 rows x 64 B, rounded up to 1024
-constexpr int kRuMidChunkBytes = kBlockM * 64;      // 128 rows x 32 bf16 (one plane)
 constexpr int kRuSlabBytes = kBlockM * 128;         // 128 rows x 32 fp32
-constexpr int kRuEpiWarps = 8;
-constexpr int kRuEpiThreads = kRuEpiWarps * 32;
-constexpr int kRuResWarp = 2 + kRuEpiWarps;
-constexpr int kRuThreads = (3 + kRuEpiWarps) * 32;
+// warp roles: 0..7 mid team, 8..15 final team, 16 / 17 / 18 TMA producers (residual, activations, weights),
+// 19 MMA issuer.
+// The warp scheduler favours the highest warp id among eligible warps, so the single-thread roles that
+// feed the tensor pipe sit ABOVE the 16 epilogue warps (which spend much of their time polling mbarriers).
+// A warp may only read the TMEM lane quarter warp_id % 4: both teams start at a multiple of 4, so
+// `warp & 3` enumerates the four quarters twice per team.
+constexpr int kRuTeamWarps = 8;
+constexpr int kRuTeamThreads = kRuTeamWarps * 32;
+constexpr int kRuMidWarp0 = 0;
+constexpr int kRuFinWarp0 = kRuMidWarp0 + kRuTeamWarps;
+constexpr int kRuResWarp = kRuFinWarp0 + kRuTeamWarps;   // residual slabs
+constexpr int kRuTmaAWarp = kRuResWarp + 1;              // activation halo tiles
+constexpr int kRuTmaWWarp = kRuTmaAWarp + 1;             // W7 / W1 tiles
+constexpr int kRuMmaWarp = kRuTmaWWarp + 1;
+constexpr int kRuThreads = (kRuMmaWarp + 1) * 32;
+constexpr int kRuMidArrivals = kRuTeamThreads / 2;   // a mid chunk is written by one warp per lane quarter
 
 struct RuParams {
   int batch, L, dil, halo_rows;
@@ -44,7 +62,9 @@ struct RuParams {
   const float *bias1, *alpha_out, *inv_out;   // [C]; alpha_out/inv_out unused when out_hi == null
   float* x;                                   // (batch, L, C) fp32, read as residual and overwritten
   __nv_bfloat16 *out_hi, *out_lo;             // (batch, L, C) operand planes of the next layer (optional)
+  long long* dbg;                             // SPARKCODEC_RU_TRACE: per-tile event clocks of CTA 0 (else null)
 };
+constexpr int kRuTraceEvents = 32, kRuTraceTiles = 16;
 
 template <int C, int NTERMS>
 struct RuCfg {
@@ -55,21 +75,23 @@ struct RuCfg {
   static constexpr int kAStage = G * kPlanes * kRuAChunkBytes;
   static constexpr int kWChunk = C * 64;                           // C rows x 64 B (one plane)
   static constexpr int kWStage = G * kPlanes * kWChunk;
-  static constexpr int kMidSlot = kPlanes * kRuMidChunkBytes;
   static constexpr int NB1 = C <= 96 ? 2 : 1;                      // acc1 / acc2 buffers in TMEM
   static constexpr int NB2 = NB1;
   static constexpr int SKEW = NB1 - 1;
   // ring depths (227 KB budget)
-  static constexpr int SA = (NTERMS == 3) ? (C <= 96 ? 3 : 2) : (C <= 96 ? 2 : 3);
-  static constexpr int SW = (C <= 96) ? 4 : 3;
-  static constexpr int SM = (NTERMS == 3) ? (C <= 96 ? 4 : 3) : 4;
-  static constexpr int SR = (NTERMS == 3 && C > 96) ? 3 : 2;
+  static constexpr int SA = (NTERMS == 3) ? 2 : (C <= 96 ? 2 : 3);
+  static constexpr int SR = 3;
   static constexpr int kParBytes = 3 * C * 4;
-  static constexpr int kNumBars = 2 * SA + 2 * SW + 2 * SM + NB1 + 2 * NB2 + 2 * SR;
-  static constexpr int kSmemBytes = SA * kAStage + SW * kWStage + SM * kMidSlot + SR * kRuSlabBytes + kParBytes +
-                                    kNumBars * 8 + 16 + 1024 /* alignment */;
+  static constexpr int kFixed = SA * kAStage + SR * kRuSlabBytes + kParBytes + 1024 /* barriers */ + 1024 /* alignment */;
+  static constexpr int SWRaw = (227 * 1024 - kFixed) / kWStage;
+  static constexpr int SW = SWRaw > 12 ? 12 : SWRaw;
+  static constexpr int kNumMid = NB1 * kChunks;                    // one "chunk converted" barrier per (acc1 buffer, chunk)
+  static constexpr int kNumBars = 2 * SA + 2 * SW + kNumMid + NB1 + 2 * NB2 + 2 * SR;
+  static constexpr int kSmemBytes = SA * kAStage + SW * kWStage + SR * kRuSlabBytes + kParBytes + kNumBars * 8 + 16 +
+                                    1024 /* alignment */;
+  static_assert(kNumBars * 8 + 16 <= 1024, "barrier block larger than budgeted");
+  static_assert(SW >= 3, "weight ring too shallow");
   static_assert(kChunks % G == 0, "K groups must tile the channels");
-  static_assert(SM >= G + SKEW, "mid ring too shallow");
   static_assert((NB1 + NB2) * C <= 512, "accumulators must fit TMEM");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
   static_assert(kWChunk % 1024 == 0, "weight chunks must stay 1024 B aligned");
@@ -78,49 +100,68 @@ struct RuCfg {
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat162 v) { return *reinterpret_cast<uint32_t*>(&v); }
+// event trace of CTA 0 (debug builds of the schedule; dbg is null in normal runs)
+__device__ __forceinline__ void ru_trace(const RuParams& p, int tile_it, int ev) {
+  if (p.dbg && blockIdx.x == 0 && tile_it < kRuTraceTiles) p.dbg[tile_it * kRuTraceEvents + ev] = clock64();
+}
 
-template <int C, int NTERMS>
+// mbar_wait that adds the cycles spent waiting to `acc` when tracing (schedule debugging)
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, bool timed, long long& acc) {
+  if (!timed) { mbar_wait(bar, parity); return; }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
+}
+
+template <int C, int NTERMS, int CL>
 __global__ void __launch_bounds__(kRuThreads, 1)
 resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                      const __grid_constant__ CUtensorMap tm_w7_hi, const __grid_constant__ CUtensorMap tm_w7_lo,
                      const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_constant__ CUtensorMap tm_w1_lo,
                      const __grid_constant__ CUtensorMap tm_res, const RuParams p) {
   using Cfg = RuCfg<C, NTERMS>;
-  constexpr int SA = Cfg::SA, SW = Cfg::SW, SM = Cfg::SM, SR = Cfg::SR, NB1 = Cfg::NB1, NB2 = Cfg::NB2;
-  constexpr int G = Cfg::G, SKEW = Cfg::SKEW;
+  constexpr int SA = Cfg::SA, SW = Cfg::SW, SR = Cfg::SR, NB1 = Cfg::NB1, NB2 = Cfg::NB2;
+  constexpr int G = Cfg::G, SKEW = Cfg::SKEW, NMID = Cfg::kNumMid;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;
   const uint32_t w_base = a_base + SA * Cfg::kAStage;
-  const uint32_t mid_base = w_base + SW * Cfg::kWStage;
-  const uint32_t res_base = mid_base + SM * Cfg::kMidSlot;
+  const uint32_t res_base = w_base + SW * Cfg::kWStage;
   const uint32_t par_base = res_base + SR * kRuSlabBytes;
   const uint32_t bar_base = par_base + Cfg::kParBytes;
   auto a_full = [&](int s) { return bar_base + 8u * s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (SA + s); };
   auto w_full = [&](int s) { return bar_base + 8u * (2 * SA + s); };
   auto w_empty = [&](int s) { return bar_base + 8u * (2 * SA + SW + s); };
-  auto mid_full = [&](int s) { return bar_base + 8u * (2 * SA + 2 * SW + s); };
-  auto mid_empty = [&](int s) { return bar_base + 8u * (2 * SA + 2 * SW + SM + s); };
-  auto acc1_full = [&](int s) { return bar_base + 8u * (2 * SA + 2 * SW + 2 * SM + s); };
-  auto acc2_full = [&](int s) { return bar_base + 8u * (2 * SA + 2 * SW + 2 * SM + NB1 + s); };
-  auto acc2_empty = [&](int s) { return bar_base + 8u * (2 * SA + 2 * SW + 2 * SM + NB1 + NB2 + s); };
-  auto res_full = [&](int s) { return bar_base + 8u * (2 * SA + 2 * SW + 2 * SM + NB1 + 2 * NB2 + s); };
-  auto res_empty = [&](int s) { return bar_base + 8u * (2 * SA + 2 * SW + 2 * SM + NB1 + 2 * NB2 + SR + s); };
+  auto mid_full = [&](int buf, int chunk) { return bar_base + 8u * (2 * SA + 2 * SW + buf * Cfg::kChunks + chunk); };
+  auto acc1_full = [&](int s) { return bar_base + 8u * (2 * SA + 2 * SW + NMID + s); };
+  auto acc2_full = [&](int s) { return bar_base + 8u * (2 * SA + 2 * SW + NMID + NB1 + s); };
+  auto acc2_empty = [&](int s) { return bar_base + 8u * (2 * SA + 2 * SW + NMID + NB1 + NB2 + s); };
+  auto res_full = [&](int s) { return bar_base + 8u * (2 * SA + 2 * SW + NMID + NB1 + 2 * NB2 + s); };
+  auto res_empty = [&](int s) { return bar_base + 8u * (2 * SA + 2 * SW + NMID + NB1 + 2 * NB2 + SR + s); };
   const uint32_t tmem_slot = bar_base + 8u * Cfg::kNumBars;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   float* s_par = reinterpret_cast<float*>(smem_raw + (par_base - smem_u32(smem_raw)));   // [bias7 | alpha_mid | inv_mid]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n_my = ((int)blockIdx.x < p.num_tiles) ? (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  // Tiles are dealt to CLUSTERS: the CL CTAs of a cluster work on CL consecutive tiles in lock step and share
+  // every weight stage (each CTA fetches 1/CL of it and multicasts).  A trailing partial group computes a
+  // dummy tile (all rows out of range: TMA zero fill, stores masked).
+  const int cl_rank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int cid = (int)blockIdx.x / CL, ncl = (int)gridDim.x / CL;
+  const int n_groups = (p.num_tiles + CL - 1) / CL;
+  const int n_my = cid < n_groups ? (n_groups - cid + ncl - 1) / ncl : 0;
+  auto tile_of = [&](int it) { return (cid + it * ncl) * CL + cl_rank; };
+  auto tile_b = [&](int tile) { return tile < p.num_tiles ? tile / p.m_tiles_per_utt : p.batch; };   // batch = out of range
+  auto tile_l0 = [&](int tile) { return tile < p.num_tiles ? (tile % p.m_tiles_per_utt) * kBlockM : 0; };
 
   for (int i = threadIdx.x; i < C; i += blockDim.x) {
     s_par[i] = __ldg(p.bias7 + i);
     s_par[C + i] = __ldg(p.alpha_mid + i);
     s_par[2 * C + i] = __ldg(p.inv_mid + i);
   }
-  if (warp == 0 && lane == 0) {
+  if (warp == kRuTmaWWarp && lane == 0) {
     prefetch_tmap(&tm_a_hi);
     prefetch_tmap(&tm_w7_hi);
     prefetch_tmap(&tm_w1_hi);
@@ -130,47 +171,74 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
       prefetch_tmap(&tm_w1_lo);
     }
     for (int s = 0; s < SA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
-    for (int s = 0; s < SW; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
-    for (int s = 0; s < SM; ++s) { mbar_init(mid_full(s), kRuEpiThreads); mbar_init(mid_empty(s), 1); }
+    for (int s = 0; s < SW; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), CL); }
+    for (int s = 0; s < NMID; ++s) mbar_init(mid_full(0, s), kRuMidArrivals);
     for (int s = 0; s < NB1; ++s) mbar_init(acc1_full(s), 1);
-    for (int s = 0; s < NB2; ++s) { mbar_init(acc2_full(s), 1); mbar_init(acc2_empty(s), kRuEpiThreads); }
-    for (int s = 0; s < SR; ++s) { mbar_init(res_full(s), 1); mbar_init(res_empty(s), kRuEpiThreads); }
+    for (int s = 0; s < NB2; ++s) { mbar_init(acc2_full(s), 1); mbar_init(acc2_empty(s), kRuTeamThreads); }
+    for (int s = 0; s < SR; ++s) { mbar_init(res_full(s), 1); mbar_init(res_empty(s), kRuTeamThreads); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == kRuMmaWarp) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast / remote arrive
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  if (warp == 0) {
-    // ================================ TMA producer ================================
+  if (warp == kRuTmaAWarp) {
+    // ================================ TMA producer: activation halo tiles ================================
     if (elect_one()) {
-      uint32_t as = 0, aph = 0, ws = 0, wph = 0;
+      uint32_t as = 0, aph = 0;
       const uint32_t a_tx = (uint32_t)(G * Cfg::kPlanes) * (uint32_t)p.halo_rows * 64u;
+      for (int it = 0; it < n_my; ++it) {
+        const int tile = tile_of(it);
+        const int b = tile_b(tile);
+        const int row0 = tile_l0(tile) - 3 * p.dil;
+        if (it + 1 < n_my) {   // next tile's operand rows -> L2 (they come from HBM: written by the previous kernel)
+          const int nt = tile_of(it + 1);
+          const int nb = tile_b(nt), nrow0 = tile_l0(nt) - 3 * p.dil;
+          for (int kc = 0; kc < Cfg::kChunks; ++kc) {
+            tma_prefetch_3d(&tm_a_hi, kc * 32, nrow0, nb);
+            if (NTERMS == 3) tma_prefetch_3d(&tm_a_lo, kc * 32, nrow0, nb);
+          }
+        }
+        for (int kg = 0; kg < Cfg::kGroups; ++kg) {
+          mbar_wait(a_empty(as), aph ^ 1u);
+          mbar_expect_tx(a_full(as), a_tx);
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            const uint32_t sa = a_base + as * Cfg::kAStage + (uint32_t)(g * Cfg::kPlanes) * kRuAChunkBytes;
+            tma_load_3d(sa, &tm_a_hi, a_full(as), (kg * G + g) * 32, row0, b);
+            if (NTERMS == 3) tma_load_3d(sa + kRuAChunkBytes, &tm_a_lo, a_full(as), (kg * G + g) * 32, row0, b);
+          }
+          if (++as == SA) { as = 0; aph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == kRuTmaWWarp) {
+    // ================================ TMA producer: weights ================================
+    // One ring for the W7 tap tiles of tile `it` and the W1 tiles of tile `it - SKEW`, in the order the MMA
+    // warp consumes them.  With CL > 1 this CTA fetches rows [cl_rank * C / CL, +C / CL) of every chunk and
+    // multicasts them to all CTAs of the cluster; a stage is refilled once EVERY CTA's MMAs released it.
+    if (elect_one()) {
+      uint32_t ws = 0, wph = 0;
+      constexpr uint16_t mask = (uint16_t)((1u << CL) - 1u);
+      const uint32_t row_off = (uint32_t)(cl_rank * (C / CL)) * 64u;
+      auto load_w = [&](uint32_t dst, const CUtensorMap* map, uint32_t bar, int k0) {
+        if (CL > 1) tma_load_2d_mc(dst + row_off, map, bar, k0, cl_rank * (C / CL), mask);
+        else tma_load_2d(dst, map, bar, k0, 0);
+      };
       for (int it = 0; it < n_my + SKEW; ++it) {
         if (it < n_my) {
-          const int tile = blockIdx.x + it * gridDim.x;
-          const int b = tile / p.m_tiles_per_utt;
-          const int row0 = (tile % p.m_tiles_per_utt) * kBlockM - 3 * p.dil;
           for (int kg = 0; kg < Cfg::kGroups; ++kg) {
-            mbar_wait(a_empty(as), aph ^ 1u);
-            mbar_expect_tx(a_full(as), a_tx);
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-              const uint32_t sa = a_base + as * Cfg::kAStage + (uint32_t)(g * Cfg::kPlanes) * kRuAChunkBytes;
-              tma_load_3d(sa, &tm_a_hi, a_full(as), (kg * G + g) * 32, row0, b);
-              if (NTERMS == 3) tma_load_3d(sa + kRuAChunkBytes, &tm_a_lo, a_full(as), (kg * G + g) * 32, row0, b);
-            }
-            if (++as == SA) { as = 0; aph ^= 1u; }
             for (int j = 0; j < 7; ++j) {
               mbar_wait(w_empty(ws), wph ^ 1u);
               mbar_expect_tx(w_full(ws), Cfg::kWStage);
 #pragma unroll
               for (int g = 0; g < G; ++g) {
                 const uint32_t sw = w_base + ws * Cfg::kWStage + (uint32_t)(g * Cfg::kPlanes) * Cfg::kWChunk;
-                tma_load_2d(sw, &tm_w7_hi, w_full(ws), j * C + (kg * G + g) * 32, 0);
-                if (NTERMS == 3) tma_load_2d(sw + Cfg::kWChunk, &tm_w7_lo, w_full(ws), j * C + (kg * G + g) * 32, 0);
+                load_w(sw, &tm_w7_hi, w_full(ws), j * C + (kg * G + g) * 32);
+                if (NTERMS == 3) load_w(sw + Cfg::kWChunk, &tm_w7_lo, w_full(ws), j * C + (kg * G + g) * 32);
               }
               if (++ws == SW) { ws = 0; wph ^= 1u; }
             }
@@ -183,30 +251,33 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
 #pragma unroll
             for (int g = 0; g < G; ++g) {
               const uint32_t sw = w_base + ws * Cfg::kWStage + (uint32_t)(g * Cfg::kPlanes) * Cfg::kWChunk;
-              tma_load_2d(sw, &tm_w1_hi, w_full(ws), (kg * G + g) * 32, 0);
-              if (NTERMS == 3) tma_load_2d(sw + Cfg::kWChunk, &tm_w1_lo, w_full(ws), (kg * G + g) * 32, 0);
+              load_w(sw, &tm_w1_hi, w_full(ws), (kg * G + g) * 32);
+              if (NTERMS == 3) load_w(sw + Cfg::kWChunk, &tm_w1_lo, w_full(ws), (kg * G + g) * 32);
             }
             if (++ws == SW) { ws = 0; wph ^= 1u; }
           }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kRuMmaWarp) {
     // ================================ MMA issuer ================================
     if (elect_one()) {
       constexpr uint32_t idesc = make_idesc<C>();
-      uint32_t as = 0, aph = 0, ws = 0, wph = 0, ms = 0, mph = 0;
+      uint32_t as = 0, aph = 0, ws = 0, wph = 0;
+      const bool timed = p.dbg != nullptr && blockIdx.x == 0;
       for (int it = 0; it < n_my + SKEW; ++it) {
+        long long wa = 0, ww = 0, ww1 = 0, wm = 0, w2 = 0;
         if (it < n_my) {
           // ---- k7 (dilated) conv of tile `it` -> acc1[it % NB1].  The buffer is free: the 1x1 conv of the
           // tile that last used it was issued earlier in program order and waited for every mid chunk, i.e.
           // for the epilogue warps to have drained it.
           const uint32_t d1 = tmem_base + (uint32_t)(it % NB1) * C;
           for (int kg = 0; kg < Cfg::kGroups; ++kg) {
-            mbar_wait(a_full(as), aph);
+            mbar_wait_t(a_full(as), aph, timed, wa);
+            if (kg == 0) ru_trace(p, it, 0);
             const uint32_t sa = a_base + as * Cfg::kAStage;
             for (int j = 0; j < 7; ++j) {
-              mbar_wait(w_full(ws), wph);
+              mbar_wait_t(w_full(ws), wph, timed, ww);
               tc_fence_after();
               const uint32_t sw = w_base + ws * Cfg::kWStage;
               const uint32_t a_off = (uint32_t)(j * p.dil) * 64u;   // tap j starts j*dil rows into the halo tile
@@ -225,47 +296,56 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
                   for (int k = 0; k < 2; ++k) umma_bf16(d1, a_hi + 2 * k, w_lo + 2 * k, idesc, 1u);
                 }
               }
-              umma_commit(w_empty(ws));
+              umma_commit_cl<CL>(w_empty(ws));
               if (++ws == SW) { ws = 0; wph ^= 1u; }
             }
             umma_commit(a_empty(as));
             if (++as == SA) { as = 0; aph ^= 1u; }
           }
           umma_commit(acc1_full(it % NB1));
+          ru_trace(p, it, 1);
+          if (timed && it < kRuTraceTiles) { p.dbg[it * kRuTraceEvents + 27] = wa; p.dbg[it * kRuTraceEvents + 28] = ww; }
         }
         if (it >= SKEW) {
           // ---- 1x1 conv of tile jt: split-K over the mid chunks as the epilogue warps publish them
           const int jt = it - SKEW;
           const uint32_t d2 = tmem_base + (uint32_t)(NB1 + jt % NB2) * C;
-          mbar_wait(acc2_empty(jt % NB2), ((uint32_t)(jt / NB2) & 1u) ^ 1u);
+          mbar_wait_t(acc2_empty(jt % NB2), ((uint32_t)(jt / NB2) & 1u) ^ 1u, timed, w2);
           tc_fence_after();
+          ru_trace(p, jt, 2);
+          const uint32_t mid_tmem = tmem_base + (uint32_t)(jt % NB1) * C;   // acc1 buffer of tile jt, converted in place
+          const uint32_t mid_par = (uint32_t)(jt / NB1) & 1u;
           for (int kg = 0; kg < Cfg::kGroups; ++kg) {
-            mbar_wait(w_full(ws), wph);
+            mbar_wait_t(w_full(ws), wph, timed, ww1);
             const uint32_t sw = w_base + ws * Cfg::kWStage;
 #pragma unroll
             for (int g = 0; g < G; ++g) {
-              mbar_wait(mid_full(ms), mph);
+              const int kc = kg * G + g;
+              mbar_wait_t(mid_full(jt % NB1, kc), mid_par, timed, wm);
               tc_fence_after();
-              const uint32_t sm = mid_base + ms * Cfg::kMidSlot;
-              const uint64_t a_hi = make_smem_desc<32>(sm);
+              ru_trace(p, jt, 3 + kc);
+              // A operand in tensor memory: lane = row, 16 K values = 8 columns of packed bf16 pairs
+              const uint32_t a_hi = mid_tmem + (uint32_t)kc * 32u;
               const uint64_t w_hi = make_smem_desc<32>(sw + (uint32_t)(g * Cfg::kPlanes) * Cfg::kWChunk);
 #pragma unroll
-              for (int k = 0; k < 2; ++k) umma_bf16(d2, a_hi + 2 * k, w_hi + 2 * k, idesc, (kg | g | k) != 0);
+              for (int k = 0; k < 2; ++k) umma_bf16_ts(d2, a_hi + 8 * k, w_hi + 2 * k, idesc, (kg | g | k) != 0);
               if (NTERMS == 3) {
-                const uint64_t a_lo = make_smem_desc<32>(sm + kRuMidChunkBytes);
+                const uint32_t a_lo = a_hi + 16u;
                 const uint64_t w_lo = make_smem_desc<32>(sw + (uint32_t)(g * Cfg::kPlanes + 1) * Cfg::kWChunk);
 #pragma unroll
-                for (int k = 0; k < 2; ++k) umma_bf16(d2, a_lo + 2 * k, w_hi + 2 * k, idesc, 1u);
+                for (int k = 0; k < 2; ++k) umma_bf16_ts(d2, a_lo + 8 * k, w_hi + 2 * k, idesc, 1u);
 #pragma unroll
-                for (int k = 0; k < 2; ++k) umma_bf16(d2, a_hi + 2 * k, w_lo + 2 * k, idesc, 1u);
+                for (int k = 0; k < 2; ++k) umma_bf16_ts(d2, a_hi + 8 * k, w_lo + 2 * k, idesc, 1u);
               }
-              umma_commit(mid_empty(ms));
-              if (++ms == SM) { ms = 0; mph ^= 1u; }
             }
-            umma_commit(w_empty(ws));
+            umma_commit_cl<CL>(w_empty(ws));
             if (++ws == SW) { ws = 0; wph ^= 1u; }
           }
           umma_commit(acc2_full(jt % NB2));
+          ru_trace(p, jt, 9);
+          if (timed && jt < kRuTraceTiles) {
+            p.dbg[jt * kRuTraceEvents + 29] = ww1; p.dbg[jt * kRuTraceEvents + 30] = wm; p.dbg[jt * kRuTraceEvents + 31] = w2;
+          }
         }
       }
     }
@@ -275,9 +355,13 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
       prefetch_tmap(&tm_res);
       uint32_t rs = 0, rph = 0;
       for (int jt = 0; jt < n_my; ++jt) {
-        const int tile = blockIdx.x + jt * gridDim.x;
-        const int b = tile / p.m_tiles_per_utt;
-        const int l0 = (tile % p.m_tiles_per_utt) * kBlockM;
+        const int tile = tile_of(jt);
+        const int b = tile_b(tile);
+        const int l0 = tile_l0(tile);
+        if (jt + 1 < n_my) {   // pull the next tile's residual rows into L2 while this tile is processed
+          const int nt = tile_of(jt + 1);
+          for (int c = 0; c < C; c += 32) tma_prefetch_3d(&tm_res, c, tile_l0(nt), tile_b(nt));
+        }
         for (int c = 0; c < C; c += 32) {
           mbar_wait(res_empty(rs), rph ^ 1u);
           mbar_expect_tx(res_full(rs), kRuSlabBytes);
@@ -287,158 +371,184 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
       }
     }
   } else {
-    // ================================ epilogue warps ================================
+    // ================================ epilogue teams ================================
+    const bool fin_team = warp >= kRuFinWarp0;
     const int group = warp & 3;                 // TMEM lane quarter this warp may read
     const int row_in_tile = group * 32 + lane;
-    const int ew = warp - 2;                    // 0..7
-    const int half = ew >> 2;                   // which 16 of a chunk's 32 columns this warp drains from TMEM
-    const int q4 = lane & 7, rsub = lane >> 3;  // final stage, phase 2: column quad, row within a 4-row group
-    uint32_t ms = 0, mph = 0, rs = 0, rph = 0;
-    for (int it = 0; it < n_my + SKEW; ++it) {
-      if (it < n_my) {
-        // ---- mid stage of tile `it`: acc1 -> + b7 -> Snake -> bf16 hi/lo -> K-major SWIZZLE_64B smem chunks
-        mbar_wait(acc1_full(it % NB1), (uint32_t)(it / NB1) & 1u);
-        tc_fence_after();
-        const uint32_t t_row = tmem_base + ((uint32_t)(group * 32) << 16) + (uint32_t)(it % NB1) * C;
+
+    // ---- mid stage of tile `it`: acc1 -> + b7 -> Snake -> bf16 hi/lo, written back IN PLACE: the 32 fp32 columns
+    // of a chunk become 16 columns of packed hi pairs + 16 columns of packed lo pairs, which is exactly the
+    // tensor-memory A-operand layout of the 1x1 conv's MMAs (lane = row, 2 K values per 32-bit column).
+    // A warp converts whole chunks of its lane quarter; the `nsubs` warps of a quarter take the chunks
+    // round-robin, so `nsubs` chunks are in flight.
+    auto mid_stage = [&](int it, int sub, int nsubs) {
+      const int buf = it % NB1;
+      mbar_wait(acc1_full(buf), (uint32_t)(it / NB1) & 1u);
+      tc_fence_after();
+      if (warp == 0 && lane == 0) ru_trace(p, it, 10);
+      const uint32_t t_row = tmem_base + ((uint32_t)(group * 32) << 16) + (uint32_t)buf * C;
 #pragma unroll 1
-        for (int c = 0; c < C; c += 32) {
-          mbar_wait(mid_empty(ms), mph ^ 1u);
-          uint32_t r[16];
-          tmem_ld_x16(t_row + c + 16 * half, r);
-          tmem_ld_wait();
-          const int n0 = c + 16 * half;
+      for (int ci = 0; ci < Cfg::kChunks; ++ci) {
+        const uint32_t cg = (uint32_t)it * Cfg::kChunks + ci;   // running chunk number
+        if ((int)(cg % (uint32_t)nsubs) != sub) continue;
+        const int c = ci * 32;
+        uint32_t r[32];
+        tmem_ld_x32(t_row + c, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {     // 16 columns -> 8 packed hi columns + 8 packed lo columns
           uint32_t hi[8], lo[8];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 b4 = *reinterpret_cast<const float4*>(s_par + n0 + 4 * q);
-            const float4 a4 = *reinterpret_cast<const float4*>(s_par + C + n0 + 4 * q);
-            const float4 i4 = *reinterpret_cast<const float4*>(s_par + 2 * C + n0 + 4 * q);
+          for (int qq = 0; qq < 4; ++qq) {
+            const int q = 4 * hf + qq;
+            const float4 b4 = *reinterpret_cast<const float4*>(s_par + c + 4 * q);
+            const float4 a4 = *reinterpret_cast<const float4*>(s_par + C + c + 4 * q);
+            const float4 i4 = *reinterpret_cast<const float4*>(s_par + 2 * C + c + 4 * q);
             const float v0 = snake_f(__uint_as_float(r[4 * q + 0]) + b4.x, a4.x, i4.x);
             const float v1 = snake_f(__uint_as_float(r[4 * q + 1]) + b4.y, a4.y, i4.y);
             const float v2 = snake_f(__uint_as_float(r[4 * q + 2]) + b4.z, a4.z, i4.z);
             const float v3 = snake_f(__uint_as_float(r[4 * q + 3]) + b4.w, a4.w, i4.w);
             const __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1), h1 = __floats2bfloat162_rn(v2, v3);
-            hi[2 * q] = pack_bf16(h0);
-            hi[2 * q + 1] = pack_bf16(h1);
+            hi[2 * qq] = pack_bf16(h0);
+            hi[2 * qq + 1] = pack_bf16(h1);
             if (NTERMS == 3) {
               const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
-              lo[2 * q] = pack_bf16(__floats2bfloat162_rn(v0 - f0.x, v1 - f0.y));
-              lo[2 * q + 1] = pack_bf16(__floats2bfloat162_rn(v2 - f1.x, v3 - f1.y));
+              lo[2 * qq] = pack_bf16(__floats2bfloat162_rn(v0 - f0.x, v1 - f0.y));
+              lo[2 * qq + 1] = pack_bf16(__floats2bfloat162_rn(v2 - f1.x, v3 - f1.y));
             }
           }
-          // row r of a chunk is 64 B; 16 B piece j lives at j ^ ((r >> 1) & 3) (TMA/UMMA SWIZZLE_64B)
-          const uint32_t row_addr = mid_base + ms * Cfg::kMidSlot + (uint32_t)row_in_tile * 64u;
-          const uint32_t sw = (uint32_t)(row_in_tile >> 1) & 3u;
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const uint32_t off = (((uint32_t)(2 * half + j)) ^ sw) << 4;
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + off), "r"(hi[4 * j]),
-                         "r"(hi[4 * j + 1]), "r"(hi[4 * j + 2]), "r"(hi[4 * j + 3])
-                         : "memory");
-            if (NTERMS == 3)
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + kRuMidChunkBytes + off),
-                           "r"(lo[4 * j]), "r"(lo[4 * j + 1]), "r"(lo[4 * j + 2]), "r"(lo[4 * j + 3])
-                           : "memory");
-          }
-          fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
-          tc_fence_before();
-          mbar_arrive(mid_full(ms));
-          if (++ms == SM) { ms = 0; mph ^= 1u; }
+          // every accumulator column of the chunk is already in registers, so the in-place stores are safe
+          tmem_st_x8(t_row + c + 8 * hf, hi);
+          if (NTERMS == 3) tmem_st_x8(t_row + c + 16 + 8 * hf, lo);
         }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(mid_full(buf, ci));
+        if (group == 0 && lane == 0) ru_trace(p, it, 11 + ci);
       }
-      if (it >= SKEW) {
-        // ---- final stage of tile jt: acc2 + residual slab (+ b1) -> x, Snake -> operand planes.
-        // Phase 1: each thread adds its 16 accumulator columns into ITS row of the residual slab (in place);
-        // phase 2: the slab is read back transposed (8 lanes = one 128 B row) so every global access is a
-        // full row segment.
-        const int jt = it - SKEW;
-        const int tile = blockIdx.x + jt * gridDim.x;
-        const int b = tile / p.m_tiles_per_utt;
-        const int l0 = (tile % p.m_tiles_per_utt) * kBlockM;
-        mbar_wait(acc2_full(jt % NB2), (uint32_t)(jt / NB2) & 1u);
-        tc_fence_after();
-        const uint32_t t_row = tmem_base + ((uint32_t)(group * 32) << 16) + (uint32_t)(NB1 + jt % NB2) * C;
+    };
+
+    // ---- final stage of tile `jt` (final team only): acc2 + residual slab (+ b1) -> x, Snake -> operand planes.
+    // Phase 1: each thread adds its 16 accumulator columns into ITS row of the residual slab (in place);
+    // phase 2: the slab is read back transposed (8 lanes = one 128 B row) so every global access is a
+    // full row segment.
+    const int ew = (warp - kRuFinWarp0) & 7;    // 0..7 within the final team
+    const int half = ew >> 2;                   // which 16 of a chunk's 32 columns this warp drains from TMEM
+    const int q4 = lane & 7, rsub = lane >> 3;  // phase 2: column quad, row within a 4-row group
+    uint32_t rs = 0, rph = 0;
+    auto final_stage = [&](int jt) {
+      const int tile = tile_of(jt);
+      const bool real = tile < p.num_tiles;
+      const int b = real ? tile / p.m_tiles_per_utt : 0;
+      const int l0 = tile_l0(tile);
+      const int rows_left = real ? p.L - l0 : 0;   // rows of this tile inside the utterance (0: dummy tile)
+      const size_t tile_off = ((size_t)b * p.L + l0) * (size_t)C;
+      float* const x_tile = p.x + tile_off;
+      __nv_bfloat16* const hi_tile = p.out_hi ? p.out_hi + tile_off : nullptr;
+      __nv_bfloat16* const lo_tile = p.out_lo ? p.out_lo + tile_off : nullptr;
+      mbar_wait(acc2_full(jt % NB2), (uint32_t)(jt / NB2) & 1u);
+      tc_fence_after();
+      if (warp == kRuFinWarp0 && lane == 0) ru_trace(p, jt, 20);
+      const uint32_t t_row = tmem_base + ((uint32_t)(group * 32) << 16) + (uint32_t)(NB1 + jt % NB2) * C;
 #pragma unroll 1
-        for (int c = 0; c < C; c += 32) {
-          const int n = c + q4 * 4;
-          const float4 bias4 = __ldg(reinterpret_cast<const float4*>(p.bias1 + n));
-          float4 alpha4 = make_float4(0.f, 0.f, 0.f, 0.f), inv4 = alpha4;
-          if (p.out_hi) {
-            alpha4 = __ldg(reinterpret_cast<const float4*>(p.alpha_out + n));
-            inv4 = __ldg(reinterpret_cast<const float4*>(p.inv_out + n));
-          }
-          uint32_t r[16];
-          tmem_ld_x16(t_row + c + 16 * half, r);
-          tmem_ld_wait();
-          if (c + 32 >= C) {   // accumulator fully drained: hand the TMEM buffer back to the MMA warp
-            tc_fence_before();
-            mbar_arrive(acc2_empty(jt % NB2));
-          }
-          const uint32_t slab = res_base + rs * kRuSlabBytes;
-          mbar_wait(res_full(rs), rph);
-          {
-            const uint32_t row_addr = slab + (uint32_t)row_in_tile * 128u;
+      for (int c = 0; c < C; c += 32) {
+        const int n = c + q4 * 4;
+        const float4 bias4 = __ldg(reinterpret_cast<const float4*>(p.bias1 + n));
+        float4 alpha4 = make_float4(0.f, 0.f, 0.f, 0.f), inv4 = alpha4;
+        if (hi_tile) {
+          alpha4 = __ldg(reinterpret_cast<const float4*>(p.alpha_out + n));
+          inv4 = __ldg(reinterpret_cast<const float4*>(p.inv_out + n));
+        }
+        uint32_t r[16];
+        tmem_ld_x16(t_row + c + 16 * half, r);
+        tmem_ld_wait();
+        if (c + 32 >= C) {   // accumulator fully drained: hand the TMEM buffer back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(acc2_empty(jt % NB2));
+        }
+        const uint32_t slab = res_base + rs * kRuSlabBytes;
+        mbar_wait(res_full(rs), rph);
+        {
+          const uint32_t row_addr = slab + (uint32_t)row_in_tile * 128u;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t addr = row_addr + ((((uint32_t)(4 * half + j)) ^ ((uint32_t)row_in_tile & 7u)) << 4);
-              float4 v;
-              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                           : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                           : "r"(addr));
-              // same association as the stand-alone 1x1 kernel: (acc + residual) + bias
-              v.x = __uint_as_float(r[4 * j + 0]) + v.x;
-              v.y = __uint_as_float(r[4 * j + 1]) + v.y;
-              v.z = __uint_as_float(r[4 * j + 2]) + v.z;
-              v.w = __uint_as_float(r[4 * j + 3]) + v.w;
-              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-                           : "memory");
-            }
-          }
-          asm volatile("bar.sync 1, %0;" ::"n"(kRuEpiThreads) : "memory");
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int rr = ew * 16 + i * 4 + rsub;
-            const int l = l0 + rr;
-            const uint32_t off = (uint32_t)rr * 128u + ((uint32_t)(q4 ^ (rr & 7)) << 4);
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t addr = row_addr + ((((uint32_t)(4 * half + j)) ^ ((uint32_t)row_in_tile & 7u)) << 4);
             float4 v;
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                          : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                         : "r"(slab + off));
-            if (l < p.L) {
-              v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
-              const size_t idx = ((size_t)b * p.L + l) * (size_t)C + n;
-              *reinterpret_cast<float4*>(p.x + idx) = v;
-              if (p.out_hi) {
-                v.x = snake_f(v.x, alpha4.x, inv4.x); v.y = snake_f(v.y, alpha4.y, inv4.y);
-                v.z = snake_f(v.z, alpha4.z, inv4.z); v.w = snake_f(v.w, alpha4.w, inv4.w);
-                const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
-                *reinterpret_cast<uint2*>(p.out_hi + idx) = make_uint2(pack_bf16(h0), pack_bf16(h1));
-                if (p.out_lo) {
-                  const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
-                  *reinterpret_cast<uint2*>(p.out_lo + idx) =
-                      make_uint2(pack_bf16(__floats2bfloat162_rn(v.x - f0.x, v.y - f0.y)),
-                                 pack_bf16(__floats2bfloat162_rn(v.z - f1.x, v.w - f1.y)));
-                }
+                         : "r"(addr));
+            // same association as the stand-alone 1x1 kernel: (acc + residual) + bias
+            v.x = __uint_as_float(r[4 * j + 0]) + v.x;
+            v.y = __uint_as_float(r[4 * j + 1]) + v.y;
+            v.z = __uint_as_float(r[4 * j + 2]) + v.z;
+            v.w = __uint_as_float(r[4 * j + 3]) + v.w;
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                         : "memory");
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kRuTeamThreads) : "memory");
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rr = ew * 16 + i * 4 + rsub;
+          const uint32_t off = (uint32_t)rr * 128u + ((uint32_t)(q4 ^ (rr & 7)) << 4);
+          float4 v;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                       : "r"(slab + off));
+          if (rr < rows_left) {
+            v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+            const uint32_t idx = (uint32_t)rr * C + n;
+            *reinterpret_cast<float4*>(x_tile + idx) = v;
+            if (hi_tile) {
+              v.x = snake_f(v.x, alpha4.x, inv4.x); v.y = snake_f(v.y, alpha4.y, inv4.y);
+              v.z = snake_f(v.z, alpha4.z, inv4.z); v.w = snake_f(v.w, alpha4.w, inv4.w);
+              const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+              *reinterpret_cast<uint2*>(hi_tile + idx) = make_uint2(pack_bf16(h0), pack_bf16(h1));
+              if (lo_tile) {
+                const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+                *reinterpret_cast<uint2*>(lo_tile + idx) =
+                    make_uint2(pack_bf16(__floats2bfloat162_rn(v.x - f0.x, v.y - f0.y)),
+                               pack_bf16(__floats2bfloat162_rn(v.z - f1.x, v.w - f1.y)));
               }
             }
           }
-          fence_proxy_async();   // this slab was written through the generic proxy; the next TMA load overwrites it
-          mbar_arrive(res_empty(rs));
-          if (++rs == SR) { rs = 0; rph ^= 1u; }
         }
+        fence_proxy_async();   // this slab was written through the generic proxy; the next TMA load overwrites it
+        mbar_arrive(res_empty(rs));
+        if (++rs == SR) { rs = 0; rph ^= 1u; }
+        if (warp == kRuFinWarp0 && lane == 0) ru_trace(p, jt, 21 + c / 32);
+      }
+    };
+
+    const int sub = (warp - kRuMidWarp0) >> 2;   // 0..1 mid team, 2..3 final team
+    if (SKEW) {
+      // the teams work on different tiles at the same time: mid of tile i, final of tile i - 1
+      if (!fin_team) {
+        for (int it = 0; it < n_my; ++it) mid_stage(it, sub, 2);
+      } else {
+        for (int jt = 0; jt < n_my; ++jt) final_stage(jt);
+      }
+    } else {
+      // un-skewed: the tensor pipe waits for the mid stage and the final team has nothing to do before acc2
+      // completes, so BOTH teams convert mid chunks (4 in flight); the final team then finishes the tile
+      // while the next tile's k7 conv runs.
+      for (int it = 0; it < n_my; ++it) {
+        mid_stage(it, sub, 4);
+        if (fin_team) final_stage(it);
       }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
+  if (CL > 1) cluster_sync_all();   // no CTA leaves while a peer may still multicast into it / arrive on its barriers
+  else __syncthreads();
+  if (warp == kRuMmaWarp) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }
 }
 
-template <int C, int NTERMS>
+template <int C, int NTERMS, int CL>
 int launch_ru(const GemmWeights& c7, const GemmWeights& c1, const OpBuf& a, int batch, int L, const RuParams& p,
               int num_sms, cudaStream_t stream) {
   using Cfg = RuCfg<C, NTERMS>;
@@ -452,16 +562,65 @@ int launch_ru(const GemmWeights& c7, const GemmWeights& c1, const OpBuf& a, int 
   const uint64_t rstr[2] = {(uint64_t)C * 4, (uint64_t)L * C * 4};
   const uint32_t rbox[3] = {32u, (uint32_t)kBlockM, 1u};
   SC_TRY(encode_tmap(&t_res, p.x, 3, dims, rstr, rbox, 128, false, true));
-  auto kern = resunit_fused_kernel<C, NTERMS>;
-  static bool attr_done = false;   // per instantiation
-  if (!attr_done) {
-    SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_done = true;
+  // weight maps: (K, N) boxes of 32 x C / CL rows (each CTA of a cluster fetches its share of a stage)
+  CUtensorMap tw[4];
+  const GemmWeights* gw[2] = {&c7, &c1};
+  for (int i = 0; i < 2; ++i) {
+    const uint64_t wd[2] = {(uint64_t)gw[i]->kt * C, (uint64_t)C};
+    const uint64_t ws[1] = {(uint64_t)gw[i]->kt * C * 2};
+    const uint32_t wb[2] = {32u, (uint32_t)(C / CL)};
+    SC_TRY(encode_tmap(&tw[2 * i], gw[i]->w_hi, 2, wd, ws, wb, 64, true, false));
+    SC_TRY(encode_tmap(&tw[2 * i + 1], NTERMS == 3 ? gw[i]->w_lo : gw[i]->w_hi, 2, wd, ws, wb, 64, true, false));
   }
-  const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-  kern<<<grid, kRuThreads, Cfg::kSmemBytes, stream>>>(ta_hi, ta_lo, c7.tmap_hi[1], NTERMS == 3 ? c7.tmap_lo[1] : c7.tmap_hi[1],
-                                                       c1.tmap_hi[1], NTERMS == 3 ? c1.tmap_lo[1] : c1.tmap_hi[1], t_res, p);
+  auto kern = resunit_fused_kernel<C, NTERMS, CL>;
+  static int max_clusters = 0;   // per instantiation
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(kRuThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  if (!max_clusters) {
+    SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    if (CL > 1) {
+      cfg.gridDim = dim3(num_sms / CL * CL);
+      SC_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+      if (max_clusters < 1) { set_error("resunit_fused: no cluster of %d CTAs fits the device", CL); return SPARKCODEC_ECUDA; }
+    } else {
+      max_clusters = num_sms;
+    }
+  }
+  const int groups = (p.num_tiles + CL - 1) / CL;
+  const int clusters = std::min(std::min(groups, max_clusters), num_sms / CL);
+  cfg.gridDim = dim3(clusters * CL);
+  static const bool trace = getenv("SPARKCODEC_RU_TRACE") != nullptr;   // schedule debugging only
+  RuParams pp = p;
+  static long long* dbg = nullptr;
+  const size_t dbg_n = (size_t)kRuTraceTiles * kRuTraceEvents;
+  if (trace) {
+    if (!dbg) SC_CUDA(cudaMalloc(&dbg, dbg_n * sizeof(long long)));
+    SC_CUDA(cudaMemsetAsync(dbg, 0, dbg_n * sizeof(long long), stream));
+    pp.dbg = dbg;
+  }
+  SC_CUDA(cudaLaunchKernelEx(&cfg, kern, ta_hi, ta_lo, tw[0], tw[1], tw[2], tw[3], t_res, pp));
   SC_LAUNCH_CHECK();
+  if (trace) {
+    std::vector<long long> hst(dbg_n);
+    SC_CUDA(cudaStreamSynchronize(stream));
+    SC_CUDA(cudaMemcpy(hst.data(), dbg, dbg_n * sizeof(long long), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "# ru trace C=%d terms=%d cl=%d dil=%d L=%d grid=%d (cycles relative to tile 2's k7 start; CTA 0)\n", C,
+            NTERMS, CL, p.dil, L, clusters * CL);
+    const long long t0 = hst[2 * kRuTraceEvents];
+    for (int t = 2; t < 8; ++t) {
+      fprintf(stderr, "tile %d:", t);
+      for (int e = 0; e < kRuTraceEvents; ++e)
+        if (hst[t * kRuTraceEvents + e]) fprintf(stderr, " e%d=%lld", e, hst[t * kRuTraceEvents + e] - (e >= 27 ? 0 : t0));
+      fprintf(stderr, "\n");
+    }
+  }
   return 0;
 }
 
@@ -504,13 +663,21 @@ int launch_resunit_fused(const GemmWeights& c7, const GemmWeights& c1, const OpB
   p.bias7 = c7.bias; p.alpha_mid = alpha_mid; p.inv_mid = inv_mid;
   p.bias1 = c1.bias; p.alpha_out = alpha_out; p.inv_out = inv_out;
   p.x = x;
+  p.dbg = nullptr;
   p.out_hi = out.hi;
   p.out_lo = f32 ? out.lo : nullptr;
-  if (c7.c_in == 96)
-    return f32 ? launch_ru<96, 3>(c7, c1, a, batch, L, p, num_sms, stream)
-               : launch_ru<96, 1>(c7, c1, a, batch, L, p, num_sms, stream);
-  return f32 ? launch_ru<192, 3>(c7, c1, a, batch, L, p, num_sms, stream)
-             : launch_ru<192, 1>(c7, c1, a, batch, L, p, num_sms, stream);
+  static const int cl = [] {
+    const char* e = getenv("SPARKCODEC_CLUSTER");   // 1: no weight multicast (A/B timing)
+    return e ? atoi(e) : 2;
+  }();
+#define RU_DISPATCH(CC, NT)                                                                   \
+  return cl > 1 ? launch_ru<CC, NT, 2>(c7, c1, a, batch, L, p, num_sms, stream)               \
+                : launch_ru<CC, NT, 1>(c7, c1, a, batch, L, p, num_sms, stream)
+  if (c7.c_in == 96) {
+    if (f32) { RU_DISPATCH(96, 3); } else { RU_DISPATCH(96, 1); }
+  }
+  if (f32) { RU_DISPATCH(192, 3); } else { RU_DISPATCH(192, 1); }
+#undef RU_DISPATCH
 }
 
 }  // namespace sparkcodec
