@@ -13,6 +13,7 @@ struct ConvGemmParams {
   int num_n_tiles;       // n_total / BLOCK_N
   int halo_rows;         // halo mainloop: rows of the A box (128 + tap span, multiple of 8)
   int halo_bo_mode;      // halo mainloop: descriptor base-offset convention (see tc_gemm.cu)
+  int halo_stages;       // halo mainloop: halo tiles in flight (2 or 3); the weight ring gets the rest of smem
   // epilogue
   const float* bias;
   const float* rowbias;

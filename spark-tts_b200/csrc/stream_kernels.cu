@@ -9,6 +9,7 @@
 
 #include "common.cuh"
 #include "gemm_params.cuh"
+#include "tc_ptx.cuh"
 
 namespace sparkcodec {
 namespace {
@@ -163,122 +164,198 @@ __global__ void small_linear_kernel(const float* __restrict__ x, const float* __
 // x (batch, rows, C) fp32 -> [dwconv k=7 pad 3 over rows] -> LayerNorm over C (biased variance, eps)
 // -> * scale[b] + shift[b] -> fp32 and/or operand planes.
 // (vocos.py:69-75 ConvNeXtBlock head, :105-110 AdaLayerNorm, :328-334 backbone norms.)
-// One CTA stages TR + 6 rows of one utterance in shared memory with coalesced 128-bit loads (halo rows
-// outside the utterance are the conv's zero padding); each warp then owns whole rows: a lane holds
-// C/32 channels as float4s, so the row statistics are two warp-shuffle reductions.
-constexpr int kLnRows = 16;
+//
+// One persistent CTA per SM walks 32-row tiles of one utterance with a three-deep pipeline of BULK async copies:
+// a tile with its halo is one contiguous span of memory, so one elected thread moves it with a single
+// cp.async.bulk (TMA, mbarrier completion) while the other warps normalise tile i; tiles i+1 and i+2 are in
+// flight.  Halo rows outside the utterance (the conv's zero padding) are zero-filled by the CTA.  A warp owns 4 CONSECUTIVE output rows: a lane holds C/32 channels as float4s,
+// keeps its 7 x C/32 depthwise taps in REGISTERS for the whole kernel and reads each of the 10 input rows it
+// needs once (7.5 LDS.128 per output row instead of 21 + 21 weight loads); the row statistics are
+// warp-shuffle reductions, four rows interleaved.  Nothing but the tile itself is read in the main loop,
+// so the tiny L1 left next to 117 KB of shared memory is not in the way.
+constexpr int kLnRows = 32;        // output rows per tile
+constexpr int kLnWarpRows = 4;     // consecutive rows per warp (8 warps x 4 = 32)
+constexpr int kLnStages = 3;       // tiles in shared memory
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
   const int sz = valid ? 16 : 0;   // src-size 0 => 16 zero bytes (the conv's zero padding)
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
 }
 
-// Persistent CTAs; every CTA walks row tiles with a two-deep cp.async pipeline: tile i+1 streams into
-// the other smem buffer while tile i is normalised.
 template <int NV, bool DW>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 1)
 dwconv_ln_kernel(const float* __restrict__ x, int rows, const float* __restrict__ dw_w /* [7][C] */,
                  const float* __restrict__ dw_b, const float* __restrict__ scale, const float* __restrict__ shift,
                  int ss_stride, float eps, float* __restrict__ out_f32, OpBuf out_op, int tiles_per_utt,
                  int total_tiles) {
   constexpr int C = NV * 128;
   constexpr int HALO = DW ? 3 : 0;
+  constexpr int TAPS = DW ? 7 : 1;
   constexpr int TROWS = kLnRows + 2 * HALO;
   constexpr int C4 = C / 4;
-  extern __shared__ __align__(16) float s_buf[];   // [2][TROWS][C]
+  extern __shared__ __align__(16) float s_buf[];   // [kLnStages][TROWS][C]
   const uint32_t s_base = static_cast<uint32_t>(__cvta_generic_to_shared(s_buf));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  __shared__ uint64_t s_bar[kLnStages];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kLnStages; ++i) mbar_init(smem_u32(&s_bar[i]), 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  // rows [r0 - HALO, r0 + kLnRows + HALO) of utterance b -> buffer `buf`; only rows inside the utterance are copied
   auto issue = [&](int tile, int buf) {
     const int b = tile / tiles_per_utt;
     const int r0 = (tile % tiles_per_utt) * kLnRows;
-    const float* xb = x + (size_t)b * rows * C;
-    for (int i = threadIdx.x; i < TROWS * C4; i += blockDim.x) {
-      const int rr = i / C4, c4 = i % C4;
-      const int r = r0 + rr - HALO;
-      const bool ok = r >= 0 && r < rows;
-      cp_async16(s_base + (uint32_t)((buf * TROWS * C4 + i) * 16), xb + (size_t)(ok ? r : 0) * C + c4 * 4, ok);
+    const int ra = max(r0 - HALO, 0), rb = min(r0 + kLnRows + HALO, rows);
+    const int first = ra - (r0 - HALO);                   // staged row index of utterance row ra
+    const uint32_t dst = s_base + (uint32_t)((buf * TROWS + first) * C * 4);
+    if (first > 0 || rb - (r0 - HALO) < TROWS) {          // edge tile: zero the staged rows outside the utterance
+      for (int i = threadIdx.x; i < TROWS * C4; i += blockDim.x) {
+        const int rr = i / C4;
+        if (rr < first || rr >= rb - (r0 - HALO))
+          reinterpret_cast<float4*>(s_buf)[buf * TROWS * C4 + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (threadIdx.x == 0) {
+      const uint32_t bytes = (uint32_t)(rb - ra) * C * 4;
+      const uint32_t bar = smem_u32(&s_bar[buf]);
+      mbar_expect_tx(bar, bytes);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                   "l"(x + ((size_t)b * rows + ra) * C), "r"(bytes), "r"(bar)
+                   : "memory");
+    }
   };
 
   int tile = blockIdx.x, buf = 0;
-  if (tile < total_tiles) issue(tile, 0);
-  for (; tile < total_tiles; tile += gridDim.x, buf ^= 1) {
-    const int nxt = tile + gridDim.x;
-    if (nxt < total_tiles) {
-      issue(nxt, buf ^ 1);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    __syncthreads();
-    const float* s_x = s_buf + buf * TROWS * C;
+  uint32_t phase = 0;
+#pragma unroll
+  for (int i = 0; i < kLnStages - 1; ++i)   // prologue: kLnStages - 1 tiles in flight
+    if (tile + i * (int)gridDim.x < total_tiles) issue(tile + i * gridDim.x, i);
+
+  // depthwise taps / bias of this lane's channels: registers for the whole kernel
+  float4 wt[TAPS][NV], bias[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int c = v * 128 + lane * 4;
+    bias[v] = DW ? __ldg(reinterpret_cast<const float4*>(dw_b + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < TAPS; ++j)
+      wt[j][v] = DW ? __ldg(reinterpret_cast<const float4*>(dw_w + j * C + c)) : make_float4(1.f, 1.f, 1.f, 1.f);
+  }
+
+  for (; tile < total_tiles; tile += gridDim.x) {
+    const int nxt = tile + (kLnStages - 1) * gridDim.x;
     const int b = tile / tiles_per_utt;
     const int r0 = (tile % tiles_per_utt) * kLnRows;
-    for (int rr = warp; rr < kLnRows; rr += 8) {
-      const int r = r0 + rr;
-      if (r >= rows) break;
-      float4 y[NV];
+    // per-utterance affine of this lane's channels (AdaLayerNorm: scale/shift depend on the utterance)
+    float4 g[NV], h[NV];
 #pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        const int c = v * 128 + lane * 4;
-        if (DW) {
-          float4 a = __ldg(reinterpret_cast<const float4*>(dw_b + c));
+    for (int v = 0; v < NV; ++v) {
+      const int c = v * 128 + lane * 4;
+      g[v] = __ldg(reinterpret_cast<const float4*>(scale + (size_t)b * ss_stride + c));
+      h[v] = __ldg(reinterpret_cast<const float4*>(shift + (size_t)b * ss_stride + c));
+    }
+    // the buffer of tile - 1 (everyone left it at the barrier that closed the previous iteration) takes tile + 2
+    if (nxt < total_tiles) issue(nxt, (buf + kLnStages - 1) % kLnStages);
+    mbar_wait(smem_u32(&s_bar[buf]), phase);
+    __syncthreads();   // (edge tiles: the zero-fill of this buffer by other threads is complete and visible)
+    const float* s_x = s_buf + buf * TROWS * C;
+    const int rw = warp * kLnWarpRows;                 // first output row of this warp inside the tile
+    if (r0 + rw < rows) {
+      float4 y[kLnWarpRows][NV];
 #pragma unroll
-          for (int j = 0; j < 7; ++j) {
-            const float4 w = __ldg(reinterpret_cast<const float4*>(dw_w + j * C + c));
-            const float4 s = *reinterpret_cast<const float4*>(s_x + (rr + j) * C + c);
-            a.x = fmaf(w.x, s.x, a.x); a.y = fmaf(w.y, s.y, a.y);
-            a.z = fmaf(w.z, s.z, a.z); a.w = fmaf(w.w, s.w, a.w);
+      for (int q = 0; q < kLnWarpRows; ++q)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) y[q][v] = bias[v];
+      // input row (rw + j) of the staged tile feeds output row q through tap j - q
+#pragma unroll
+      for (int j = 0; j < kLnWarpRows + TAPS - 1; ++j) {
+        float4 xin[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) xin[v] = *reinterpret_cast<const float4*>(s_x + (rw + j) * C + v * 128 + lane * 4);
+#pragma unroll
+        for (int q = 0; q < kLnWarpRows; ++q) {
+          const int t = j - q;
+          if (t >= 0 && t < TAPS) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+              if (DW) {
+                y[q][v].x = fmaf(wt[t][v].x, xin[v].x, y[q][v].x); y[q][v].y = fmaf(wt[t][v].y, xin[v].y, y[q][v].y);
+                y[q][v].z = fmaf(wt[t][v].z, xin[v].z, y[q][v].z); y[q][v].w = fmaf(wt[t][v].w, xin[v].w, y[q][v].w);
+              } else {
+                y[q][v] = xin[v];
+              }
+            }
           }
-          y[v] = a;
-        } else {
-          y[v] = *reinterpret_cast<const float4*>(s_x + rr * C + c);
         }
       }
-      float sum = 0.f;
+      float sum[kLnWarpRows], sq[kLnWarpRows];
 #pragma unroll
-      for (int v = 0; v < NV; ++v) sum += (y[v].x + y[v].y) + (y[v].z + y[v].w);
+      for (int q = 0; q < kLnWarpRows; ++q) {
+        sum[q] = 0.f;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      const float mean = sum * (1.0f / C);
-      float sq = 0.f;
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        y[v].x -= mean; y[v].y -= mean; y[v].z -= mean; y[v].w -= mean;
-        sq += (y[v].x * y[v].x + y[v].y * y[v].y) + (y[v].z * y[v].z + y[v].w * y[v].w);
+        for (int v = 0; v < NV; ++v) sum[q] += (y[q][v].x + y[q][v].y) + (y[q][v].z + y[q][v].w);
       }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-      const float rstd = rsqrtf(sq * (1.0f / C) + eps);
-      const size_t row_off = ((size_t)b * rows + r) * C;
+      for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        const int c = v * 128 + lane * 4;
-        const float4 g = __ldg(reinterpret_cast<const float4*>(scale + (size_t)b * ss_stride + c));
-        const float4 h = __ldg(reinterpret_cast<const float4*>(shift + (size_t)b * ss_stride + c));
-        float4 o;
-        o.x = fmaf(y[v].x * rstd, g.x, h.x); o.y = fmaf(y[v].y * rstd, g.y, h.y);
-        o.z = fmaf(y[v].z * rstd, g.z, h.z); o.w = fmaf(y[v].w * rstd, g.w, h.w);
-        if (out_f32) *reinterpret_cast<float4*>(out_f32 + row_off + c) = o;
-        if (out_op.hi) store_op4(out_op, row_off + c, o);
+        for (int q = 0; q < kLnWarpRows; ++q) sum[q] += __shfl_xor_sync(0xffffffffu, sum[q], o);
+#pragma unroll
+      for (int q = 0; q < kLnWarpRows; ++q) {
+        const float mean = sum[q] * (1.0f / C);
+        sq[q] = 0.f;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          y[q][v].x -= mean; y[q][v].y -= mean; y[q][v].z -= mean; y[q][v].w -= mean;
+          sq[q] += (y[q][v].x * y[q][v].x + y[q][v].y * y[q][v].y) + (y[q][v].z * y[q][v].z + y[q][v].w * y[q][v].w);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int q = 0; q < kLnWarpRows; ++q) sq[q] += __shfl_xor_sync(0xffffffffu, sq[q], o);
+#pragma unroll
+      for (int q = 0; q < kLnWarpRows; ++q) {
+        const int r = r0 + rw + q;
+        if (r < rows) {
+          const float rstd = rsqrtf(sq[q] * (1.0f / C) + eps);
+          const size_t row_off = ((size_t)b * rows + r) * C;
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            const int c = v * 128 + lane * 4;
+            float4 o;
+            o.x = fmaf(y[q][v].x * rstd, g[v].x, h[v].x); o.y = fmaf(y[q][v].y * rstd, g[v].y, h[v].y);
+            o.z = fmaf(y[q][v].z * rstd, g[v].z, h[v].z); o.w = fmaf(y[q][v].w * rstd, g[v].w, h[v].w);
+            if (out_f32) *reinterpret_cast<float4*>(out_f32 + row_off + c) = o;
+            if (out_op.hi) store_op4(out_op, row_off + c, o);
+          }
+        }
       }
     }
-    __syncthreads();   // everyone is done with this buffer before the next-but-one tile streams into it
+    // everyone is done with this buffer before the next-but-one tile streams into it (the generic-proxy
+    // accesses are ordered before the async-proxy bulk copy by the fence + barrier)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (++buf == kLnStages) { buf = 0; phase ^= 1u; }
   }
 }
 
 // ------------------------------------------------------------------------------------ waveform head
 // wav[b, l] = tanh(bias + sum_j sum_c w[j, c] * snake(x[b, l + j - 3, c]))     (wave_generator.py:77-81)
-// A warp walks a run of kHeadRun consecutive samples of one utterance: every lane owns C/32 channels,
-// streams the rows straight from HBM with coalesced loads (each element is read and Snake'd once per
-// run, 6 halo rows per run, 8 rows of loads in flight per lane) and keeps the 7-row window in registers.
-// The per-lane partial sums of 32 consecutive samples are transposed through a padded per-warp smem
-// tile (one st.shared + one ld.shared per sample instead of a 5-step shuffle tree per sample); lane L
-// ends up with sample L, so the stores are coalesced 128 B lines.
+// A warp walks a run of kHeadRun consecutive samples of one utterance.  The rows of a run are contiguous in
+// memory, so the warp streams them into its own shared-memory ring with coalesced 16 B cp.async copies, 7 granules
+// (28 rows, 10.5 KB) ahead of the row it is working on: ~130 KB are in flight per SM, which is what it takes
+// to keep HBM busy (the first version kept 8 rows per warp in registers: 36 KB per SM, latency bound).
+// Rows outside the utterance are zero-filled by cp.async; snake(0) == 0, so that IS the conv's zero padding.
+// Every lane owns C/32 channels (conflict-free LDS), Snakes each element once and keeps the 7-row window
+// in registers.  The per-lane partial sums of 32 consecutive samples are transposed through a padded
+// per-warp smem tile (one st.shared + one ld.shared per sample instead of a 5-step shuffle tree per sample);
+// lane L ends up with sample L, so the stores are coalesced 128 B lines.
 constexpr int kHeadRun = 128;
-constexpr int kHeadWarps = 4;   // 144 registers/thread: 4-warp CTAs keep 3 CTAs (12 warps) resident per SM
+constexpr int kHeadWarps = 4;
+constexpr int kHeadGranRows = 4;     // rows per cp.async group (4 rows x 96 ch = 3 x 32 float4 for C = 96)
+constexpr int kHeadRingGran = 8;     // granules in the ring (7 in flight + the one being read)
 
 template <int NCH>
 __global__ void __launch_bounds__(kHeadWarps * 32)
@@ -286,11 +363,20 @@ head_kernel(const float* __restrict__ x, int rows, const float* __restrict__ alp
             const float* __restrict__ inv_alpha, const float* __restrict__ w /* [7][C] */, float bias,
             float* __restrict__ wav, int runs_per_utt, int total_runs) {
   constexpr int C = NCH * 32;
-  const int run = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  constexpr int GRAN_F4 = kHeadGranRows * C / 4;          // float4s per granule (multiple of 32 for C % 32 == 0)
+  constexpr int RING_ROWS = kHeadGranRows * kHeadRingGran;
+  constexpr int N_GRAN = (kHeadRun + 6 + kHeadGranRows - 1) / kHeadGranRows;   // granules of a run incl. halo
+  extern __shared__ __align__(16) float s_head[];         // per warp: ring [RING_ROWS][C] | part [32][33]
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* ring = s_head + (size_t)wib * (RING_ROWS * C + 32 * 33);
+  float(*sp)[33] = reinterpret_cast<float(*)[33]>(ring + RING_ROWS * C);
+  const uint32_t ring_s = static_cast<uint32_t>(__cvta_generic_to_shared(ring));
+  const int run = blockIdx.x * kHeadWarps + wib;
   if (run >= total_runs) return;
   const int b = run / runs_per_utt;
   const int l0 = (run % runs_per_utt) * kHeadRun;
   const float* xb = x + (size_t)b * rows * C;
+
   float a[NCH], ia[NCH], wt[7][NCH];
 #pragma unroll
   for (int k = 0; k < NCH; ++k) {
@@ -299,68 +385,69 @@ head_kernel(const float* __restrict__ x, int rows, const float* __restrict__ alp
 #pragma unroll
     for (int j = 0; j < 7; ++j) wt[j][k] = __ldg(w + j * C + lane + 32 * k);
   }
-  auto load_row = [&](int r, float (&dst)[NCH]) {
+  // granule g holds rows l0 - 3 + 4g .. +3 of the utterance
+  auto issue = [&](int g) {
+    if (g < N_GRAN) {
+      const int slot = g % kHeadRingGran;
 #pragma unroll
-    for (int k = 0; k < NCH; ++k) dst[k] = (r >= 0 && r < rows) ? __ldg(xb + (size_t)r * C + lane + 32 * k) : 0.f;
+      for (int i = 0; i < GRAN_F4 / 32; ++i) {
+        const int f = i * 32 + lane;                       // float4 index inside the granule
+        const int r = l0 - 3 + g * kHeadGranRows + (f * 4) / C;
+        const bool ok = r >= 0 && r < rows;
+        const float* src = xb + (size_t)(ok ? r : 0) * C + (f * 4) % C;
+        const int sz = ok ? 16 : 0;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ring_s + (uint32_t)((slot * GRAN_F4 + f) * 16)),
+                     "l"(src), "r"(sz)
+                     : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");   // (empty groups keep the wait counts uniform)
   };
-  auto act_row = [&](int r, float (&v)[NCH]) {
-    // zero padding applies to the Snake OUTPUT (the conv pads its input, which is snake(x))
 #pragma unroll
-    for (int k = 0; k < NCH; ++k) v[k] = (r >= 0 && r < rows) ? snake_f(v[k], a[k], ia[k]) : 0.f;
-  };
+  for (int g = 0; g < kHeadRingGran - 1; ++g) issue(g);
+
   float win[7][NCH];   // win[j] = snake(x[l + j - 3])
 #pragma unroll
-  for (int k = 0; k < NCH; ++k) win[0][k] = 0.f;
+  for (int j = 0; j < 7; ++j)
 #pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    load_row(l0 + j - 3, win[j + 1]);
-    act_row(l0 + j - 3, win[j + 1]);
-  }
+    for (int k = 0; k < NCH; ++k) win[j][k] = 0.f;
   const int l_end = min(l0 + kHeadRun, rows);
-  __shared__ float s_part[kHeadWarps][32][33];   // per warp: [sample][lane] partial sums (+1 pad: conflict-free both ways)
-  float(*sp)[33] = s_part[threadIdx.x >> 5];
-  // Software pipeline over groups of 8 rows: while group g is Snake'd and convolved, the 8 rows of group
-  // g+1 are already in flight (two register buffers, loop unrolled by two so no buffer copies).
-  float bufA[8][NCH], bufB[8][NCH];
-  auto load_group = [&](int gi, float (&dst)[8][NCH]) {
+#pragma unroll 1
+  for (int g = 0; g < N_GRAN; ++g) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(kHeadRingGran - 2) : "memory");   // granule g has landed
+    __syncwarp();
+    const float* gp = ring + (g % kHeadRingGran) * (kHeadGranRows * C);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) load_row(l0 + gi * 8 + u + 3, dst[u]);
-  };
-  auto compute_group = [&](int gi, float (&src)[8][NCH]) {
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      act_row(l0 + gi * 8 + u + 3, src[u]);
+    for (int u = 0; u < kHeadGranRows; ++u) {
+      const int ri = g * kHeadGranRows + u;                // row index inside the run (0 = l0 - 3)
 #pragma unroll
       for (int j = 0; j < 6; ++j)
 #pragma unroll
         for (int k = 0; k < NCH; ++k) win[j][k] = win[j + 1][k];
 #pragma unroll
-      for (int k = 0; k < NCH; ++k) win[6][k] = src[u][k];
-      float s = 0.f;
+      for (int k = 0; k < NCH; ++k) win[6][k] = snake_f(gp[u * C + lane + 32 * k], a[k], ia[k]);
+      // window complete for output sample ri - 6
+      const int so = ri - 6;
+      if (so >= 0 && so < kHeadRun) {
+        float s = 0.f;
 #pragma unroll
-      for (int j = 0; j < 7; ++j)
+        for (int j = 0; j < 7; ++j)
 #pragma unroll
-        for (int k = 0; k < NCH; ++k) s = fmaf(wt[j][k], win[j][k], s);
-      sp[(gi & 3) * 8 + u][lane] = s;
+          for (int k = 0; k < NCH; ++k) s = fmaf(wt[j][k], win[j][k], s);
+        sp[so & 31][lane] = s;
+        if ((so & 31) == 31) {   // 32 samples done: transpose-reduce through shared memory, lane L gets sample L
+          __syncwarp();
+          float tot = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) tot += sp[lane][j];
+          __syncwarp();
+          const int l = l0 + so - 31 + lane;
+          if (l < l_end) wav[(size_t)b * rows + l] = tanhf(tot + bias);
+        }
+      }
     }
-  };
-  constexpr int kGroups = kHeadRun / 8;
-  load_group(0, bufA);
-#pragma unroll 1
-  for (int gp = 0; gp < kGroups; gp += 2) {
-    load_group(gp + 1, bufB);
-    compute_group(gp, bufA);
-    if (gp + 2 < kGroups) load_group(gp + 2, bufA);
-    compute_group(gp + 1, bufB);
-    if ((gp & 2) != 0) {   // 32 samples done: transpose-reduce through shared memory, lane L gets sample L
-      __syncwarp();
-      float tot = 0.f;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) tot += sp[lane][j];
-      __syncwarp();
-      const int l = l0 + (gp - 2) * 8 + lane;
-      if (l < l_end) wav[(size_t)b * rows + l] = tanhf(tot + bias);
-    }
+    __syncwarp();            // all lanes are done reading this granule's slot before it is refilled
+    issue(g + kHeadRingGran - 1);
   }
 }
 
@@ -420,19 +507,19 @@ static int launch_dwconv_ln_t(const float* x, int batch, int rows, const float* 
                               OpBuf out_op, cudaStream_t s) {
   const int tiles = (rows + kLnRows - 1) / kLnRows, total = batch * tiles;
   const bool dw = dw_w != nullptr;
-  const size_t smem = 2 * (size_t)(kLnRows + (dw ? 6 : 0)) * NV * 128 * sizeof(float);
+  const size_t smem = kLnStages * (size_t)(kLnRows + (dw ? 6 : 0)) * NV * 128 * sizeof(float);
+  if (smem > 226 * 1024) { set_error("dwconv_ln: %d channels do not fit the shared-memory pipeline", NV * 128); return SPARKCODEC_EINVAL; }
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
     SC_CUDA(cudaGetDevice(&dev));
     SC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / smem));
-  const int grid = std::min(total, num_sms * per_sm);
+  const int grid = std::min(total, num_sms);   // one persistent CTA per SM
   if (dw) {
     static bool done = false;
     if (!done) {
-      SC_CUDA(cudaFuncSetAttribute(dwconv_ln_kernel<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      SC_CUDA(cudaFuncSetAttribute(dwconv_ln_kernel<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       done = true;
     }
     dwconv_ln_kernel<NV, true><<<grid, 256, smem, s>>>(x, rows, dw_w, dw_b, scale, shift, ss, eps, out_f32, out_op,
@@ -440,7 +527,7 @@ static int launch_dwconv_ln_t(const float* x, int batch, int rows, const float* 
   } else {
     static bool done = false;
     if (!done) {
-      SC_CUDA(cudaFuncSetAttribute(dwconv_ln_kernel<NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      SC_CUDA(cudaFuncSetAttribute(dwconv_ln_kernel<NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       done = true;
     }
     dwconv_ln_kernel<NV, false><<<grid, 256, smem, s>>>(x, rows, dw_w, dw_b, scale, shift, ss, eps, out_f32, out_op,
@@ -461,19 +548,31 @@ int launch_dwconv_ln(const float* x, int batch, int rows, int c, const float* dw
   }
 }
 
-int launch_head(const float* x, int batch, int rows, int c, const float* alpha, const float* inv_alpha,
-                const float* w, float bias, float* wav, int, int, cudaStream_t s) {
+template <int NCH>
+static int launch_head_t(const float* x, int batch, int rows, const float* alpha, const float* inv_alpha, const float* w,
+                         float bias, float* wav, cudaStream_t s) {
   const int runs = (rows + kHeadRun - 1) / kHeadRun, total = batch * runs;
   const int grid = (total + kHeadWarps - 1) / kHeadWarps, blk = kHeadWarps * 32;
-  switch (c) {
-    case 32: head_kernel<1><<<grid, blk, 0, s>>>(x, rows, alpha, inv_alpha, w, bias, wav, runs, total); break;
-    case 64: head_kernel<2><<<grid, blk, 0, s>>>(x, rows, alpha, inv_alpha, w, bias, wav, runs, total); break;
-    case 96: head_kernel<3><<<grid, blk, 0, s>>>(x, rows, alpha, inv_alpha, w, bias, wav, runs, total); break;
-    case 128: head_kernel<4><<<grid, blk, 0, s>>>(x, rows, alpha, inv_alpha, w, bias, wav, runs, total); break;
-    default: set_error("head: unsupported channel count %d (32/64/96/128)", c); return SPARKCODEC_EINVAL;
+  const size_t smem = (size_t)kHeadWarps * (kHeadGranRows * kHeadRingGran * NCH * 32 + 32 * 33) * sizeof(float);
+  static bool done = false;
+  if (!done) {
+    SC_CUDA(cudaFuncSetAttribute(head_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    done = true;
   }
+  head_kernel<NCH><<<grid, blk, smem, s>>>(x, rows, alpha, inv_alpha, w, bias, wav, runs, total);
   SC_LAUNCH_CHECK();
   return 0;
+}
+
+int launch_head(const float* x, int batch, int rows, int c, const float* alpha, const float* inv_alpha,
+                const float* w, float bias, float* wav, int, int, cudaStream_t s) {
+  switch (c) {
+    case 32: return launch_head_t<1>(x, batch, rows, alpha, inv_alpha, w, bias, wav, s);
+    case 64: return launch_head_t<2>(x, batch, rows, alpha, inv_alpha, w, bias, wav, s);
+    case 96: return launch_head_t<3>(x, batch, rows, alpha, inv_alpha, w, bias, wav, s);
+    case 128: return launch_head_t<4>(x, batch, rows, alpha, inv_alpha, w, bias, wav, s);
+    default: set_error("head: unsupported channel count %d (32/64/96/128)", c); return SPARKCODEC_EINVAL;
+  }
 }
 
 }  // namespace sparkcodec

@@ -26,6 +26,9 @@ namespace {
 
 constexpr int kResSlots = 4;   // residual slabs in flight (TMA, 16 KB each)
 constexpr int kHaloRowsMax = 184;   // 128 + 6 * 9 (k=7, dilation 9) rounded up to 8
+// Halo tiles in flight (runtime, 2 or 3).  One halo tile feeds all taps of a K chunk; the shared memory it does
+// not need goes to the WEIGHT ring, which must cover the ~2k-cycle refill round trip (MMAs retire -> commit ->
+// producer -> TMA from L2 -> full) or the tensor pipe starves.
 
 constexpr int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
@@ -46,18 +49,25 @@ struct TileCfg {
   // ring 1
   static constexpr int kAHaloBytes = align_up(kHaloRowsMax * BK * 2, 1024);            // per plane
   static constexpr int kStage1Bytes = HALO ? kPlanes * kAHaloBytes : kPlanes * (kABytes + kWBytes);
+  // plain: ring depth fixed at compile time.  HALO: `halo_stages` (2 or 3, chosen per layer at launch time) halo
+  // tiles, the rest of the budget goes to the weight ring -> depths are runtime values, barrier slots are laid
+  // out for the maxima.
   static constexpr int kS1Raw = HALO ? 3 : kBudget / kStage1Bytes;
-  static constexpr int kS1 = kS1Raw > 8 ? 8 : (kS1Raw < 1 ? 1 : kS1Raw);
+  static constexpr int kS1 = kS1Raw > 8 ? 8 : (kS1Raw < 1 ? 1 : kS1Raw);      // (HALO: maximum)
   // ring 2 (HALO only)
   static constexpr int kStage2Bytes = kPlanes * kWBytes;
-  static constexpr int kS2Raw = HALO ? (kBudget - kS1 * kStage1Bytes) / kStage2Bytes : 0;
-  static constexpr int kS2 = kS2Raw > 8 ? 8 : (kS2Raw < 0 ? 0 : kS2Raw);
-  static constexpr int kRingBytes = kS1 * kStage1Bytes + kS2 * kStage2Bytes;
+  static constexpr int kS2Max = 8;
+  static constexpr int s2_for(int halo_stages) {
+    const int raw = (kBudget - halo_stages * kStage1Bytes) / kStage2Bytes;
+    return raw > kS2Max ? kS2Max : (raw < 0 ? 0 : raw);
+  }
+  static constexpr int kS2 = HALO ? kS2Max : 0;                               // barrier slots
+  static constexpr int kRingBytes = HALO ? kBudget : kS1 * kStage1Bytes;
   static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
                                    : (2 * BLOCK_N <= 256) ? 256 : 512;
   static constexpr int kBarBytes = (2 * kS1 + 2 * kS2 + 4 + 2 * kResSlots) * 8 + 16;
   static constexpr int kSmemBytes = kRingBytes + 2 * kSlabBytes + kResBytes + kBarBytes + 1024 /* alignment */;
-  static constexpr bool kValid = HALO ? (kS2 >= 3) : (kS1Raw >= 2);
+  static constexpr bool kValid = HALO ? (s2_for(2) >= 3) : (kS1Raw >= 2);
   static_assert(!kValid || kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
   static_assert(2 * BLOCK_N <= 512, "two accumulator stages must fit TMEM");
   static_assert(kABytes % 1024 == 0 && kWBytes % 1024 == 0, "swizzled tiles must stay 1024 B aligned");
@@ -76,7 +86,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
                     const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                     const __grid_constant__ CUtensorMap tm_res, const ConvGemmParams p) {
   using Cfg = TileCfg<BLOCK_N, BK, NTERMS, RES, HALO>;
-  constexpr int S = Cfg::kS1, S2 = Cfg::kS2;
+  constexpr int SB = Cfg::kS1, S2B = Cfg::kS2;                        // barrier slots (maxima)
+  const int S = HALO ? p.halo_stages : Cfg::kS1;                       // ring depths actually used
+  const int S2 = HALO ? Cfg::s2_for(p.halo_stages) : 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t ring2_base = smem_base + S * Cfg::kStage1Bytes;
@@ -84,14 +96,14 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
   const uint32_t res_base = slab_base + 2 * Cfg::kSlabBytes;       // kResSlots residual slabs (RES only)
   const uint32_t bar_base = res_base + Cfg::kResBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * S + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * S + 2 + a); };
-  auto rfull_bar = [&](int r) { return bar_base + 8u * (2 * S + 4 + r); };
-  auto rempty_bar = [&](int r) { return bar_base + 8u * (2 * S + 4 + kResSlots + r); };
-  auto wfull_bar = [&](int s) { return bar_base + 8u * (2 * S + 4 + 2 * kResSlots + s); };
-  auto wempty_bar = [&](int s) { return bar_base + 8u * (2 * S + 4 + 2 * kResSlots + S2 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 4 + 2 * kResSlots + 2 * S2);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (SB + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * SB + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * SB + 2 + a); };
+  auto rfull_bar = [&](int r) { return bar_base + 8u * (2 * SB + 4 + r); };
+  auto rempty_bar = [&](int r) { return bar_base + 8u * (2 * SB + 4 + kResSlots + r); };
+  auto wfull_bar = [&](int s) { return bar_base + 8u * (2 * SB + 4 + 2 * kResSlots + s); };
+  auto wempty_bar = [&](int s) { return bar_base + 8u * (2 * SB + 4 + 2 * kResSlots + S2B + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * SB + 4 + 2 * kResSlots + 2 * S2B);
   uint32_t* tmem_slot_ptr =
       reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -473,12 +485,12 @@ int choose_bk(int c_in, int block_n, int precision, bool residual) {
   return budget / stage64 >= 3 ? 64 : 32;
 }
 
-// K chunk for the halo mainloop: the W ring must keep >= 3 stages next to 3 halo tiles.
+// K chunk for the halo mainloop: the W ring must keep >= 4 stages next to the halo tiles.
 int choose_bk_halo(int c_in, int block_n, int precision) {
   if (c_in % 64 != 0) return 32;
   const int planes = precision == SPARKCODEC_PREC_FP32 ? 2 : 1;
   const int a64 = planes * align_up(kHaloRowsMax * 64 * 2, 1024), w64 = planes * block_n * 64 * 2;
-  return (192 * 1024 - 3 * a64) / w64 >= 4 ? 64 : 32;
+  return (192 * 1024 - 2 * a64) / w64 >= 4 ? 64 : 32;
 }
 
 int make_weight_tmaps(GemmWeights& w) {
@@ -508,7 +520,7 @@ int fill_params(const GemmWeights& w, int batch, int L, const Epilogue& ep, int 
   p->m_tiles_per_utt = (L + kBlockM - 1) / kBlockM;
   p->num_m_tiles = batch * p->m_tiles_per_utt;
   p->num_n_tiles = w.n_total / w.block_n;
-  p->halo_rows = 0; p->halo_bo_mode = 0;
+  p->halo_rows = 0; p->halo_bo_mode = 0; p->halo_stages = 3;
   p->bias = w.bias; p->rowbias = ep.rowbias; p->residual = ep.residual;
   p->alpha = ep.alpha; p->inv_alpha = ep.inv_alpha; p->act = ep.act;
   p->out_f32 = ep.out_f32; p->out_hi = ep.out_op.hi;
@@ -535,6 +547,10 @@ int launch_conv_gemm_tc(const GemmWeights& w, const OpBuf& a, int batch, int L, 
   int bk = choose_bk(w.c_in, w.block_n, precision, res);
   if (halo) {
     p.halo_rows = (kBlockM + span + 7) / 8 * 8;
+    // a halo tile is consumed over max_taps weight stages: with 7 taps two tiles in flight are plenty and the
+    // weight ring gets the memory; the 2-3 tap polyphase branches turn their halo tiles over quickly
+    static const int forced = [] { const char* e = getenv("SPARKCODEC_HALO_STAGES"); return e ? atoi(e) : 0; }();
+    p.halo_stages = forced ? forced : (max_taps >= 5 ? 2 : 3);
     p.halo_bo_mode = 0;
     if (p.halo_rows > kHaloRowsMax) halo = false;
     else bk = choose_bk_halo(w.c_in, w.block_n, precision);
