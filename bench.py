@@ -38,6 +38,18 @@ def _peaks():
     return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
 
 
+def _ncu_traffic(kernel_name: str, args):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of the same
+    command (profiles/r1_traffic.json: {"<precision> b<batch> t<frames>": {"<kernel name>": bytes}}), else None."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        return d[f"{args.precision} b{args.batch} t{args.frames}"].get(kernel_name)
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 class ClockSampler:
     """Samples nvidia-smi SM clocks + throttle reasons during the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -130,6 +142,14 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: anything a library prints there (NCCL's version banner under
+    # torchrun, ...) is diverted to stderr, the result line goes to the saved descriptor.
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(result_fd, (json.dumps(obj) + "\n").encode())
 
     import torch
     from spark_tts_b200 import BiCodecConfig
@@ -158,7 +178,7 @@ def main():
                                  "sample": info["sample"], "cpu": info["cpu"]},
                 "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
 
     # ------------------------------------------------------------------ our arm
@@ -241,11 +261,22 @@ def main():
         peaks = _peaks()
         # ---- roofline of the dominant kernel: per-launch CUDA events in a separate, untimed pass ----
         if not args.no_profile:
-            model.profile(True)
-            model.detokenize(sem_d, glob_d)
-            rows = model.profile_read()
-            model.profile(False)
-            gemm = [r for r in rows if r["name"].startswith("conv_gemm_tc")]
+            n_prof = 3
+            rows = None
+            for _ in range(n_prof):                      # average launch duration over n_prof profiled passes
+                model.profile(True)
+                model.detokenize(sem_d, glob_d)
+                cur = model.profile_read()
+                model.profile(False)
+                if rows is None:
+                    rows = cur
+                else:
+                    for a, b in zip(rows, cur):
+                        a["ms"] += b["ms"]
+            for r in rows:
+                r["ms"] /= n_prof
+            # tensor-pipe kernels: the generic tcgen05 conv kernel and the fused ResidualUnit kernel
+            gemm = [r for r in rows if r["name"].startswith(("conv_gemm_tc", "resunit_fused"))]
             agg = {}
             for r in gemm:
                 a = agg.setdefault(r["name"], dict(ms=0.0, flops=0.0, n=0))
@@ -259,7 +290,7 @@ def main():
             line["roofline"] = {
                 "bound": "tensor", "kernel": top_name, "launches": top["n"],
                 "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"],
-                "traffic": None, "peak_source": peaks["source"] + ", sustained bf16",
+                "traffic": _ncu_traffic(top_name, args), "peak_source": peaks["source"] + ", sustained bf16",
                 "tensor_work_factor": work, "tensor_pipe_frac": ach * work / peaks["tf_sustained"],
                 "all_gemm": {"achieved": gemm_flops / (gemm_ms * 1e-3) / 1e12,
                              "frac": gemm_flops / (gemm_ms * 1e-3) / 1e12 / peaks["tf_sustained"],
@@ -267,6 +298,13 @@ def main():
                              "share_of_step": gemm_ms / total_ms},
                 "note": "achieved = algorithmic 2*MAC of the convolution / CUDA-event duration; the fp32 mode issues "
                         "3 bf16 MMAs per algorithmic MAC (tensor_work_factor)"}
+            fused = [r for r in rows if r["name"].startswith("resunit_fused")]
+            if fused:
+                f_ms, f_fl = sum(r["ms"] for r in fused), sum(r["flops"] for r in fused)
+                line["roofline"]["resunit_fused"] = {
+                    "launches": len(fused), "achieved": f_fl / (f_ms * 1e-3) / 1e12,
+                    "tensor_pipe_frac": f_fl * work / (f_ms * 1e-3) / 1e12 / peaks["tf_sustained"],
+                    "share_of_step": f_ms / total_ms}
             stream = {}
             for r in rows:
                 key = r["name"] if r["name"] in ("head", "dwconv_ln", "ln") else None
@@ -283,7 +321,7 @@ def main():
             v, info = cpu_reference(cfg, sd, steps=3, warmup=1)
             line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": info["cores"], "kind": "port",
                                     "sample": info["sample"], "cpu": info["cpu"]}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -135,6 +135,20 @@ SPARKCODEC_API int sparkcodec_halo_frames(sparkcodec_handle* h, int* prenet_halo
  * was out of range (message holds which input, position and value). */
 SPARKCODEC_API int sparkcodec_check_tokens(sparkcodec_handle* h, void* stream);
 
+/* Token feed, the step immediately BEFORE the path.  The reference decodes the LLM's
+ * generated ids to text on the host and regex-matches "bicodec_semantic_(\d+)" / "bicodec_global_(\d+)"
+ * (cli/SparkTTS.py:213-228, runtime/triton_trtllm/model_repo/spark_tts/1/model.py:283-295).  Those tokens
+ * are contiguous added-token id ranges of the tokenizer, so the same selection is an order-preserving
+ * compaction on the device:
+ *   token_ids     : device, (batch, n_tokens) generated ids (prompt already trimmed), dtype id_dtype
+ *   semantic_out  : device int32 (batch, n_tokens): row b holds semantic_len[b] codes in generation order
+ *   global_out    : device int32 (batch, max_global): row b holds min(global_len[b], max_global) codes
+ * `*_base` = tokenizer id of "<|bicodec_semantic_0|>" / "<|bicodec_global_0|>".  Stateless, asynchronous. */
+SPARKCODEC_API int sparkcodec_extract_codes(const void* token_ids, int id_dtype, int batch, int n_tokens,
+                             int64_t semantic_base, int codebook_size, int64_t global_base, int global_size,
+                             int32_t* semantic_out, int32_t* semantic_len, int32_t* global_out, int max_global,
+                             int32_t* global_len, void* stream);
+
 /* ---- test / profiling hooks (not needed by a drop-in user) --------------------------------- */
 
 /* Selects tcgen05 (default) or the CUDA-core verification kernels for the dense contractions. */

@@ -9,3 +9,4 @@ from .config import BiCodecConfig, load_bicodec_yaml  # noqa: F401
 from .bicodec import BiCodec  # noqa: F401,E402
 from .audio_tokenizer import BiCodecTokenizer  # noqa: F401,E402
 from .onnx_contract import VocoderSession  # noqa: F401,E402
+from . import token_feed  # noqa: F401,E402

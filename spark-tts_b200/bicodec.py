@@ -189,6 +189,37 @@ class BiCodec:
 
     __call__ = detokenize
 
+    @torch.no_grad()
+    def detokenize_ragged(self, semantic_list, global_tokens: torch.Tensor, precision: Optional[str] = None):
+        """Utterances of DIFFERENT lengths in one call: ``semantic_list[b]`` is (T_b,) or (1, T_b), ``global_tokens``
+        (B, N) or (B, 1, N).  Returns a list of (hop * T_b,) float32 tensors.
+
+        The reference's Triton vocoder can only batch equal lengths (``torch.cat`` of the requests,
+        runtime/triton_trtllm/model_repo/vocoder/1/model.py:72-106).  Here utterances are bucketed by length
+        and every bucket is one batched pass; nothing is padded, because padding frames would leak into the
+        last 67 real frames through the receptive field.  Every waveform is bit-identical to decoding that
+        utterance alone (the kernels are batch-invariant)."""
+        B = len(semantic_list)
+        if global_tokens.shape[0] != B:
+            raise ValueError("one row of global tokens per utterance")
+        glob = global_tokens.reshape(B, -1)
+        rows = [t.reshape(-1) for t in semantic_list]
+        buckets: Dict[int, list] = {}
+        for i, t in enumerate(rows):
+            buckets.setdefault(int(t.numel()), []).append(i)
+        out: list = [None] * B
+        for T, idx in sorted(buckets.items()):
+            if T == 0:
+                for i in idx:
+                    out[i] = torch.empty((0,), dtype=torch.float32, device=glob.device)
+                continue
+            sem = torch.stack([rows[i] for i in idx], dim=0)
+            sel = torch.as_tensor(idx, device=glob.device)
+            wav = self.detokenize(sem, glob.index_select(0, sel).unsqueeze(1).contiguous(), precision)
+            for j, i in enumerate(idx):
+                out[i] = wav[j, 0]
+        return out
+
     # ------------------------------------------------------------------ halves, for time-sharding
     @torch.no_grad()
     def prenet(self, semantic_tokens, global_tokens, precision: Optional[str] = None) -> torch.Tensor:

@@ -858,6 +858,20 @@ int sparkcodec_check_tokens(sparkcodec_handle* h, void* stream) {
   return SPARKCODEC_EINDEX;
 }
 
+int sparkcodec_extract_codes(const void* token_ids, int id_dtype, int batch, int n_tokens, int64_t semantic_base,
+                             int codebook_size, int64_t global_base, int global_size, int32_t* semantic_out,
+                             int32_t* semantic_len, int32_t* global_out, int max_global, int32_t* global_len,
+                             void* stream) {
+  if (batch < 0 || n_tokens < 0 || max_global < 0 || codebook_size < 0 || global_size < 0) { set_error("negative size"); return SPARKCODEC_EINVAL; }
+  if (id_dtype != SPARKCODEC_I32 && id_dtype != SPARKCODEC_I64) { set_error("token dtype must be SPARKCODEC_I32 or SPARKCODEC_I64"); return SPARKCODEC_EINVAL; }
+  if (batch == 0) return 0;
+  if (!token_ids || !semantic_out || !semantic_len || !global_out || !global_len) { set_error("null argument"); return SPARKCODEC_EINVAL; }
+  g_launch_counter = nullptr;
+  return launch_extract_codes(token_ids, id_dtype, batch, n_tokens, semantic_base, codebook_size, global_base, global_size,
+                              semantic_out, semantic_len, global_out, max_global, global_len,
+                              static_cast<cudaStream_t>(stream));
+}
+
 int sparkcodec_set_impl(sparkcodec_handle* h, int impl) {
   if (!h || (impl != SPARKCODEC_IMPL_TC && impl != SPARKCODEC_IMPL_SIMT && impl != SPARKCODEC_IMPL_TC_UNFUSED)) {
     set_error("bad impl");

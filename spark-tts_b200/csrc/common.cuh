@@ -105,6 +105,9 @@ int launch_resunit_fused(const GemmWeights& c7, const GemmWeights& c1, const OpB
 // streaming / token kernels
 int launch_split(const float* x, OpBuf out, size_t n, cudaStream_t s);                 // fp32 -> hi/lo
 int launch_merge(const OpBuf& in, float* out, size_t n, cudaStream_t s);               // hi(+lo) -> fp32
+int launch_extract_codes(const void* ids, int id_dtype, int batch, int n_tokens, long long sem_base, int sem_size,
+                         long long glob_base, int glob_size, int* sem_out, int* sem_len, int* glob_out, int max_global,
+                         int* glob_len, cudaStream_t s);
 int launch_vq_embed(const void* sem, int sem_dtype, int batch, int frames, int t0, int rows,
                     int codebook_size, int codebook_dim, const float* codebook, const float* mat,
                     const float* vec, int c_out, OpBuf out, int* err_flag, cudaStream_t s);

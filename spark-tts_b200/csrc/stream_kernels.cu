@@ -160,6 +160,47 @@ __global__ void small_linear_kernel(const float* __restrict__ x, const float* __
   }
 }
 
+// --------------------------------------------------------------------------------- token feed
+// LLM output ids -> BiCodec codes without a host round trip.  The reference decodes the generated ids to
+// text and regex-matches "bicodec_semantic_(\d+)" / "bicodec_global_(\d+)" (cli/SparkTTS.py:213-228,
+// runtime/triton_trtllm/model_repo/spark_tts/1/model.py:283-295); in the tokenizer those are contiguous
+// added-token id ranges, so the same selection is an ORDER-PRESERVING compaction of the ids that fall into
+// [semantic_base, semantic_base + codebook) resp. [global_base, global_base + global_size).
+// One CTA per utterance; 256 ids per round, warp ballots + a block prefix over the 8 warp totals.
+__global__ void __launch_bounds__(256)
+extract_codes_kernel(const void* __restrict__ ids, int id_dtype, int n_tokens, long long sem_base, int sem_size,
+                     long long glob_base, int glob_size, int* __restrict__ sem_out, int* __restrict__ sem_len,
+                     int* __restrict__ glob_out, int max_global, int* __restrict__ glob_len) {
+  __shared__ int s_cnt[2][8];
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int run[2] = {0, 0};     // codes written so far (same value in every thread)
+  for (int t0 = 0; t0 < n_tokens; t0 += 256) {
+    const int t = t0 + threadIdx.x;
+    long long id = -1;
+    if (t < n_tokens) id = load_token(ids, id_dtype, (size_t)b * n_tokens + t);
+    const bool is_s = id >= sem_base && id < sem_base + sem_size;
+    const bool is_g = id >= glob_base && id < glob_base + glob_size;
+    const unsigned ms = __ballot_sync(0xffffffffu, is_s), mg = __ballot_sync(0xffffffffu, is_g);
+    if (lane == 0) { s_cnt[0][warp] = __popc(ms); s_cnt[1][warp] = __popc(mg); }
+    __syncthreads();
+    int before[2] = {0, 0}, total[2] = {0, 0};
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      if (w < warp) { before[0] += s_cnt[0][w]; before[1] += s_cnt[1][w]; }
+      total[0] += s_cnt[0][w]; total[1] += s_cnt[1][w];
+    }
+    const unsigned lt = (1u << lane) - 1u;
+    if (is_s) sem_out[(size_t)b * n_tokens + run[0] + before[0] + __popc(ms & lt)] = (int)(id - sem_base);
+    if (is_g) {
+      const int pos = run[1] + before[1] + __popc(mg & lt);
+      if (pos < max_global) glob_out[(size_t)b * max_global + pos] = (int)(id - glob_base);
+    }
+    run[0] += total[0]; run[1] += total[1];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { sem_len[b] = run[0]; glob_len[b] = run[1]; }
+}
+
 // ------------------------------------------------------------------- depthwise conv + LayerNorm
 // x (batch, rows, C) fp32 -> [dwconv k=7 pad 3 over rows] -> LayerNorm over C (biased variance, eps)
 // -> * scale[b] + shift[b] -> fp32 and/or operand planes.
@@ -465,6 +506,14 @@ int launch_split(const float* x, OpBuf out, size_t n, cudaStream_t s) {
 int launch_merge(const OpBuf& in, float* out, size_t n, cudaStream_t s) {
   const int grid = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
   merge_kernel<<<grid, 256, 0, s>>>(in, out, n);
+  SC_LAUNCH_CHECK();
+  return 0;
+}
+int launch_extract_codes(const void* ids, int id_dtype, int batch, int n_tokens, long long sem_base, int sem_size,
+                         long long glob_base, int glob_size, int* sem_out, int* sem_len, int* glob_out, int max_global,
+                         int* glob_len, cudaStream_t s) {
+  extract_codes_kernel<<<batch, 256, 0, s>>>(ids, id_dtype, n_tokens, sem_base, sem_size, glob_base, glob_size, sem_out,
+                                             sem_len, glob_out, max_global, glob_len);
   SC_LAUNCH_CHECK();
   return 0;
 }
