@@ -15,6 +15,9 @@
 //                     overlapped with the next tile's MMAs through the second TMEM stage.
 // Precision modes: NTERMS == 1 : A_hi*W_hi (bf16);  NTERMS == 3 : A_hi*W_hi + A_lo*W_hi + A_hi*W_lo
 // (error-compensated split, ~2^-16 relative per product, fp32 accumulate) = the "fp32" mode.
+#include <algorithm>
+#include <cstdlib>
+
 #include "gemm_params.cuh"
 #include "tc_ptx.cuh"
 
@@ -37,11 +40,11 @@ constexpr int align_up(int v, int a) { return (v + a - 1) / a * a; }
 //  * HALO   : (k>1 convs) ring 1 holds A tiles with the conv halo (128 + (k-1)*dilation rows) for one
 //             K-chunk, fetched ONCE and used by all taps through row-offset smem descriptors; ring 2 holds
 //             the per-(tap, K-chunk) W tiles.  Cuts the L2->smem operand traffic by 26-45 %.
-template <int BLOCK_N, int BK, int NTERMS, bool RES, bool HALO>
+template <int BLOCK_N, int BK, int NTERMS, bool RES, bool HALO, int CG>
 struct TileCfg {
   static constexpr int kPlanes = (NTERMS == 3) ? 2 : 1;
   static constexpr int kABytes = kBlockM * BK * 2;
-  static constexpr int kWBytes = BLOCK_N * BK * 2;
+  static constexpr int kWBytes = (BLOCK_N / CG) * BK * 2;   // CTA-pair mode: each CTA stages half of the N rows
   static constexpr int kSlabBytes = kBlockM * 128;   // epilogue transpose slab: 128 rows x 32 fp32, 128B-swizzled
   static constexpr int kResBytes = RES ? kResSlots * kSlabBytes : 0;   // residual slabs (same swizzled format)
   // smem ring budget: 227 KB - 2 slabs - residual ring - barriers - alignment slack
@@ -80,12 +83,12 @@ constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kResWarp = 2 + kEpiWarps;
 constexpr int kNumThreads = (3 + kEpiWarps) * 32;
 
-template <int BLOCK_N, int BK, int NTERMS, bool RES, bool HALO>
+template <int BLOCK_N, int BK, int NTERMS, bool RES, bool HALO, int CG>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                     const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                     const __grid_constant__ CUtensorMap tm_res, const ConvGemmParams p) {
-  using Cfg = TileCfg<BLOCK_N, BK, NTERMS, RES, HALO>;
+  using Cfg = TileCfg<BLOCK_N, BK, NTERMS, RES, HALO, CG>;
   constexpr int SB = Cfg::kS1, S2B = Cfg::kS2;                        // barrier slots (maxima)
   const int S = HALO ? p.halo_stages : Cfg::kS1;                       // ring depths actually used
   const int S2 = HALO ? Cfg::s2_for(p.halo_stages) : 0;
@@ -109,8 +112,26 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int k_chunks = p.c_in / BK;
+  // Tiles are dealt to clusters of CG CTAs: the CTAs of a cluster take CG consecutive M tiles of the SAME N tile
+  // (CG == 2: one M = 256 pair MMA, each CTA stages half of the weight rows).  A trailing M tile without a
+  // partner is a dummy (all rows out of range: TMA zero fill, no stores).
+  const int rank = CG > 1 ? (int)cluster_ctarank() : 0;
+  const bool leader = rank == 0;
+  const int cid = (int)blockIdx.x / CG, ncl = (int)gridDim.x / CG;
+  const int num_super = ((p.num_m_tiles + CG - 1) / CG) * p.num_n_tiles;
+  struct Tile { int n0, b, l0; };
+  auto tile_of = [&](int st) {
+    Tile t;
+    t.n0 = (st % p.num_n_tiles) * BLOCK_N;
+    const int m_tile = (st / p.num_n_tiles) * CG + rank;
+    const bool valid = m_tile < p.num_m_tiles;
+    t.b = valid ? m_tile / p.m_tiles_per_utt : p.batch;              // batch = out of range
+    t.l0 = valid ? (m_tile % p.m_tiles_per_utt) * kBlockM : p.L;     // rows >= L are never stored
+    return t;
+  };
+  // barrier that collects this stage's TMA bytes: the leader's (pair mode) or our own
+  auto tx_bar = [&](uint32_t bar) { return CG > 1 ? mapa_shared(bar, 0) : bar; };
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_a_hi);
@@ -129,7 +150,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), kEpiThreads);
+      mbar_init(tempty_bar(a), CG * kEpiThreads);   // pair mode: both CTAs' epilogues release the leader's MMA warp
     }
     for (int r = 0; r < kResSlots; ++r) {
       mbar_init(rfull_bar(r), 1);
@@ -137,9 +158,13 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (warp == 1) {
+    if (CG > 1) tmem_alloc_cg2<Cfg::kTmemCols>(tmem_slot);
+    else tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CG > 1) cluster_sync_all();   // the peer's barriers exist before any remote arrive / TMA completion
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -147,11 +172,18 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     // ================================ TMA producer ================================
     if (elect_one()) {
       uint32_t stage = 0, phase = 0, ws = 0, wphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;
-        const int b = m_tile / p.m_tiles_per_utt;
-        const int l0 = (m_tile % p.m_tiles_per_utt) * kBlockM;
-        const int n0 = n_tile * BLOCK_N;
+      const int wrow = rank * (BLOCK_N / CG);   // this CTA's share of the weight rows of an N tile
+      auto load_a = [&](uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+        if (CG > 1) tma_load_3d_cg2(dst, map, tx_bar(bar), c0, c1, c2);
+        else tma_load_3d(dst, map, bar, c0, c1, c2);
+      };
+      auto load_w = [&](uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+        if (CG > 1) tma_load_2d_cg2(dst, map, tx_bar(bar), c0, c1 + wrow);
+        else tma_load_2d(dst, map, bar, c0, c1);
+      };
+      for (int st = cid; st < num_super; st += ncl) {
+        const Tile t = tile_of(st);
+        const int b = t.b, l0 = t.l0, n0 = t.n0;
         const int ph = n0 / p.taps.cols_per_phase;
         const int ntaps = p.taps.ntaps[ph];
         if (HALO) {
@@ -159,17 +191,16 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
           for (int kc = 0; kc < k_chunks; ++kc) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t sa = smem_base + stage * Cfg::kStage1Bytes;
-            mbar_expect_tx(full_bar(stage), a_tx);
-            tma_load_3d(sa, &tm_a_hi, full_bar(stage), kc * BK, l0 + p.taps.shift[ph][0], b);
-            if (NTERMS == 3)
-              tma_load_3d(sa + Cfg::kAHaloBytes, &tm_a_lo, full_bar(stage), kc * BK, l0 + p.taps.shift[ph][0], b);
+            if (leader) mbar_expect_tx(full_bar(stage), CG * a_tx);   // bytes of every CTA of the pair
+            load_a(sa, &tm_a_hi, full_bar(stage), kc * BK, l0 + p.taps.shift[ph][0], b);
+            if (NTERMS == 3) load_a(sa + Cfg::kAHaloBytes, &tm_a_lo, full_bar(stage), kc * BK, l0 + p.taps.shift[ph][0], b);
             if (++stage == S) { stage = 0; phase ^= 1u; }
             for (int j = 0; j < ntaps; ++j) {
               mbar_wait(wempty_bar(ws), wphase ^ 1u);
               const uint32_t sw = ring2_base + ws * Cfg::kStage2Bytes;
-              mbar_expect_tx(wfull_bar(ws), Cfg::kStage2Bytes);
-              tma_load_2d(sw, &tm_w_hi, wfull_bar(ws), j * p.c_in + kc * BK, n0);
-              if (NTERMS == 3) tma_load_2d(sw + Cfg::kWBytes, &tm_w_lo, wfull_bar(ws), j * p.c_in + kc * BK, n0);
+              if (leader) mbar_expect_tx(wfull_bar(ws), CG * Cfg::kStage2Bytes);
+              load_w(sw, &tm_w_hi, wfull_bar(ws), j * p.c_in + kc * BK, n0);
+              if (NTERMS == 3) load_w(sw + Cfg::kWBytes, &tm_w_lo, wfull_bar(ws), j * p.c_in + kc * BK, n0);
               if (++ws == S2) { ws = 0; wphase ^= 1u; }
             }
           }
@@ -180,12 +211,12 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
               mbar_wait(empty_bar(stage), phase ^ 1u);
               const uint32_t sa = smem_base + stage * Cfg::kStage1Bytes;
               const uint32_t sw = sa + Cfg::kPlanes * Cfg::kABytes;
-              mbar_expect_tx(full_bar(stage), Cfg::kStage1Bytes);
-              tma_load_3d(sa, &tm_a_hi, full_bar(stage), kc * BK, row, b);
-              tma_load_2d(sw, &tm_w_hi, full_bar(stage), j * p.c_in + kc * BK, n0);
+              if (leader) mbar_expect_tx(full_bar(stage), CG * Cfg::kStage1Bytes);
+              load_a(sa, &tm_a_hi, full_bar(stage), kc * BK, row, b);
+              load_w(sw, &tm_w_hi, full_bar(stage), j * p.c_in + kc * BK, n0);
               if (NTERMS == 3) {
-                tma_load_3d(sa + Cfg::kABytes, &tm_a_lo, full_bar(stage), kc * BK, row, b);
-                tma_load_2d(sw + Cfg::kWBytes, &tm_w_lo, full_bar(stage), j * p.c_in + kc * BK, n0);
+                load_a(sa + Cfg::kABytes, &tm_a_lo, full_bar(stage), kc * BK, row, b);
+                load_w(sw + Cfg::kWBytes, &tm_w_lo, full_bar(stage), j * p.c_in + kc * BK, n0);
               }
               if (++stage == S) { stage = 0; phase ^= 1u; }
             }
@@ -195,11 +226,20 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc<BLOCK_N>();
+    // pair mode: the leader CTA's thread issues the M = 256 MMAs for both CTAs
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = CG > 1 ? make_idesc_cg2<BLOCK_N>() : make_idesc<BLOCK_N>();
+      auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t accumulate) {
+        if (CG > 1) umma_bf16_cg2(d, a, b, idesc, accumulate);
+        else umma_bf16(d, a, b, idesc, accumulate);
+      };
+      auto commit = [&](uint32_t bar) {     // pair mode: arrives on the barrier at this offset in BOTH CTAs
+        if (CG > 1) umma_commit_cg2(bar);
+        else umma_commit(bar);
+      };
       uint32_t stage = 0, phase = 0, iter = 0, ws = 0, wphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
-        const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
+      for (int st = cid; st < num_super; st += ncl, ++iter) {
+        const int n0 = (st % p.num_n_tiles) * BLOCK_N;
         const int ph = n0 / p.taps.cols_per_phase;
         const int ntaps = p.taps.ntaps[ph];
         const uint32_t acc = iter & 1u, acc_phase = (iter >> 1) & 1u;
@@ -219,20 +259,20 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
               const uint64_t a_hi = make_smem_desc_rows<BK>(sa + a_off, p.halo_bo_mode);
               const uint64_t w_hi = make_smem_desc<BK>(sw);
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, a_hi + 2 * k, w_hi + 2 * k, idesc, (kc | j | k) != 0);
+              for (int k = 0; k < BK / 16; ++k) mma(d_tmem, a_hi + 2 * k, w_hi + 2 * k, (kc | j | k) != 0);
               if (NTERMS == 3) {
                 const uint64_t a_lo = make_smem_desc_rows<BK>(sa + Cfg::kAHaloBytes + a_off, p.halo_bo_mode);
                 const uint64_t w_lo = make_smem_desc<BK>(sw + Cfg::kWBytes);
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, a_lo + 2 * k, w_hi + 2 * k, idesc, 1u);
+                for (int k = 0; k < BK / 16; ++k) mma(d_tmem, a_lo + 2 * k, w_hi + 2 * k, 1u);
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, a_hi + 2 * k, w_lo + 2 * k, idesc, 1u);
+                for (int k = 0; k < BK / 16; ++k) mma(d_tmem, a_hi + 2 * k, w_lo + 2 * k, 1u);
               }
-              umma_commit(wempty_bar(ws));
+              commit(wempty_bar(ws));
               if (++ws == S2) { ws = 0; wphase ^= 1u; }
             }
-            umma_commit(empty_bar(stage));                        // halo tile free once all its taps retired
-            if (kc == k_chunks - 1) umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+            commit(empty_bar(stage));                        // halo tile free once all its taps retired
+            if (kc == k_chunks - 1) commit(tfull_bar(acc));  // accumulator complete -> epilogue
             if (++stage == S) { stage = 0; phase ^= 1u; }
           }
         } else {
@@ -245,17 +285,17 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
             const uint64_t a_hi = make_smem_desc<BK>(sa), w_hi = make_smem_desc<BK>(sw);
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)   // +32 B (=2 in >>4 units) per 16-element K step inside the swizzle row
-              umma_bf16(d_tmem, a_hi + 2 * k, w_hi + 2 * k, idesc, (ki | k) != 0);
+              mma(d_tmem, a_hi + 2 * k, w_hi + 2 * k, (ki | k) != 0);
             if (NTERMS == 3) {
               const uint64_t a_lo = make_smem_desc<BK>(sa + Cfg::kABytes);
               const uint64_t w_lo = make_smem_desc<BK>(sw + Cfg::kWBytes);
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, a_lo + 2 * k, w_hi + 2 * k, idesc, 1u);
+              for (int k = 0; k < BK / 16; ++k) mma(d_tmem, a_lo + 2 * k, w_hi + 2 * k, 1u);
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, a_hi + 2 * k, w_lo + 2 * k, idesc, 1u);
+              for (int k = 0; k < BK / 16; ++k) mma(d_tmem, a_hi + 2 * k, w_lo + 2 * k, 1u);
             }
-            umma_commit(empty_bar(stage));                    // smem slot free once these MMAs retire
-            if (ki == n_k - 1) umma_commit(tfull_bar(acc));   // accumulator complete -> epilogue
+            commit(empty_bar(stage));                    // smem slot free once these MMAs retire
+            if (ki == n_k - 1) commit(tfull_bar(acc));   // accumulator complete -> epilogue
             if (++stage == S) { stage = 0; phase ^= 1u; }
           }
         }
@@ -268,11 +308,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     if (RES && elect_one()) {
       prefetch_tmap(&tm_res);
       uint32_t rs = 0, rphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;
-        const int b = m_tile / p.m_tiles_per_utt;
-        const int l0 = (m_tile % p.m_tiles_per_utt) * kBlockM;
-        const int n0 = n_tile * BLOCK_N;
+      for (int st = cid; st < num_super; st += ncl) {
+        const Tile t = tile_of(st);
+        const int b = t.b, l0 = t.l0, n0 = t.n0;
         for (int c = 0; c < BLOCK_N; c += 32) {
           mbar_wait(rempty_bar(rs), rphase ^ 1u);
           mbar_expect_tx(rfull_bar(rs), Cfg::kSlabBytes);
@@ -299,11 +337,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     // The residual (fp32, may alias out_f32: every element is read by TMA before the thread that
     // owns it stores the sum) arrives through the slab ring filled by warp 6.
     uint32_t rs = 0, rphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
-      const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;
-      const int b = m_tile / p.m_tiles_per_utt;
-      const int l0 = (m_tile % p.m_tiles_per_utt) * kBlockM;
-      const int n0 = n_tile * BLOCK_N;
+    for (int st = cid; st < num_super; st += ncl, ++iter) {
+      const Tile t = tile_of(st);
+      const int b = t.b, l0 = t.l0, n0 = t.n0;
       const uint32_t acc = iter & 1u, acc_phase = (iter >> 1) & 1u;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
@@ -329,7 +365,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
         }
         if (c + 32 >= BLOCK_N) {   // accumulator fully drained: hand the TMEM stage back to the MMA warp
           tc_fence_before();
-          mbar_arrive(tempty_bar(acc));
+          if (CG > 1) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));   // the leader's MMA warp waits for both CTAs
+          else mbar_arrive(tempty_bar(acc));
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         uint32_t rslab = 0;
@@ -365,10 +402,12 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG > 1) cluster_sync_all();   // no CTA leaves while its peer may still complete bytes / arrive on its barriers
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if (CG > 1) tmem_dealloc_cg2<Cfg::kTmemCols>(tmem_base);
+    else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
@@ -404,10 +443,10 @@ int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dim
   return 0;
 }
 
-template <int BLOCK_N, int BK, int NTERMS, bool RES, bool HALO>
+template <int BLOCK_N, int BK, int NTERMS, bool RES, bool HALO, int CG>
 int launch_inst(const GemmWeights& w, const OpBuf& a, int batch, int L, const ConvGemmParams& p, int num_sms,
                 cudaStream_t stream) {
-  using Cfg = TileCfg<BLOCK_N, BK, NTERMS, RES, HALO>;
+  using Cfg = TileCfg<BLOCK_N, BK, NTERMS, RES, HALO, CG>;
   if constexpr (!Cfg::kValid) {
     set_error("tile %dx%d (terms %d, residual %d, halo %d) does not fit shared memory", BLOCK_N, BK, NTERMS,
               (int)RES, (int)HALO);
@@ -427,17 +466,42 @@ int launch_inst(const GemmWeights& w, const OpBuf& a, int batch, int L, const Co
     const uint32_t rbox[3] = {32u, (uint32_t)kBlockM, 1u};
     SC_TRY(encode_map(&t_res, p.residual, 3, rdims, rstr, rbox, 64, false, /*fp32=*/true));
   }
-  auto kern = conv_gemm_tc_kernel<BLOCK_N, BK, NTERMS, RES, HALO>;
-  static bool attr_done = false;   // per instantiation
-  if (!attr_done) {
-    SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_done = true;
-  }
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
-  const int grid = tiles < num_sms ? tiles : num_sms;
+  // weight maps: the cached (BK x BLOCK_N) boxes, or (BK x BLOCK_N / 2) boxes for a CTA pair
   constexpr int mi = BK == 64 ? 0 : 1;
-  kern<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta_hi, ta_lo, w.tmap_hi[mi],
-                                                        NTERMS == 3 ? w.tmap_lo[mi] : w.tmap_hi[mi], t_res, p);
+  CUtensorMap tw_hi = w.tmap_hi[mi], tw_lo = NTERMS == 3 ? w.tmap_lo[mi] : w.tmap_hi[mi];
+  if (CG > 1) {
+    const uint64_t wd[2] = {(uint64_t)w.kt * w.c_in, (uint64_t)w.n_total};
+    const uint64_t ws[1] = {(uint64_t)w.kt * w.c_in * 2};
+    const uint32_t wb[2] = {(uint32_t)BK, (uint32_t)(BLOCK_N / CG)};
+    SC_TRY(encode_map(&tw_hi, w.w_hi, 2, wd, ws, wb, BK, true));
+    if (NTERMS == 3) SC_TRY(encode_map(&tw_lo, w.w_lo, 2, wd, ws, wb, BK, true));
+    else tw_lo = tw_hi;
+  }
+  auto kern = conv_gemm_tc_kernel<BLOCK_N, BK, NTERMS, RES, HALO, CG>;
+  static int max_clusters = 0;   // per instantiation
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cfg.attrs = attr;
+  cfg.numAttrs = CG > 1 ? 1 : 0;
+  if (!max_clusters) {
+    SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    if (CG > 1) {
+      cfg.gridDim = dim3(num_sms / CG * CG);
+      SC_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+      if (max_clusters < 1) { set_error("conv_gemm: no cluster of %d CTAs fits the device", CG); return SPARKCODEC_ECUDA; }
+    } else {
+      max_clusters = num_sms;
+    }
+  }
+  const int supers = ((p.num_m_tiles + CG - 1) / CG) * p.num_n_tiles;
+  const int clusters = std::min(std::min(supers, max_clusters), num_sms / CG);
+  cfg.gridDim = dim3(clusters * CG);
+  SC_CUDA(cudaLaunchKernelEx(&cfg, kern, ta_hi, ta_lo, tw_hi, tw_lo, t_res, p));
   SC_LAUNCH_CHECK();
   return 0;
   }
@@ -543,6 +607,16 @@ int launch_conv_gemm_tc(const GemmWeights& w, const OpBuf& a, int batch, int L, 
     if (nt > 0 && w.taps.shift[r][nt - 1] - w.taps.shift[r][0] > span) span = w.taps.shift[r][nt - 1] - w.taps.shift[r][0];
     for (int j = 1; j < nt; ++j) ascending &= w.taps.shift[r][j] > w.taps.shift[r][j - 1];
   }
+  // CTA-pair mode (cta_group::2, M = 256): each CTA stages half of the weight rows, which halves the weight
+  // traffic per SM and doubles the depth of the weight ring in tensor-pipe time.  SPARKCODEC_PAIR=0 disables.
+  // Measured per layer (profiles/r1_pair_mode_ab.txt): the pair wins where a tile carries a long reduction
+  // (k7 convs, the wide up-samplers, pw2), and loses where the tile is short and the epilogue / HBM dominates
+  // (pw1, the narrow 1x1 convs): the two CTAs of a pair run in lock step, which costs overlap there.
+  // SPARKCODEC_PAIR = 0 never, 1 heuristic (default), 2 always.
+  static const int pair_mode = [] { const char* e = getenv("SPARKCODEC_PAIR"); return e ? atoi(e) : 1; }();
+  const int k_total = max_taps * w.c_in;
+  const bool pair = p.num_m_tiles >= 2 &&
+                    (pair_mode == 2 || (pair_mode == 1 && k_total >= (f32 ? 768 : 1536)));
   bool halo = g_halo_mode != 0 && max_taps > 1 && ascending && !res;
   int bk = choose_bk(w.c_in, w.block_n, precision, res);
   if (halo) {
@@ -555,18 +629,22 @@ int launch_conv_gemm_tc(const GemmWeights& w, const OpBuf& a, int batch, int L, 
     if (p.halo_rows > kHaloRowsMax) halo = false;
     else bk = choose_bk_halo(w.c_in, w.block_n, precision);
   }
-#define SC_INST(BN, BKK)                                                                          \
-  if (w.block_n == BN && bk == BKK) {                                                             \
-    if (halo)                                                                                     \
-      return f32 ? launch_inst<BN, BKK, 3, false, true>(w, a, batch, L, p, num_sms, stream)       \
-                 : launch_inst<BN, BKK, 1, false, true>(w, a, batch, L, p, num_sms, stream);      \
-    return res ? (f32 ? launch_inst<BN, BKK, 3, true, false>(w, a, batch, L, p, num_sms, stream)  \
-                      : launch_inst<BN, BKK, 1, true, false>(w, a, batch, L, p, num_sms, stream)) \
-               : (f32 ? launch_inst<BN, BKK, 3, false, false>(w, a, batch, L, p, num_sms, stream) \
-                      : launch_inst<BN, BKK, 1, false, false>(w, a, batch, L, p, num_sms, stream)); \
+#define SC_INST2(BN, BKK, CGV)                                                                         \
+    if (halo)                                                                                          \
+      return f32 ? launch_inst<BN, BKK, 3, false, true, CGV>(w, a, batch, L, p, num_sms, stream)       \
+                 : launch_inst<BN, BKK, 1, false, true, CGV>(w, a, batch, L, p, num_sms, stream);      \
+    return res ? (f32 ? launch_inst<BN, BKK, 3, true, false, CGV>(w, a, batch, L, p, num_sms, stream)  \
+                      : launch_inst<BN, BKK, 1, true, false, CGV>(w, a, batch, L, p, num_sms, stream)) \
+               : (f32 ? launch_inst<BN, BKK, 3, false, false, CGV>(w, a, batch, L, p, num_sms, stream) \
+                      : launch_inst<BN, BKK, 1, false, false, CGV>(w, a, batch, L, p, num_sms, stream));
+#define SC_INST(BN, BKK)                   \
+  if (w.block_n == BN && bk == BKK) {      \
+    if (pair) { SC_INST2(BN, BKK, 2) }     \
+    SC_INST2(BN, BKK, 1)                   \
   }
   SC_INST(256, 64) SC_INST(192, 64) SC_INST(128, 64) SC_INST(96, 64) SC_INST(64, 64)
   SC_INST(256, 32) SC_INST(192, 32) SC_INST(128, 32) SC_INST(96, 32) SC_INST(64, 32)
+#undef SC_INST2
 #undef SC_INST
   set_error("no tcgen05 instantiation for block_n=%d bk=%d", w.block_n, bk);
   return SPARKCODEC_EINVAL;
