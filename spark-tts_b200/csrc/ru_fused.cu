@@ -66,14 +66,14 @@ struct RuParams {
 };
 constexpr int kRuTraceEvents = 32, kRuTraceTiles = 16;
 
-template <int C, int NTERMS>
+template <int C, int NTERMS, int PG>   // PG = CTAs sharing one MMA (1, or 2 = cta_group::2 pair)
 struct RuCfg {
   static constexpr int kPlanes = NTERMS == 3 ? 2 : 1;
   static constexpr int kChunks = C / 32;                           // K chunks of 32 channels
   static constexpr int G = NTERMS == 3 ? 1 : (C == 96 ? 3 : 2);   // K chunks per ring stage
   static constexpr int kGroups = kChunks / G;
   static constexpr int kAStage = G * kPlanes * kRuAChunkBytes;
-  static constexpr int kWChunk = C * 64;                           // C rows x 64 B (one plane)
+  static constexpr int kWChunk = (C / PG) * 64;                    // C / PG rows x 64 B (one plane): a CTA pair splits the N rows
   static constexpr int kWStage = G * kPlanes * kWChunk;
   static constexpr int NB1 = C <= 96 ? 2 : 1;                      // acc1 / acc2 buffers in TMEM
   static constexpr int NB2 = NB1;
@@ -113,13 +113,15 @@ __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, bool 
   acc += clock64() - t0;
 }
 
-template <int C, int NTERMS, int CL>
+template <int C, int NTERMS, int CL, bool PAIR>
 __global__ void __launch_bounds__(kRuThreads, 1)
 resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                      const __grid_constant__ CUtensorMap tm_w7_hi, const __grid_constant__ CUtensorMap tm_w7_lo,
                      const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_constant__ CUtensorMap tm_w1_lo,
                      const __grid_constant__ CUtensorMap tm_res, const RuParams p) {
-  using Cfg = RuCfg<C, NTERMS>;
+  static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of two");
+  constexpr int PG = PAIR ? 2 : 1;
+  using Cfg = RuCfg<C, NTERMS, PG>;
   constexpr int SA = Cfg::SA, SW = Cfg::SW, SR = Cfg::SR, NB1 = Cfg::NB1, NB2 = Cfg::NB2;
   constexpr int G = Cfg::G, SKEW = Cfg::SKEW, NMID = Cfg::kNumMid;
   extern __shared__ uint8_t smem_raw[];
@@ -145,10 +147,23 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  // Tiles are dealt to CLUSTERS: the CL CTAs of a cluster work on CL consecutive tiles in lock step and share
-  // every weight stage (each CTA fetches 1/CL of it and multicasts).  A trailing partial group computes a
-  // dummy tile (all rows out of range: TMA zero fill, stores masked).
+  // Tiles are dealt to CLUSTERS of CL CTAs that work on CL consecutive tiles in lock step and share the weights:
+  //  * PAIR (cta_group::2): the two CTAs run ONE M = 256 MMA stream issued by the leader; each CTA stages its own
+  //    128 activation rows and HALF of the weight rows of every stage (the tensor cores read the other half from
+  //    the peer), so the weight traffic per SM halves and the weight ring is twice as deep in tensor-pipe time.
+  //    Best where the tensor pipe is the limit (fp32 mode: 3 MMAs per MAC).
+  //  * multicast (CL == 2, !PAIR): independent M = 128 MMA streams; every weight stage is fetched half by each CTA
+  //    and multicast to both (half the L2 reads, same shared-memory footprint).  Best where the epilogue is the
+  //    limit (bf16 mode): the CTAs are only coupled through the weight ring.
+  // A trailing tile without a partner is a dummy (all rows out of range: TMA zero fill, stores masked).
   const int cl_rank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const bool leader = !PAIR || cl_rank == 0;       // owner of the barriers the MMA issuer waits on
+  // barrier of the pair's leader CTA / arrive on it from either CTA
+  auto lead = [&](uint32_t bar) { return PAIR ? mapa_shared(bar, 0) : bar; };
+  auto arrive_lead = [&](uint32_t bar) {
+    if (PAIR) mbar_arrive_cluster(mapa_shared(bar, 0));
+    else mbar_arrive(bar);
+  };
   const int cid = (int)blockIdx.x / CL, ncl = (int)gridDim.x / CL;
   const int n_groups = (p.num_tiles + CL - 1) / CL;
   const int n_my = cid < n_groups ? (n_groups - cid + ncl - 1) / ncl : 0;
@@ -171,14 +186,17 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
       prefetch_tmap(&tm_w1_lo);
     }
     for (int s = 0; s < SA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
-    for (int s = 0; s < SW; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), CL); }
-    for (int s = 0; s < NMID; ++s) mbar_init(mid_full(0, s), kRuMidArrivals);
+    for (int s = 0; s < SW; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), PAIR ? 1 : CL); }
+    for (int s = 0; s < NMID; ++s) mbar_init(mid_full(0, s), PG * kRuMidArrivals);   // pair: both CTAs' mid teams
     for (int s = 0; s < NB1; ++s) mbar_init(acc1_full(s), 1);
-    for (int s = 0; s < NB2; ++s) { mbar_init(acc2_full(s), 1); mbar_init(acc2_empty(s), kRuTeamThreads); }
+    for (int s = 0; s < NB2; ++s) { mbar_init(acc2_full(s), 1); mbar_init(acc2_empty(s), PG * kRuTeamThreads); }
     for (int s = 0; s < SR; ++s) { mbar_init(res_full(s), 1); mbar_init(res_empty(s), kRuTeamThreads); }
     fence_barrier_init();
   }
-  if (warp == kRuMmaWarp) tmem_alloc<512>(tmem_slot);
+  if (warp == kRuMmaWarp) {
+    if (PAIR) tmem_alloc_cg2<512>(tmem_slot);
+    else tmem_alloc<512>(tmem_slot);
+  }
   tc_fence_before();
   if (CL > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast / remote arrive
   else __syncthreads();
@@ -204,12 +222,17 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
         }
         for (int kg = 0; kg < Cfg::kGroups; ++kg) {
           mbar_wait(a_empty(as), aph ^ 1u);
-          mbar_expect_tx(a_full(as), a_tx);
+          if (leader) mbar_expect_tx(a_full(as), PG * a_tx);   // pair: bytes of both CTAs land on the leader's barrier
 #pragma unroll
           for (int g = 0; g < G; ++g) {
             const uint32_t sa = a_base + as * Cfg::kAStage + (uint32_t)(g * Cfg::kPlanes) * kRuAChunkBytes;
-            tma_load_3d(sa, &tm_a_hi, a_full(as), (kg * G + g) * 32, row0, b);
-            if (NTERMS == 3) tma_load_3d(sa + kRuAChunkBytes, &tm_a_lo, a_full(as), (kg * G + g) * 32, row0, b);
+            if (PAIR) {
+              tma_load_3d_cg2(sa, &tm_a_hi, lead(a_full(as)), (kg * G + g) * 32, row0, b);
+              if (NTERMS == 3) tma_load_3d_cg2(sa + kRuAChunkBytes, &tm_a_lo, lead(a_full(as)), (kg * G + g) * 32, row0, b);
+            } else {
+              tma_load_3d(sa, &tm_a_hi, a_full(as), (kg * G + g) * 32, row0, b);
+              if (NTERMS == 3) tma_load_3d(sa + kRuAChunkBytes, &tm_a_lo, a_full(as), (kg * G + g) * 32, row0, b);
+            }
           }
           if (++as == SA) { as = 0; aph ^= 1u; }
         }
@@ -218,14 +241,16 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
   } else if (warp == kRuTmaWWarp) {
     // ================================ TMA producer: weights ================================
     // One ring for the W7 tap tiles of tile `it` and the W1 tiles of tile `it - SKEW`, in the order the MMA
-    // warp consumes them.  With CL > 1 this CTA fetches rows [cl_rank * C / CL, +C / CL) of every chunk and
-    // multicasts them to all CTAs of the cluster; a stage is refilled once EVERY CTA's MMAs released it.
+    // warp consumes them.  Pair mode: this CTA fetches rows [cl_rank * C / 2, +C / 2) of every chunk into its
+    // OWN shared memory and completes the bytes on the leader's barrier.  Multicast mode: it fetches the same
+    // rows but multicasts them into BOTH CTAs' full-height chunks.
     if (elect_one()) {
       uint32_t ws = 0, wph = 0;
       constexpr uint16_t mask = (uint16_t)((1u << CL) - 1u);
-      const uint32_t row_off = (uint32_t)(cl_rank * (C / CL)) * 64u;
+      const uint32_t mc_off = (uint32_t)(cl_rank * (C / CL)) * 64u;
       auto load_w = [&](uint32_t dst, const CUtensorMap* map, uint32_t bar, int k0) {
-        if (CL > 1) tma_load_2d_mc(dst + row_off, map, bar, k0, cl_rank * (C / CL), mask);
+        if (PAIR) tma_load_2d_cg2(dst, map, lead(bar), k0, cl_rank * (C / CL));
+        else if (CL > 1) tma_load_2d_mc(dst + mc_off, map, bar, k0, cl_rank * (C / CL), mask);
         else tma_load_2d(dst, map, bar, k0, 0);
       };
       for (int it = 0; it < n_my + SKEW; ++it) {
@@ -233,7 +258,7 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
           for (int kg = 0; kg < Cfg::kGroups; ++kg) {
             for (int j = 0; j < 7; ++j) {
               mbar_wait(w_empty(ws), wph ^ 1u);
-              mbar_expect_tx(w_full(ws), Cfg::kWStage);
+              if (leader) mbar_expect_tx(w_full(ws), PG * Cfg::kWStage);
 #pragma unroll
               for (int g = 0; g < G; ++g) {
                 const uint32_t sw = w_base + ws * Cfg::kWStage + (uint32_t)(g * Cfg::kPlanes) * Cfg::kWChunk;
@@ -247,7 +272,7 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
         if (it >= SKEW) {
           for (int kg = 0; kg < Cfg::kGroups; ++kg) {
             mbar_wait(w_empty(ws), wph ^ 1u);
-            mbar_expect_tx(w_full(ws), Cfg::kWStage);
+            if (leader) mbar_expect_tx(w_full(ws), PG * Cfg::kWStage);
 #pragma unroll
             for (int g = 0; g < G; ++g) {
               const uint32_t sw = w_base + ws * Cfg::kWStage + (uint32_t)(g * Cfg::kPlanes) * Cfg::kWChunk;
@@ -261,8 +286,25 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
     }
   } else if (warp == kRuMmaWarp) {
     // ================================ MMA issuer ================================
-    if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc<C>();
+    // pair mode: the leader's thread issues the M = 256 MMAs for both CTAs
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = PAIR ? make_idesc_cg2<C>() : make_idesc<C>();
+      auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t accumulate) {
+        if (PAIR) umma_bf16_cg2(d, a, b, idesc, accumulate);
+        else umma_bf16(d, a, b, idesc, accumulate);
+      };
+      auto mma_ts = [&](uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t accumulate) {
+        if (PAIR) umma_bf16_ts_cg2(d, a_tmem, b, idesc, accumulate);
+        else umma_bf16_ts(d, a_tmem, b, idesc, accumulate);
+      };
+      auto commit = [&](uint32_t bar) {     // pair mode: arrives on the barrier at this offset in BOTH CTAs
+        if (PAIR) umma_commit_cg2(bar);
+        else umma_commit(bar);
+      };
+      auto commit_w = [&](uint32_t bar) {   // weight slots are shared by the cluster in pair AND multicast mode
+        if (PAIR) umma_commit_cg2(bar);
+        else umma_commit_cl<CL>(bar);
+      };
       uint32_t as = 0, aph = 0, ws = 0, wph = 0;
       const bool timed = p.dbg != nullptr && blockIdx.x == 0;
       for (int it = 0; it < n_my + SKEW; ++it) {
@@ -286,23 +328,23 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
                 const uint64_t a_hi = make_smem_desc<32>(sa + (uint32_t)(g * Cfg::kPlanes) * kRuAChunkBytes + a_off);
                 const uint64_t w_hi = make_smem_desc<32>(sw + (uint32_t)(g * Cfg::kPlanes) * Cfg::kWChunk);
 #pragma unroll
-                for (int k = 0; k < 2; ++k) umma_bf16(d1, a_hi + 2 * k, w_hi + 2 * k, idesc, (kg | j | g | k) != 0);
+                for (int k = 0; k < 2; ++k) mma(d1, a_hi + 2 * k, w_hi + 2 * k, (kg | j | g | k) != 0);
                 if (NTERMS == 3) {
                   const uint64_t a_lo = make_smem_desc<32>(sa + (uint32_t)(g * Cfg::kPlanes + 1) * kRuAChunkBytes + a_off);
                   const uint64_t w_lo = make_smem_desc<32>(sw + (uint32_t)(g * Cfg::kPlanes + 1) * Cfg::kWChunk);
 #pragma unroll
-                  for (int k = 0; k < 2; ++k) umma_bf16(d1, a_lo + 2 * k, w_hi + 2 * k, idesc, 1u);
+                  for (int k = 0; k < 2; ++k) mma(d1, a_lo + 2 * k, w_hi + 2 * k, 1u);
 #pragma unroll
-                  for (int k = 0; k < 2; ++k) umma_bf16(d1, a_hi + 2 * k, w_lo + 2 * k, idesc, 1u);
+                  for (int k = 0; k < 2; ++k) mma(d1, a_hi + 2 * k, w_lo + 2 * k, 1u);
                 }
               }
-              umma_commit_cl<CL>(w_empty(ws));
+              commit_w(w_empty(ws));
               if (++ws == SW) { ws = 0; wph ^= 1u; }
             }
-            umma_commit(a_empty(as));
+            commit(a_empty(as));
             if (++as == SA) { as = 0; aph ^= 1u; }
           }
-          umma_commit(acc1_full(it % NB1));
+          commit(acc1_full(it % NB1));
           ru_trace(p, it, 1);
           if (timed && it < kRuTraceTiles) { p.dbg[it * kRuTraceEvents + 27] = wa; p.dbg[it * kRuTraceEvents + 28] = ww; }
         }
@@ -328,20 +370,20 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
               const uint32_t a_hi = mid_tmem + (uint32_t)kc * 32u;
               const uint64_t w_hi = make_smem_desc<32>(sw + (uint32_t)(g * Cfg::kPlanes) * Cfg::kWChunk);
 #pragma unroll
-              for (int k = 0; k < 2; ++k) umma_bf16_ts(d2, a_hi + 8 * k, w_hi + 2 * k, idesc, (kg | g | k) != 0);
+              for (int k = 0; k < 2; ++k) mma_ts(d2, a_hi + 8 * k, w_hi + 2 * k, (kg | g | k) != 0);
               if (NTERMS == 3) {
                 const uint32_t a_lo = a_hi + 16u;
                 const uint64_t w_lo = make_smem_desc<32>(sw + (uint32_t)(g * Cfg::kPlanes + 1) * Cfg::kWChunk);
 #pragma unroll
-                for (int k = 0; k < 2; ++k) umma_bf16_ts(d2, a_lo + 8 * k, w_hi + 2 * k, idesc, 1u);
+                for (int k = 0; k < 2; ++k) mma_ts(d2, a_lo + 8 * k, w_hi + 2 * k, 1u);
 #pragma unroll
-                for (int k = 0; k < 2; ++k) umma_bf16_ts(d2, a_hi + 8 * k, w_lo + 2 * k, idesc, 1u);
+                for (int k = 0; k < 2; ++k) mma_ts(d2, a_hi + 8 * k, w_lo + 2 * k, 1u);
               }
             }
-            umma_commit_cl<CL>(w_empty(ws));
+            commit_w(w_empty(ws));
             if (++ws == SW) { ws = 0; wph ^= 1u; }
           }
-          umma_commit(acc2_full(jt % NB2));
+          commit(acc2_full(jt % NB2));
           ru_trace(p, jt, 9);
           if (timed && jt < kRuTraceTiles) {
             p.dbg[jt * kRuTraceEvents + 29] = ww1; p.dbg[jt * kRuTraceEvents + 30] = wm; p.dbg[jt * kRuTraceEvents + 31] = w2;
@@ -423,7 +465,7 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
         }
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(mid_full(buf, ci));
+        arrive_lead(mid_full(buf, ci));
         if (group == 0 && lane == 0) ru_trace(p, it, 11 + ci);
       }
     };
@@ -464,7 +506,7 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
         tmem_ld_wait();
         if (c + 32 >= C) {   // accumulator fully drained: hand the TMEM buffer back to the MMA warp
           tc_fence_before();
-          mbar_arrive(acc2_empty(jt % NB2));
+          arrive_lead(acc2_empty(jt % NB2));
         }
         const uint32_t slab = res_base + rs * kRuSlabBytes;
         mbar_wait(res_full(rs), rph);
@@ -544,14 +586,15 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
   else __syncthreads();
   if (warp == kRuMmaWarp) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    if (PAIR) tmem_dealloc_cg2<512>(tmem_base);
+    else tmem_dealloc<512>(tmem_base);
   }
 }
 
-template <int C, int NTERMS, int CL>
+template <int C, int NTERMS, int CL, bool PAIR>
 int launch_ru(const GemmWeights& c7, const GemmWeights& c1, const OpBuf& a, int batch, int L, const RuParams& p,
               int num_sms, cudaStream_t stream) {
-  using Cfg = RuCfg<C, NTERMS>;
+  using Cfg = RuCfg<C, NTERMS, PAIR ? 2 : 1>;
   CUtensorMap ta_hi, ta_lo, t_res;
   const uint64_t dims[3] = {(uint64_t)C, (uint64_t)L, (uint64_t)batch};
   const uint64_t strides[2] = {(uint64_t)C * 2, (uint64_t)L * C * 2};
@@ -572,7 +615,7 @@ int launch_ru(const GemmWeights& c7, const GemmWeights& c1, const OpBuf& a, int 
     SC_TRY(encode_tmap(&tw[2 * i], gw[i]->w_hi, 2, wd, ws, wb, 64, true, false));
     SC_TRY(encode_tmap(&tw[2 * i + 1], NTERMS == 3 ? gw[i]->w_lo : gw[i]->w_hi, 2, wd, ws, wb, 64, true, false));
   }
-  auto kern = resunit_fused_kernel<C, NTERMS, CL>;
+  auto kern = resunit_fused_kernel<C, NTERMS, CL, PAIR>;
   static int max_clusters = 0;   // per instantiation
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
@@ -666,13 +709,17 @@ int launch_resunit_fused(const GemmWeights& c7, const GemmWeights& c1, const OpB
   p.dbg = nullptr;
   p.out_hi = out.hi;
   p.out_lo = f32 ? out.lo : nullptr;
-  static const int cl = [] {
-    const char* e = getenv("SPARKCODEC_CLUSTER");   // 1: no weight multicast (A/B timing)
-    return e ? atoi(e) : 2;
+  // SPARKCODEC_CLUSTER: 1 = single CTAs, 2 = multicast clusters, 3 = CTA pairs; default: pairs in fp32 mode (tensor
+  // pipe bound: 3 MMAs per MAC), multicast in bf16 mode (epilogue bound) -- profiles/r1_pair_mode_ab.txt
+  static const int forced = [] {
+    const char* e = getenv("SPARKCODEC_CLUSTER");
+    return e ? atoi(e) : 0;
   }();
-#define RU_DISPATCH(CC, NT)                                                                   \
-  return cl > 1 ? launch_ru<CC, NT, 2>(c7, c1, a, batch, L, p, num_sms, stream)               \
-                : launch_ru<CC, NT, 1>(c7, c1, a, batch, L, p, num_sms, stream)
+  const int mode = forced ? forced : (f32 ? 3 : 2);
+#define RU_DISPATCH(CC, NT)                                                                              \
+  return mode >= 3 ? launch_ru<CC, NT, 2, true>(c7, c1, a, batch, L, p, num_sms, stream)                 \
+         : mode == 2 ? launch_ru<CC, NT, 2, false>(c7, c1, a, batch, L, p, num_sms, stream)              \
+                     : launch_ru<CC, NT, 1, false>(c7, c1, a, batch, L, p, num_sms, stream)
   if (c7.c_in == 96) {
     if (f32) { RU_DISPATCH(96, 3); } else { RU_DISPATCH(96, 1); }
   }
