@@ -14,6 +14,7 @@ struct ConvGemmParams {
   int halo_rows;         // halo mainloop: rows of the A box (128 + tap span, multiple of 8)
   int halo_bo_mode;      // halo mainloop: descriptor base-offset convention (see tc_gemm.cu)
   int halo_stages;       // halo mainloop: halo tiles in flight (2 or 3); the weight ring gets the rest of smem
+  int dbg_skip_store;    // timing experiments only (SPARKCODEC_DEBUG_SKIP_STORE): skip the epilogue maths + stores
   // epilogue
   const float* bias;
   const float* rowbias;
@@ -47,8 +48,24 @@ __device__ __forceinline__ float snake_f(float x, float a, float inv) {
   return fmaf(inv * s, s, x);
 }
 
-__device__ __forceinline__ float gelu_erf(float v) {   // nn.GELU() default (vocos.py:57)
+// nn.GELU() default = 0.5 v (1 + erf(v / sqrt 2)) (vocos.py:57).  erf by Abramowitz-Stegun 7.1.26 (|err| <= 6e-7 in
+// fp32 arithmetic, two SFU ops + 7 FMAs, no branches) instead of erff(): the pw1 epilogue applies this to 2048
+// hidden channels per frame and was issue bound on it; the result is then split into bf16 hi/lo (2^-17), so the
+// approximation error is far below what the next layer sees.
+__device__ __forceinline__ float gelu_erf(float v) {
+#ifdef SPARKCODEC_EXACT_ERF
   return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+#else
+  const float ax = fabsf(v) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = __expf(-ax * ax);
+  const float erf_abs = fmaf(-poly * t, e, 1.0f);
+  return 0.5f * v * (1.0f + copysignf(erf_abs, v));
+#endif
 }
 
 // Finishes 4 consecutive output columns [n, n+4) of one output row: bias (+rowbias)(+residual),

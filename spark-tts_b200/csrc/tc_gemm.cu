@@ -76,12 +76,17 @@ struct TileCfg {
   static_assert(kABytes % 1024 == 0 && kWBytes % 1024 == 0, "swizzled tiles must stay 1024 B aligned");
 };
 
-// warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue (two warps per TMEM lane quarter, each
-// draining half of a 32-column chunk), warp 10 residual TMA producer
-constexpr int kEpiWarps = 8;
-constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kResWarp = 2 + kEpiWarps;
-constexpr int kNumThreads = (3 + kEpiWarps) * 32;
+// warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 / 10..17 two epilogue teams (two warps per TMEM lane quarter
+// and team, each draining half of a 32-column chunk), warp 18 residual TMA producer.
+// The teams take alternate 32-column chunks of an accumulator, each with its own transpose slab, so two
+// chunks are in flight: a chunk is a chain of long-latency steps (tcgen05.ld -> slab -> barrier -> slab ->
+// SFU maths -> global stores) and ONE team left the short-reduction layers (pw1, the 1x1 convs, the narrow
+// up-samplers) epilogue bound at ~1 element per cycle per SM.
+constexpr int kEpiTeams = 2;
+constexpr int kEpiWarps = 8;                    // per team
+constexpr int kEpiThreads = kEpiWarps * 32;     // per team
+constexpr int kResWarp = 2 + kEpiTeams * kEpiWarps;
+constexpr int kNumThreads = (kResWarp + 1) * 32;
 
 template <int BLOCK_N, int BK, int NTERMS, bool RES, bool HALO, int CG>
 __global__ void __launch_bounds__(kNumThreads, 1)
@@ -150,7 +155,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), CG * kEpiThreads);   // pair mode: both CTAs' epilogues release the leader's MMA warp
+      mbar_init(tempty_bar(a), CG * kEpiTeams * kEpiThreads);   // pair mode: both CTAs' epilogues release the leader's MMA warp
     }
     for (int r = 0; r < kResSlots; ++r) {
       mbar_init(rfull_bar(r), 1);
@@ -330,32 +335,39 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     //      alpha) are fixed per lane and loaded once per chunk.
     const int group = warp & 3;                 // TMEM lane quarter this warp may read
     const int row_in_tile = group * 32 + lane;
-    const int ew = warp - 2;                    // 0..7
+    const int team = (warp - 2) / kEpiWarps;    // 0 / 1: even / odd chunks of every accumulator
+    const int ew = (warp - 2) % kEpiWarps;      // 0..7 within the team
     const int half = ew >> 2;                   // which 16 of a chunk's 32 columns this warp drains from TMEM
     const int q4 = lane & 7, rsub = lane >> 3;  // phase-2 mapping: column quad, row within a 4-row group
-    uint32_t iter = 0, chunk_ctr = 0;
-    // The residual (fp32, may alias out_f32: every element is read by TMA before the thread that
-    // owns it stores the sum) arrives through the slab ring filled by warp 6.
-    uint32_t rs = 0, rphase = 0;
+    constexpr int kChunks = BLOCK_N / 32;
+    const uint32_t slab = slab_base + (uint32_t)team * Cfg::kSlabBytes;
+    const int bar_a = 1 + 2 * team, bar_b = 2 + 2 * team;   // named barriers of this team
+    uint32_t iter = 0;
+    // The residual (fp32, may alias out_f32: every element is read by TMA before the thread that owns it
+    // stores the sum) arrives through the slab ring filled by the residual producer warp, one slot per chunk.
     for (int st = cid; st < num_super; st += ncl, ++iter) {
       const Tile t = tile_of(st);
       const int b = t.b, l0 = t.l0, n0 = t.n0;
+      const size_t tile_off = ((size_t)b * p.L + l0) * (size_t)p.n_total;
       const uint32_t acc = iter & 1u, acc_phase = (iter >> 1) & 1u;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(group * 32) << 16) + acc * BLOCK_N;
+      const int my_last = ((kChunks - 1 - team) & ~1) + team;   // last chunk of this team (may be < 0: no chunk)
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32, ++chunk_ctr) {
-        const uint32_t slab = slab_base + (chunk_ctr & 1u) * Cfg::kSlabBytes;
+      for (int ci = team; ci < kChunks; ci += kEpiTeams) {
+        const int c = ci * 32;
         // per-column parameters of this lane's 4 columns: issued first so their latency hides behind the
         // TMEM load, the slab write and the barrier
         const int n = n0 + c + q4 * 4;
         float4 bias4, alpha4, inv4;
         load_col_params4(p, n, bias4, alpha4, inv4);
+        uint32_t r[16];
+        tmem_ld_x16(t_row + c + 16 * half, r);
+        // the previous chunk of this team has been read back out of the slab by every warp of the team
+        asm volatile("bar.sync %0, %1;" ::"r"(bar_a), "n"(kEpiThreads) : "memory");
+        tmem_ld_wait();
         {
-          uint32_t r[16];
-          tmem_ld_x16(t_row + c + 16 * half, r);
-          tmem_ld_wait();
           const uint32_t row_addr = slab + row_in_tile * 128;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -363,22 +375,23 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
                          "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
                          : "memory");
         }
-        if (c + 32 >= BLOCK_N) {   // accumulator fully drained: hand the TMEM stage back to the MMA warp
+        if (ci == my_last) {   // this thread's share of the accumulator is drained: hand the TMEM stage back
           tc_fence_before();
           if (CG > 1) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));   // the leader's MMA warp waits for both CTAs
           else mbar_arrive(tempty_bar(acc));
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-        uint32_t rslab = 0;
+        asm volatile("bar.sync %0, %1;" ::"r"(bar_b), "n"(kEpiThreads) : "memory");
+        uint32_t rslab = 0, rs = 0;
         if (RES) {
+          const uint32_t cg = iter * kChunks + (uint32_t)ci;     // running chunk number -> ring slot / phase
+          rs = cg % kResSlots;
           rslab = res_base + rs * Cfg::kSlabBytes;
-          mbar_wait(rfull_bar(rs), rphase);
+          mbar_wait(rfull_bar(rs), (cg / kResSlots) & 1u);
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int r = ew * 16 + i * 4 + rsub;
-          const int l = l0 + r;
-          const uint32_t off = r * 128 + ((q4 ^ (r & 7)) << 4);
+          const int r_ = ew * 16 + i * 4 + rsub;
+          const uint32_t off = r_ * 128 + ((q4 ^ (r_ & 7)) << 4);
           float4 v;
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                        : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
@@ -390,13 +403,16 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
                          : "r"(rslab + off));
             v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
           }
-          if (l < p.L) epilogue_store4(p, v, b, ((size_t)b * p.L + l) * (size_t)p.n_total, n, bias4, alpha4, inv4,
-                                          /*add_residual=*/false);
+          if (l0 + r_ < p.L && p.dbg_skip_store == 0)
+            epilogue_store4(p, v, b, tile_off + (size_t)((uint32_t)r_ * (uint32_t)p.n_total), n, bias4, alpha4, inv4,
+                            /*add_residual=*/false);
         }
-        if (RES) {
-          mbar_arrive(rempty_bar(rs));
-          if (++rs == kResSlots) { rs = 0; rphase ^= 1u; }
-        }
+        if (RES) mbar_arrive(rempty_bar(rs));
+      }
+      if (my_last < 0) {   // (BLOCK_N == 32 only) a team without a chunk still releases the accumulator
+        tc_fence_before();
+        if (CG > 1) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
+        else mbar_arrive(tempty_bar(acc));
       }
     }
   }
@@ -585,6 +601,8 @@ int fill_params(const GemmWeights& w, int batch, int L, const Epilogue& ep, int 
   p->num_m_tiles = batch * p->m_tiles_per_utt;
   p->num_n_tiles = w.n_total / w.block_n;
   p->halo_rows = 0; p->halo_bo_mode = 0; p->halo_stages = 3;
+  static const int skip = [] { const char* e = getenv("SPARKCODEC_DEBUG_SKIP_STORE"); return e ? atoi(e) : 0; }();
+  p->dbg_skip_store = skip;   // timing experiments only: drain the accumulators but do not finish / store them
   p->bias = w.bias; p->rowbias = ep.rowbias; p->residual = ep.residual;
   p->alpha = ep.alpha; p->inv_alpha = ep.inv_alpha; p->act = ep.act;
   p->out_f32 = ep.out_f32; p->out_hi = ep.out_op.hi;
