@@ -49,22 +49,35 @@ __device__ __forceinline__ float snake_f(float x, float a, float inv) {
 }
 
 // nn.GELU() default = 0.5 v (1 + erf(v / sqrt 2)) (vocos.py:57).  erf by Abramowitz-Stegun 7.1.26 (|err| <= 6e-7 in
-// fp32 arithmetic, two SFU ops + 7 FMAs, no branches) instead of erff(): the pw1 epilogue applies this to 2048
-// hidden channels per frame and was issue bound on it; the result is then split into bf16 hi/lo (2^-17), so the
+// fp32 arithmetic): two single-instruction SFU ops (rcp.approx / ex2.approx, flush-to-zero: no denormal fix-up
+// code) + 9 FMA-pipe ops, no branches, instead of erff().  The pw1 epilogue applies this to 2048 hidden
+// channels per frame and is issue bound on it; the result is then split into bf16 hi/lo (2^-17), so the
 // approximation error is far below what the next layer sees.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float gelu_erf(float v) {
 #ifdef SPARKCODEC_EXACT_ERF
   return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
 #else
-  const float ax = fabsf(v) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  const float av = fabsf(v);
+  const float t = rcp_approx(fmaf(av, 0.3275911f * 0.70710678118654752f, 1.0f));   // 1 / (1 + p |v| / sqrt 2)
+  const float s = av * 0.84932180028801904f;                                       // sqrt(log2(e) / 2) |v|
+  const float e = ex2_approx(-s * s);                                              // exp(-v^2 / 2)
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
-  const float e = __expf(-ax * ax);
   const float erf_abs = fmaf(-poly * t, e, 1.0f);
-  return 0.5f * v * (1.0f + copysignf(erf_abs, v));
+  const float h = 0.5f * v;
+  return fmaf(h, copysignf(erf_abs, v), h);
 #endif
 }
 
