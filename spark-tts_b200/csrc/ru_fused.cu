@@ -63,6 +63,7 @@ struct RuParams {
   float* x;                                   // (batch, L, C) fp32, read as residual and overwritten
   __nv_bfloat16 *out_hi, *out_lo;             // (batch, L, C) operand planes of the next layer (optional)
   long long* dbg;                             // SPARKCODEC_RU_TRACE: per-tile event clocks of CTA 0 (else null)
+  int l2_prefetch;                            // issue L2 prefetches of the next tile's operand / residual rows
 };
 constexpr int kRuTraceEvents = 32, kRuTraceTiles = 16;
 
@@ -212,7 +213,7 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
         const int tile = tile_of(it);
         const int b = tile_b(tile);
         const int row0 = tile_l0(tile) - 3 * p.dil;
-        if (it + 1 < n_my) {   // next tile's operand rows -> L2 (they come from HBM: written by the previous kernel)
+        if (p.l2_prefetch && it + 1 < n_my) {   // next tile's operand rows -> L2 (they come from HBM: written by the previous kernel)
           const int nt = tile_of(it + 1);
           const int nb = tile_b(nt), nrow0 = tile_l0(nt) - 3 * p.dil;
           for (int kc = 0; kc < Cfg::kChunks; ++kc) {
@@ -400,7 +401,7 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
         const int tile = tile_of(jt);
         const int b = tile_b(tile);
         const int l0 = tile_l0(tile);
-        if (jt + 1 < n_my) {   // pull the next tile's residual rows into L2 while this tile is processed
+        if (p.l2_prefetch && jt + 1 < n_my) {   // pull the next tile's residual rows into L2 while this tile is processed
           const int nt = tile_of(jt + 1);
           for (int c = 0; c < C; c += 32) tma_prefetch_3d(&tm_res, c, tile_l0(nt), tile_b(nt));
         }
@@ -707,6 +708,8 @@ int launch_resunit_fused(const GemmWeights& c7, const GemmWeights& c1, const OpB
   p.bias1 = c1.bias; p.alpha_out = alpha_out; p.inv_out = inv_out;
   p.x = x;
   p.dbg = nullptr;
+  static const int l2pf = [] { const char* e = getenv("SPARKCODEC_RU_L2_PREFETCH"); return e ? atoi(e) : 0; }();
+  p.l2_prefetch = l2pf;   // off: ncu showed 1.7x the algorithmic DRAM reads with it (evicted before use) and no speed-up
   p.out_hi = out.hi;
   p.out_lo = f32 ? out.lo : nullptr;
   // SPARKCODEC_CLUSTER: 1 = single CTAs, 2 = multicast clusters, 3 = CTA pairs; default: pairs in fp32 mode (tensor
