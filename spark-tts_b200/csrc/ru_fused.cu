@@ -38,6 +38,7 @@ namespace {
 constexpr int kRuHaloRowsMax = 184;                 // 128 + 6 * 9, multiple of 8
 constexpr int kRuAChunkBytes = 12 * 1024;           // 184 rows x 64 B, rounded up to 1024
 constexpr int kRuSlabBytes = kBlockM * 128;         // 128 rows x 32 fp32
+constexpr int kRuPlaneTile = kBlockM * 64;          // 128 rows x 32 bf16 (one operand plane of an output chunk)
 // warp roles: 0..7 mid team, 8..15 final team, 16 / 17 / 18 TMA producers (residual, activations, weights),
 // 19 MMA issuer.
 // The warp scheduler favours the highest warp id among eligible warps, so the single-thread roles that
@@ -83,13 +84,15 @@ struct RuCfg {
   static constexpr int SA = (NTERMS == 3) ? 2 : (C <= 96 ? 2 : 3);
   static constexpr int SR = 3;
   static constexpr int kParBytes = 3 * C * 4;
-  static constexpr int kFixed = SA * kAStage + SR * kRuSlabBytes + kParBytes + 1024 /* barriers */ + 1024 /* alignment */;
+  static constexpr int kStageOut = 2 * kPlanes * kRuPlaneTile;      // staging of the operand-plane TMA stores (2 slots)
+  static constexpr int kFixed = SA * kAStage + SR * kRuSlabBytes + kStageOut + kParBytes + 1024 /* barriers */ +
+                                1024 /* alignment */;
   static constexpr int SWRaw = (227 * 1024 - kFixed) / kWStage;
   static constexpr int SW = SWRaw > 12 ? 12 : SWRaw;
   static constexpr int kNumMid = NB1 * kChunks;                    // one "chunk converted" barrier per (acc1 buffer, chunk)
   static constexpr int kNumBars = 2 * SA + 2 * SW + kNumMid + NB1 + 2 * NB2 + 2 * SR;
-  static constexpr int kSmemBytes = SA * kAStage + SW * kWStage + SR * kRuSlabBytes + kParBytes + kNumBars * 8 + 16 +
-                                    1024 /* alignment */;
+  static constexpr int kSmemBytes = SA * kAStage + SW * kWStage + SR * kRuSlabBytes + kStageOut + kParBytes +
+                                    kNumBars * 8 + 16 + 1024 /* alignment */;
   static_assert(kNumBars * 8 + 16 <= 1024, "barrier block larger than budgeted");
   static_assert(SW >= 3, "weight ring too shallow");
   static_assert(kChunks % G == 0, "K groups must tile the channels");
@@ -119,7 +122,8 @@ __global__ void __launch_bounds__(kRuThreads, 1)
 resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                      const __grid_constant__ CUtensorMap tm_w7_hi, const __grid_constant__ CUtensorMap tm_w7_lo,
                      const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_constant__ CUtensorMap tm_w1_lo,
-                     const __grid_constant__ CUtensorMap tm_res, const RuParams p) {
+                     const __grid_constant__ CUtensorMap tm_res, const __grid_constant__ CUtensorMap tm_o_hi,
+                     const __grid_constant__ CUtensorMap tm_o_lo, const RuParams p) {
   static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of two");
   constexpr int PG = PAIR ? 2 : 1;
   using Cfg = RuCfg<C, NTERMS, PG>;
@@ -130,7 +134,8 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
   const uint32_t a_base = smem_base;
   const uint32_t w_base = a_base + SA * Cfg::kAStage;
   const uint32_t res_base = w_base + SW * Cfg::kWStage;
-  const uint32_t par_base = res_base + SR * kRuSlabBytes;
+  const uint32_t out_base = res_base + SR * kRuSlabBytes;          // operand-plane staging, 1024 B aligned
+  const uint32_t par_base = out_base + Cfg::kStageOut;
   const uint32_t bar_base = par_base + Cfg::kParBytes;
   auto a_full = [&](int s) { return bar_base + 8u * s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (SA + s); };
@@ -188,10 +193,10 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
     }
     for (int s = 0; s < SA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < SW; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), PAIR ? 1 : CL); }
-    for (int s = 0; s < NMID; ++s) mbar_init(mid_full(0, s), PG * kRuMidArrivals);   // pair: both CTAs' mid teams
+    for (int s = 0; s < NMID; ++s) mbar_init(mid_full(0, s), PG);   // one arrive per CTA (after a named barrier of the 4 warps that converted the chunk)
     for (int s = 0; s < NB1; ++s) mbar_init(acc1_full(s), 1);
-    for (int s = 0; s < NB2; ++s) { mbar_init(acc2_full(s), 1); mbar_init(acc2_empty(s), PG * kRuTeamThreads); }
-    for (int s = 0; s < SR; ++s) { mbar_init(res_full(s), 1); mbar_init(res_empty(s), kRuTeamThreads); }
+    for (int s = 0; s < NB2; ++s) { mbar_init(acc2_full(s), 1); mbar_init(acc2_empty(s), PG); }
+    for (int s = 0; s < SR; ++s) { mbar_init(res_full(s), 1); mbar_init(res_empty(s), 1); }
     fence_barrier_init();
   }
   if (warp == kRuMmaWarp) {
@@ -466,98 +471,113 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
         }
         tmem_st_wait();
         tc_fence_before();
-        arrive_lead(mid_full(buf, ci));
+        // the 4 warps (one per lane quarter) that share `sub` converted this chunk: sync them, then ONE thread
+        // arrives (a cluster-scope release arrive by every thread costs thousands of cycles in pair mode)
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + sub) : "memory");
+        if (group == 0 && lane == 0) arrive_lead(mid_full(buf, ci));
         if (group == 0 && lane == 0) ru_trace(p, it, 11 + ci);
       }
     };
 
-    // ---- final stage of tile `jt` (final team only): acc2 + residual slab (+ b1) -> x, Snake -> operand planes.
-    // Phase 1: each thread adds its 16 accumulator columns into ITS row of the residual slab (in place);
-    // phase 2: the slab is read back transposed (8 lanes = one 128 B row) so every global access is a
-    // full row segment.
+    // ---- final stage of tile `jt` (final team only): acc2 + residual slab + b1 -> x, Snake -> operand planes.
+    // A thread owns 16 columns of ITS row (TMEM lane): it adds them into its row of the residual slab IN PLACE
+    // (the slab then holds the new x tile in the TMA box layout), Snakes them straight from registers and
+    // parks the bf16 hi/lo pairs in a staging tile (SWIZZLE_64B box layout).  One elected thread then stores
+    // the x slab and the staging tiles with TMA: no transposed re-read, no per-thread global stores or
+    // address arithmetic, rows beyond the utterance (and dummy tiles) are clipped by the TMA unit.
     const int ew = (warp - kRuFinWarp0) & 7;    // 0..7 within the final team
     const int half = ew >> 2;                   // which 16 of a chunk's 32 columns this warp drains from TMEM
-    const int q4 = lane & 7, rsub = lane >> 3;  // phase 2: column quad, row within a 4-row group
-    uint32_t rs = 0, rph = 0;
+    const bool storer = warp == kRuFinWarp0 && lane == 0;
+    uint32_t rs = 0, rph = 0, out_ctr = 0;
+    int prev_rs = -1;                           // residual slot whose x store is still reading it
     auto final_stage = [&](int jt) {
       const int tile = tile_of(jt);
-      const bool real = tile < p.num_tiles;
-      const int b = real ? tile / p.m_tiles_per_utt : 0;
-      const int l0 = tile_l0(tile);
-      const int rows_left = real ? p.L - l0 : 0;   // rows of this tile inside the utterance (0: dummy tile)
-      const size_t tile_off = ((size_t)b * p.L + l0) * (size_t)C;
-      float* const x_tile = p.x + tile_off;
-      __nv_bfloat16* const hi_tile = p.out_hi ? p.out_hi + tile_off : nullptr;
-      __nv_bfloat16* const lo_tile = p.out_lo ? p.out_lo + tile_off : nullptr;
+      const int b = tile_b(tile), l0 = tile_l0(tile);
+      const bool has_out = p.out_hi != nullptr;
       mbar_wait(acc2_full(jt % NB2), (uint32_t)(jt / NB2) & 1u);
       tc_fence_after();
       if (warp == kRuFinWarp0 && lane == 0) ru_trace(p, jt, 20);
       const uint32_t t_row = tmem_base + ((uint32_t)(group * 32) << 16) + (uint32_t)(NB1 + jt % NB2) * C;
 #pragma unroll 1
-      for (int c = 0; c < C; c += 32) {
-        const int n = c + q4 * 4;
-        const float4 bias4 = __ldg(reinterpret_cast<const float4*>(p.bias1 + n));
-        float4 alpha4 = make_float4(0.f, 0.f, 0.f, 0.f), inv4 = alpha4;
-        if (hi_tile) {
-          alpha4 = __ldg(reinterpret_cast<const float4*>(p.alpha_out + n));
-          inv4 = __ldg(reinterpret_cast<const float4*>(p.inv_out + n));
-        }
+      for (int c = 0; c < C; c += 32, ++out_ctr) {
         uint32_t r[16];
         tmem_ld_x16(t_row + c + 16 * half, r);
-        tmem_ld_wait();
-        if (c + 32 >= C) {   // accumulator fully drained: hand the TMEM buffer back to the MMA warp
-          tc_fence_before();
-          arrive_lead(acc2_empty(jt % NB2));
+        // the stores issued two chunks ago have finished READING shared memory: their staging slot is ours
+        // again and the residual slot they read can be refilled
+        if (storer) {
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          if (prev_rs >= 0) mbar_arrive(res_empty(prev_rs));
         }
+        tmem_ld_wait();
+        tc_fence_before();
         const uint32_t slab = res_base + rs * kRuSlabBytes;
+        const uint32_t st_hi = out_base + (out_ctr & 1u) * (uint32_t)(Cfg::kPlanes * kRuPlaneTile);
+        const uint32_t st_lo = st_hi + kRuPlaneTile;
         mbar_wait(res_full(rs), rph);
-        {
-          const uint32_t row_addr = slab + (uint32_t)row_in_tile * 128u;
+        // the previous chunk's barrier ordered this thread after the storer's wait above (one chunk earlier)
+        const uint32_t row_addr = slab + (uint32_t)row_in_tile * 128u;
+        const uint32_t st_row = (uint32_t)row_in_tile * 64u;
+        const uint32_t swz64 = (uint32_t)(row_in_tile >> 1) & 3u;
+        const int n0 = c + 16 * half;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+        for (int jj = 0; jj < 2; ++jj) {          // 8 columns = one 16 B piece of each operand plane
+          uint32_t hp[4], lp[4];
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const int j = 2 * jj + h2;
             const uint32_t addr = row_addr + ((((uint32_t)(4 * half + j)) ^ ((uint32_t)row_in_tile & 7u)) << 4);
             float4 v;
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                          : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                          : "r"(addr));
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias1 + n0 + 4 * j));
             // same association as the stand-alone 1x1 kernel: (acc + residual) + bias
-            v.x = __uint_as_float(r[4 * j + 0]) + v.x;
-            v.y = __uint_as_float(r[4 * j + 1]) + v.y;
-            v.z = __uint_as_float(r[4 * j + 2]) + v.z;
-            v.w = __uint_as_float(r[4 * j + 3]) + v.w;
+            v.x = (__uint_as_float(r[4 * j + 0]) + v.x) + b4.x;
+            v.y = (__uint_as_float(r[4 * j + 1]) + v.y) + b4.y;
+            v.z = (__uint_as_float(r[4 * j + 2]) + v.z) + b4.z;
+            v.w = (__uint_as_float(r[4 * j + 3]) + v.w) + b4.w;
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                          : "memory");
-          }
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(kRuTeamThreads) : "memory");
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int rr = ew * 16 + i * 4 + rsub;
-          const uint32_t off = (uint32_t)rr * 128u + ((uint32_t)(q4 ^ (rr & 7)) << 4);
-          float4 v;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                       : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                       : "r"(slab + off));
-          if (rr < rows_left) {
-            v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
-            const uint32_t idx = (uint32_t)rr * C + n;
-            *reinterpret_cast<float4*>(x_tile + idx) = v;
-            if (hi_tile) {
-              v.x = snake_f(v.x, alpha4.x, inv4.x); v.y = snake_f(v.y, alpha4.y, inv4.y);
-              v.z = snake_f(v.z, alpha4.z, inv4.z); v.w = snake_f(v.w, alpha4.w, inv4.w);
+            if (has_out) {
+              const float4 a4 = __ldg(reinterpret_cast<const float4*>(p.alpha_out + n0 + 4 * j));
+              const float4 i4 = __ldg(reinterpret_cast<const float4*>(p.inv_out + n0 + 4 * j));
+              v.x = snake_f(v.x, a4.x, i4.x); v.y = snake_f(v.y, a4.y, i4.y);
+              v.z = snake_f(v.z, a4.z, i4.z); v.w = snake_f(v.w, a4.w, i4.w);
               const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
-              *reinterpret_cast<uint2*>(hi_tile + idx) = make_uint2(pack_bf16(h0), pack_bf16(h1));
-              if (lo_tile) {
+              hp[2 * h2] = pack_bf16(h0);
+              hp[2 * h2 + 1] = pack_bf16(h1);
+              if (NTERMS == 3) {
                 const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
-                *reinterpret_cast<uint2*>(lo_tile + idx) =
-                    make_uint2(pack_bf16(__floats2bfloat162_rn(v.x - f0.x, v.y - f0.y)),
-                               pack_bf16(__floats2bfloat162_rn(v.z - f1.x, v.w - f1.y)));
+                lp[2 * h2] = pack_bf16(__floats2bfloat162_rn(v.x - f0.x, v.y - f0.y));
+                lp[2 * h2 + 1] = pack_bf16(__floats2bfloat162_rn(v.z - f1.x, v.w - f1.y));
               }
             }
           }
+          if (has_out) {
+            const uint32_t off = st_row + ((((uint32_t)(2 * half + jj)) ^ swz64) << 4);   // SWIZZLE_64B box layout
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_hi + off), "r"(hp[0]), "r"(hp[1]), "r"(hp[2]),
+                         "r"(hp[3])
+                         : "memory");
+            if (NTERMS == 3)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_lo + off), "r"(lp[0]), "r"(lp[1]), "r"(lp[2]),
+                           "r"(lp[3])
+                           : "memory");
+          }
         }
-        fence_proxy_async();   // this slab was written through the generic proxy; the next TMA load overwrites it
-        mbar_arrive(res_empty(rs));
+        fence_proxy_async();   // generic-proxy writes -> visible to the TMA unit's async-proxy reads
+        asm volatile("bar.sync 1, %0;" ::"n"(kRuTeamThreads) : "memory");
+        if (storer) {
+          // every thread of the team has drained its share of the accumulator (tcgen05.wait::ld before the barrier):
+          // after the last chunk ONE thread hands the TMEM buffer back to the (leader's) MMA warp
+          if (c + 32 >= C) arrive_lead(acc2_empty(jt % NB2));
+          tma_store_3d(&tm_res, slab, c, l0, b);
+          if (has_out) {
+            tma_store_3d(&tm_o_hi, st_hi, c, l0, b);
+            if (NTERMS == 3) tma_store_3d(&tm_o_lo, st_lo, c, l0, b);
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          prev_rs = (int)rs;
+        }
         if (++rs == SR) { rs = 0; rph ^= 1u; }
         if (warp == kRuFinWarp0 && lane == 0) ru_trace(p, jt, 21 + c / 32);
       }
@@ -580,6 +600,7 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
         if (fin_team) final_stage(it);
       }
     }
+    if (storer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output stores have landed
   }
 
   tc_fence_before();
@@ -606,6 +627,14 @@ int launch_ru(const GemmWeights& c7, const GemmWeights& c1, const OpBuf& a, int 
   const uint64_t rstr[2] = {(uint64_t)C * 4, (uint64_t)L * C * 4};
   const uint32_t rbox[3] = {32u, (uint32_t)kBlockM, 1u};
   SC_TRY(encode_tmap(&t_res, p.x, 3, dims, rstr, rbox, 128, false, true));
+  // output operand planes (TMA stores): (C x L x batch) bf16, boxes of 32 columns x 128 rows, SWIZZLE_64B
+  CUtensorMap to_hi = ta_hi, to_lo = ta_hi;
+  if (p.out_hi) {
+    const uint32_t obox[3] = {32u, (uint32_t)kBlockM, 1u};
+    SC_TRY(encode_tmap(&to_hi, p.out_hi, 3, dims, strides, obox, 64, false, false));
+    if (p.out_lo) SC_TRY(encode_tmap(&to_lo, p.out_lo, 3, dims, strides, obox, 64, false, false));
+    else to_lo = to_hi;
+  }
   // weight maps: (K, N) boxes of 32 x C / CL rows (each CTA of a cluster fetches its share of a stage)
   CUtensorMap tw[4];
   const GemmWeights* gw[2] = {&c7, &c1};
@@ -649,7 +678,7 @@ int launch_ru(const GemmWeights& c7, const GemmWeights& c1, const OpBuf& a, int 
     SC_CUDA(cudaMemsetAsync(dbg, 0, dbg_n * sizeof(long long), stream));
     pp.dbg = dbg;
   }
-  SC_CUDA(cudaLaunchKernelEx(&cfg, kern, ta_hi, ta_lo, tw[0], tw[1], tw[2], tw[3], t_res, pp));
+  SC_CUDA(cudaLaunchKernelEx(&cfg, kern, ta_hi, ta_lo, tw[0], tw[1], tw[2], tw[3], t_res, to_hi, to_lo, pp));
   SC_LAUNCH_CHECK();
   if (trace) {
     std::vector<long long> hst(dbg_n);

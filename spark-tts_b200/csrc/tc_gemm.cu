@@ -155,7 +155,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), CG * kEpiTeams * kEpiThreads);   // pair mode: both CTAs' epilogues release the leader's MMA warp
+      mbar_init(tempty_bar(a), CG * kEpiTeams);   // one arrive per epilogue team (pair mode: of both CTAs)
     }
     for (int r = 0; r < kResSlots; ++r) {
       mbar_init(rfull_bar(r), 1);
@@ -375,12 +375,15 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
                          "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
                          : "memory");
         }
-        if (ci == my_last) {   // this thread's share of the accumulator is drained: hand the TMEM stage back
-          tc_fence_before();
-          if (CG > 1) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));   // the leader's MMA warp waits for both CTAs
+        tc_fence_before();
+        asm volatile("bar.sync %0, %1;" ::"r"(bar_b), "n"(kEpiThreads) : "memory");
+        // every thread of the team has drained its share of the accumulator (tcgen05.wait::ld precedes the barrier):
+        // after the team's last chunk ONE thread hands the TMEM stage back (a cluster-scope arrive by every thread
+        // costs thousands of cycles in pair mode; the leader's MMA warp waits for both teams of both CTAs)
+        if (ci == my_last && ew == 0 && lane == 0) {
+          if (CG > 1) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
           else mbar_arrive(tempty_bar(acc));
         }
-        asm volatile("bar.sync %0, %1;" ::"r"(bar_b), "n"(kEpiThreads) : "memory");
         uint32_t rslab = 0, rs = 0;
         if (RES) {
           const uint32_t cg = iter * kChunks + (uint32_t)ci;     // running chunk number -> ring slot / phase
@@ -409,8 +412,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
         }
         if (RES) mbar_arrive(rempty_bar(rs));
       }
-      if (my_last < 0) {   // (BLOCK_N == 32 only) a team without a chunk still releases the accumulator
-        tc_fence_before();
+      if (my_last < 0 && ew == 0 && lane == 0) {   // (BLOCK_N == 32 only) a team without a chunk still releases the accumulator
         if (CG > 1) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
         else mbar_arrive(tempty_bar(acc));
       }
