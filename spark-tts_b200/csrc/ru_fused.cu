@@ -515,53 +515,58 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
         const uint32_t st_lo = st_hi + kRuPlaneTile;
         mbar_wait(res_full(rs), rph);
         // the previous chunk's barrier ordered this thread after the storer's wait above (one chunk earlier)
-        const uint32_t row_addr = slab + (uint32_t)row_in_tile * 128u;
-        const uint32_t st_row = (uint32_t)row_in_tile * 64u;
+        // Plain C++ shared-memory accesses (no asm volatile): the compiler is free to issue all loads of the chunk
+        // first and to interleave the 16 Snake chains; the mbarrier waits / bar.sync around the chunk are the
+        // compiler barriers.
+        uint8_t* const slab_row = smem_raw + (slab - smem_u32(smem_raw)) + (size_t)row_in_tile * 128;
+        uint8_t* const hi_row = smem_raw + (st_hi - smem_u32(smem_raw)) + (size_t)row_in_tile * 64;
+        uint8_t* const lo_row = smem_raw + (st_lo - smem_u32(smem_raw)) + (size_t)row_in_tile * 64;
         const uint32_t swz64 = (uint32_t)(row_in_tile >> 1) & 3u;
         const int n0 = c + 16 * half;
+        float4 v[4], b4[4];
 #pragma unroll
-        for (int jj = 0; jj < 2; ++jj) {          // 8 columns = one 16 B piece of each operand plane
-          uint32_t hp[4], lp[4];
+        for (int j = 0; j < 4; ++j) {
+          v[j] = *reinterpret_cast<const float4*>(slab_row + ((((uint32_t)(4 * half + j)) ^ ((uint32_t)row_in_tile & 7u)) << 4));
+          b4[j] = __ldg(reinterpret_cast<const float4*>(p.bias1 + n0 + 4 * j));
+        }
 #pragma unroll
-          for (int h2 = 0; h2 < 2; ++h2) {
-            const int j = 2 * jj + h2;
-            const uint32_t addr = row_addr + ((((uint32_t)(4 * half + j)) ^ ((uint32_t)row_in_tile & 7u)) << 4);
-            float4 v;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                         : "r"(addr));
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias1 + n0 + 4 * j));
-            // same association as the stand-alone 1x1 kernel: (acc + residual) + bias
-            v.x = (__uint_as_float(r[4 * j + 0]) + v.x) + b4.x;
-            v.y = (__uint_as_float(r[4 * j + 1]) + v.y) + b4.y;
-            v.z = (__uint_as_float(r[4 * j + 2]) + v.z) + b4.z;
-            v.w = (__uint_as_float(r[4 * j + 3]) + v.w) + b4.w;
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-                         : "memory");
-            if (has_out) {
-              const float4 a4 = __ldg(reinterpret_cast<const float4*>(p.alpha_out + n0 + 4 * j));
-              const float4 i4 = __ldg(reinterpret_cast<const float4*>(p.inv_out + n0 + 4 * j));
-              v.x = snake_f(v.x, a4.x, i4.x); v.y = snake_f(v.y, a4.y, i4.y);
-              v.z = snake_f(v.z, a4.z, i4.z); v.w = snake_f(v.w, a4.w, i4.w);
-              const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
-              hp[2 * h2] = pack_bf16(h0);
-              hp[2 * h2 + 1] = pack_bf16(h1);
+        for (int j = 0; j < 4; ++j) {
+          // same association as the stand-alone 1x1 kernel: (acc + residual) + bias
+          v[j].x = (__uint_as_float(r[4 * j + 0]) + v[j].x) + b4[j].x;
+          v[j].y = (__uint_as_float(r[4 * j + 1]) + v[j].y) + b4[j].y;
+          v[j].z = (__uint_as_float(r[4 * j + 2]) + v[j].z) + b4[j].z;
+          v[j].w = (__uint_as_float(r[4 * j + 3]) + v[j].w) + b4[j].w;
+          *reinterpret_cast<float4*>(slab_row + ((((uint32_t)(4 * half + j)) ^ ((uint32_t)row_in_tile & 7u)) << 4)) = v[j];
+        }
+        if (has_out) {
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {          // 8 columns = one 16 B piece of each operand plane
+            uint4 hp, lp;
+            uint32_t* hpp = reinterpret_cast<uint32_t*>(&hp);
+            uint32_t* lpp = reinterpret_cast<uint32_t*>(&lp);
+            float4 a4[2], i4[2];
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+              a4[h2] = __ldg(reinterpret_cast<const float4*>(p.alpha_out + n0 + 4 * (2 * jj + h2)));
+              i4[h2] = __ldg(reinterpret_cast<const float4*>(p.inv_out + n0 + 4 * (2 * jj + h2)));
+            }
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+              const int j = 2 * jj + h2;
+              const float s0 = snake_f(v[j].x, a4[h2].x, i4[h2].x), s1 = snake_f(v[j].y, a4[h2].y, i4[h2].y);
+              const float s2 = snake_f(v[j].z, a4[h2].z, i4[h2].z), s3 = snake_f(v[j].w, a4[h2].w, i4[h2].w);
+              const __nv_bfloat162 h0 = __floats2bfloat162_rn(s0, s1), h1 = __floats2bfloat162_rn(s2, s3);
+              hpp[2 * h2] = pack_bf16(h0);
+              hpp[2 * h2 + 1] = pack_bf16(h1);
               if (NTERMS == 3) {
                 const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
-                lp[2 * h2] = pack_bf16(__floats2bfloat162_rn(v.x - f0.x, v.y - f0.y));
-                lp[2 * h2 + 1] = pack_bf16(__floats2bfloat162_rn(v.z - f1.x, v.w - f1.y));
+                lpp[2 * h2] = pack_bf16(__floats2bfloat162_rn(s0 - f0.x, s1 - f0.y));
+                lpp[2 * h2 + 1] = pack_bf16(__floats2bfloat162_rn(s2 - f1.x, s3 - f1.y));
               }
             }
-          }
-          if (has_out) {
-            const uint32_t off = st_row + ((((uint32_t)(2 * half + jj)) ^ swz64) << 4);   // SWIZZLE_64B box layout
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_hi + off), "r"(hp[0]), "r"(hp[1]), "r"(hp[2]),
-                         "r"(hp[3])
-                         : "memory");
-            if (NTERMS == 3)
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_lo + off), "r"(lp[0]), "r"(lp[1]), "r"(lp[2]),
-                           "r"(lp[3])
-                           : "memory");
+            const uint32_t off = (((uint32_t)(2 * half + jj)) ^ swz64) << 4;   // SWIZZLE_64B box layout
+            *reinterpret_cast<uint4*>(hi_row + off) = hp;
+            if (NTERMS == 3) *reinterpret_cast<uint4*>(lo_row + off) = lp;
           }
         }
         fence_proxy_async();   // generic-proxy writes -> visible to the TMA unit's async-proxy reads
