@@ -367,13 +367,12 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
         // the previous chunk of this team has been read back out of the slab by every warp of the team
         asm volatile("bar.sync %0, %1;" ::"r"(bar_a), "n"(kEpiThreads) : "memory");
         tmem_ld_wait();
-        {
-          const uint32_t row_addr = slab + row_in_tile * 128;
+        {   // plain C++ shared-memory accesses: the named barriers / mbarrier waits are the compiler barriers
+          uint8_t* const row_ptr = smem_raw + (slab - smem_u32(smem_raw)) + (size_t)row_in_tile * 128;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + (((4 * half + j) ^ (row_in_tile & 7)) << 4)),
-                         "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
-                         : "memory");
+            *reinterpret_cast<uint4*>(row_ptr + (((4 * half + j) ^ (row_in_tile & 7)) << 4)) =
+                make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
         }
         tc_fence_before();
         asm volatile("bar.sync %0, %1;" ::"r"(bar_b), "n"(kEpiThreads) : "memory");
@@ -395,15 +394,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
         for (int i = 0; i < 4; ++i) {
           const int r_ = ew * 16 + i * 4 + rsub;
           const uint32_t off = r_ * 128 + ((q4 ^ (r_ & 7)) << 4);
-          float4 v;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                       : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                       : "r"(slab + off));
+          float4 v = *reinterpret_cast<const float4*>(smem_raw + (slab - smem_u32(smem_raw)) + off);
           if (RES) {
-            float4 rr;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(rr.x), "=f"(rr.y), "=f"(rr.z), "=f"(rr.w)
-                         : "r"(rslab + off));
+            const float4 rr = *reinterpret_cast<const float4*>(smem_raw + (rslab - smem_u32(smem_raw)) + off);
             v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
           }
           if (l0 + r_ < p.L && p.dbg_skip_store == 0)
