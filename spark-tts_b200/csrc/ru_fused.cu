@@ -54,7 +54,6 @@ constexpr int kRuTmaAWarp = kRuResWarp + 1;              // activation halo tile
 constexpr int kRuTmaWWarp = kRuTmaAWarp + 1;             // W7 / W1 tiles
 constexpr int kRuMmaWarp = kRuTmaWWarp + 1;
 constexpr int kRuThreads = (kRuMmaWarp + 1) * 32;
-constexpr int kRuMidArrivals = kRuTeamThreads / 2;   // a mid chunk is written by one warp per lane quarter
 
 struct RuParams {
   int batch, L, dil, halo_rows;
@@ -77,9 +76,18 @@ struct RuCfg {
   static constexpr int kAStage = G * kPlanes * kRuAChunkBytes;
   static constexpr int kWChunk = (C / PG) * 64;                    // C / PG rows x 64 B (one plane): a CTA pair splits the N rows
   static constexpr int kWStage = G * kPlanes * kWChunk;
-  static constexpr int NB1 = C <= 96 ? 2 : 1;                      // acc1 / acc2 buffers in TMEM
-  static constexpr int NB2 = NB1;
-  static constexpr int SKEW = NB1 - 1;
+  // TMEM plan.  acc1 (k7 result, then the converted mid operand) is double buffered at both widths, and the 1x1 conv
+  // of tile i - 1 is issued AFTER (part of) the k7 conv of tile i (SKEW = 1), so the tensor pipe never waits for the
+  // mid stage.  C = 96: two 96-column acc2 buffers (4 x 96 = 384 columns).  C = 192: 2 x 192 columns of acc1 leave
+  // 128, so the 1x1 conv runs as TWO N halves through ONE 96-column accumulator (SPLIT); the halves are issued
+  // between the two halves of the next tile's k7 conv, which gives the final team time to drain the first one.
+  static constexpr bool SPLIT = C > 96;
+  static constexpr int NB1 = 2;
+  static constexpr int NH = SPLIT ? 2 : 1;                         // N halves of the 1x1 conv
+  static constexpr int N2 = C / NH;                                // accumulator width of the 1x1 conv
+  static constexpr int NB2 = SPLIT ? 1 : 2;
+  static constexpr int SKEW = 1;
+  static constexpr int kW1Stage = G * kPlanes * (N2 / PG) * 64;    // bytes of a W1 stage in this CTA (chunk stride stays kWChunk)
   // ring depths (227 KB budget)
   static constexpr int SA = (NTERMS == 3) ? 2 : (C <= 96 ? 2 : 3);
   static constexpr int SR = 3;
@@ -96,7 +104,7 @@ struct RuCfg {
   static_assert(kNumBars * 8 + 16 <= 1024, "barrier block larger than budgeted");
   static_assert(SW >= 3, "weight ring too shallow");
   static_assert(kChunks % G == 0, "K groups must tile the channels");
-  static_assert((NB1 + NB2) * C <= 512, "accumulators must fit TMEM");
+  static_assert(NB1 * C + NB2 * N2 <= 512, "accumulators must fit TMEM");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
   static_assert(kWChunk % 1024 == 0, "weight chunks must stay 1024 B aligned");
 };
@@ -128,7 +136,8 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
   constexpr int PG = PAIR ? 2 : 1;
   using Cfg = RuCfg<C, NTERMS, PG>;
   constexpr int SA = Cfg::SA, SW = Cfg::SW, SR = Cfg::SR, NB1 = Cfg::NB1, NB2 = Cfg::NB2;
-  constexpr int G = Cfg::G, SKEW = Cfg::SKEW, NMID = Cfg::kNumMid;
+  constexpr int G = Cfg::G, SKEW = Cfg::SKEW, NMID = Cfg::kNumMid, NH = Cfg::NH, N2 = Cfg::N2;
+  constexpr int KG1 = Cfg::SPLIT ? (Cfg::kGroups + 1) / 2 : Cfg::kGroups;   // k7 K groups issued before the first 1x1 half
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;
@@ -259,35 +268,48 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
         else if (CL > 1) tma_load_2d_mc(dst + mc_off, map, bar, k0, cl_rank * (C / CL), mask);
         else tma_load_2d(dst, map, bar, k0, 0);
       };
-      for (int it = 0; it < n_my + SKEW; ++it) {
-        if (it < n_my) {
-          for (int kg = 0; kg < Cfg::kGroups; ++kg) {
-            for (int j = 0; j < 7; ++j) {
-              mbar_wait(w_empty(ws), wph ^ 1u);
-              if (leader) mbar_expect_tx(w_full(ws), PG * Cfg::kWStage);
-#pragma unroll
-              for (int g = 0; g < G; ++g) {
-                const uint32_t sw = w_base + ws * Cfg::kWStage + (uint32_t)(g * Cfg::kPlanes) * Cfg::kWChunk;
-                load_w(sw, &tm_w7_hi, w_full(ws), j * C + (kg * G + g) * 32);
-                if (NTERMS == 3) load_w(sw + Cfg::kWChunk, &tm_w7_lo, w_full(ws), j * C + (kg * G + g) * 32);
-              }
-              if (++ws == SW) { ws = 0; wph ^= 1u; }
-            }
-          }
-        }
-        if (it >= SKEW) {
-          for (int kg = 0; kg < Cfg::kGroups; ++kg) {
+      const uint32_t mc1_off = (uint32_t)(cl_rank * (N2 / CL)) * 64u;
+      auto load_w1 = [&](uint32_t dst, const CUtensorMap* map, uint32_t bar, int k0, int half) {
+        const int row = half * N2 + cl_rank * (N2 / CL);
+        if (PAIR) tma_load_2d_cg2(dst, map, lead(bar), k0, row);
+        else if (CL > 1) tma_load_2d_mc(dst + mc1_off, map, bar, k0, row, mask);
+        else tma_load_2d(dst, map, bar, k0, half * N2);
+      };
+      auto w7_groups = [&](int g0, int g1) {
+        for (int kg = g0; kg < g1; ++kg) {
+          for (int j = 0; j < 7; ++j) {
             mbar_wait(w_empty(ws), wph ^ 1u);
             if (leader) mbar_expect_tx(w_full(ws), PG * Cfg::kWStage);
 #pragma unroll
             for (int g = 0; g < G; ++g) {
               const uint32_t sw = w_base + ws * Cfg::kWStage + (uint32_t)(g * Cfg::kPlanes) * Cfg::kWChunk;
-              load_w(sw, &tm_w1_hi, w_full(ws), (kg * G + g) * 32);
-              if (NTERMS == 3) load_w(sw + Cfg::kWChunk, &tm_w1_lo, w_full(ws), (kg * G + g) * 32);
+              load_w(sw, &tm_w7_hi, w_full(ws), j * C + (kg * G + g) * 32);
+              if (NTERMS == 3) load_w(sw + Cfg::kWChunk, &tm_w7_lo, w_full(ws), j * C + (kg * G + g) * 32);
             }
             if (++ws == SW) { ws = 0; wph ^= 1u; }
           }
         }
+      };
+      auto w1_half = [&](int half) {
+        for (int kg = 0; kg < Cfg::kGroups; ++kg) {
+          mbar_wait(w_empty(ws), wph ^ 1u);
+          if (leader) mbar_expect_tx(w_full(ws), PG * Cfg::kW1Stage);
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            const uint32_t sw = w_base + ws * Cfg::kWStage + (uint32_t)(g * Cfg::kPlanes) * Cfg::kWChunk;
+            load_w1(sw, &tm_w1_hi, w_full(ws), (kg * G + g) * 32, half);
+            if (NTERMS == 3) load_w1(sw + Cfg::kWChunk, &tm_w1_lo, w_full(ws), (kg * G + g) * 32, half);
+          }
+          if (++ws == SW) { ws = 0; wph ^= 1u; }
+        }
+      };
+      // same order as the MMA issuer: k7 groups [0, KG1) of tile it, 1x1 half 0 of tile it - 1, the remaining k7
+      // groups, 1x1 half 1 (SPLIT only)
+      for (int it = 0; it < n_my + SKEW; ++it) {
+        if (it < n_my) w7_groups(0, KG1);
+        if (it >= SKEW) w1_half(0);
+        if (it < n_my) w7_groups(KG1, Cfg::kGroups);
+        if (NH > 1 && it >= SKEW) w1_half(1);
       }
     }
   } else if (warp == kRuMmaWarp) {
@@ -299,10 +321,6 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
         if (PAIR) umma_bf16_cg2(d, a, b, idesc, accumulate);
         else umma_bf16(d, a, b, idesc, accumulate);
       };
-      auto mma_ts = [&](uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t accumulate) {
-        if (PAIR) umma_bf16_ts_cg2(d, a_tmem, b, idesc, accumulate);
-        else umma_bf16_ts(d, a_tmem, b, idesc, accumulate);
-      };
       auto commit = [&](uint32_t bar) {     // pair mode: arrives on the barrier at this offset in BOTH CTAs
         if (PAIR) umma_commit_cg2(bar);
         else umma_commit(bar);
@@ -311,90 +329,108 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
         if (PAIR) umma_commit_cg2(bar);
         else umma_commit_cl<CL>(bar);
       };
+      constexpr uint32_t idesc2 = PAIR ? make_idesc_cg2<N2>() : make_idesc<N2>();   // the 1x1 conv is N2 wide
+      auto mma_ts = [&](uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t accumulate) {
+        if (PAIR) umma_bf16_ts_cg2(d, a_tmem, b, idesc2, accumulate);
+        else umma_bf16_ts(d, a_tmem, b, idesc2, accumulate);
+      };
       uint32_t as = 0, aph = 0, ws = 0, wph = 0;
       const bool timed = p.dbg != nullptr && blockIdx.x == 0;
-      for (int it = 0; it < n_my + SKEW; ++it) {
-        long long wa = 0, ww = 0, ww1 = 0, wm = 0, w2 = 0;
-        if (it < n_my) {
-          // ---- k7 (dilated) conv of tile `it` -> acc1[it % NB1].  The buffer is free: the 1x1 conv of the
-          // tile that last used it was issued earlier in program order and waited for every mid chunk, i.e.
-          // for the epilogue warps to have drained it.
-          const uint32_t d1 = tmem_base + (uint32_t)(it % NB1) * C;
-          for (int kg = 0; kg < Cfg::kGroups; ++kg) {
-            mbar_wait_t(a_full(as), aph, timed, wa);
-            if (kg == 0) ru_trace(p, it, 0);
-            const uint32_t sa = a_base + as * Cfg::kAStage;
-            for (int j = 0; j < 7; ++j) {
-              mbar_wait_t(w_full(ws), wph, timed, ww);
-              tc_fence_after();
-              const uint32_t sw = w_base + ws * Cfg::kWStage;
-              const uint32_t a_off = (uint32_t)(j * p.dil) * 64u;   // tap j starts j*dil rows into the halo tile
-#pragma unroll
-              for (int g = 0; g < G; ++g) {
-                const uint64_t a_hi = make_smem_desc<32>(sa + (uint32_t)(g * Cfg::kPlanes) * kRuAChunkBytes + a_off);
-                const uint64_t w_hi = make_smem_desc<32>(sw + (uint32_t)(g * Cfg::kPlanes) * Cfg::kWChunk);
-#pragma unroll
-                for (int k = 0; k < 2; ++k) mma(d1, a_hi + 2 * k, w_hi + 2 * k, (kg | j | g | k) != 0);
-                if (NTERMS == 3) {
-                  const uint64_t a_lo = make_smem_desc<32>(sa + (uint32_t)(g * Cfg::kPlanes + 1) * kRuAChunkBytes + a_off);
-                  const uint64_t w_lo = make_smem_desc<32>(sw + (uint32_t)(g * Cfg::kPlanes + 1) * Cfg::kWChunk);
-#pragma unroll
-                  for (int k = 0; k < 2; ++k) mma(d1, a_lo + 2 * k, w_hi + 2 * k, 1u);
-#pragma unroll
-                  for (int k = 0; k < 2; ++k) mma(d1, a_hi + 2 * k, w_lo + 2 * k, 1u);
-                }
-              }
-              commit_w(w_empty(ws));
-              if (++ws == SW) { ws = 0; wph ^= 1u; }
-            }
-            commit(a_empty(as));
-            if (++as == SA) { as = 0; aph ^= 1u; }
-          }
-          commit(acc1_full(it % NB1));
-          ru_trace(p, it, 1);
-          if (timed && it < kRuTraceTiles) { p.dbg[it * kRuTraceEvents + 27] = wa; p.dbg[it * kRuTraceEvents + 28] = ww; }
-        }
-        if (it >= SKEW) {
-          // ---- 1x1 conv of tile jt: split-K over the mid chunks as the epilogue warps publish them
-          const int jt = it - SKEW;
-          const uint32_t d2 = tmem_base + (uint32_t)(NB1 + jt % NB2) * C;
-          mbar_wait_t(acc2_empty(jt % NB2), ((uint32_t)(jt / NB2) & 1u) ^ 1u, timed, w2);
-          tc_fence_after();
-          ru_trace(p, jt, 2);
-          const uint32_t mid_tmem = tmem_base + (uint32_t)(jt % NB1) * C;   // acc1 buffer of tile jt, converted in place
-          const uint32_t mid_par = (uint32_t)(jt / NB1) & 1u;
-          for (int kg = 0; kg < Cfg::kGroups; ++kg) {
-            mbar_wait_t(w_full(ws), wph, timed, ww1);
+      long long wa = 0, ww = 0, ww1 = 0, wm = 0, w2 = 0;
+      // ---- K groups [g0, g1) of the k7 (dilated) conv of tile `it` -> acc1[it % NB1].  The buffer is free: the 1x1
+      // conv of the tile that last used it was issued earlier in program order (the tensor pipe is in order) and
+      // had waited for every mid chunk, i.e. for the mid team to be done with it.
+      auto k7_groups = [&](int it, int g0, int g1) {
+        const uint32_t d1 = tmem_base + (uint32_t)(it % NB1) * C;
+        for (int kg = g0; kg < g1; ++kg) {
+          mbar_wait_t(a_full(as), aph, timed, wa);
+          if (kg == 0) ru_trace(p, it, 0);
+          const uint32_t sa = a_base + as * Cfg::kAStage;
+          for (int j = 0; j < 7; ++j) {
+            mbar_wait_t(w_full(ws), wph, timed, ww);
+            tc_fence_after();
             const uint32_t sw = w_base + ws * Cfg::kWStage;
+            const uint32_t a_off = (uint32_t)(j * p.dil) * 64u;   // tap j starts j*dil rows into the halo tile
 #pragma unroll
             for (int g = 0; g < G; ++g) {
-              const int kc = kg * G + g;
-              mbar_wait_t(mid_full(jt % NB1, kc), mid_par, timed, wm);
-              tc_fence_after();
-              ru_trace(p, jt, 3 + kc);
-              // A operand in tensor memory: lane = row, 16 K values = 8 columns of packed bf16 pairs
-              const uint32_t a_hi = mid_tmem + (uint32_t)kc * 32u;
+              const uint64_t a_hi = make_smem_desc<32>(sa + (uint32_t)(g * Cfg::kPlanes) * kRuAChunkBytes + a_off);
               const uint64_t w_hi = make_smem_desc<32>(sw + (uint32_t)(g * Cfg::kPlanes) * Cfg::kWChunk);
 #pragma unroll
-              for (int k = 0; k < 2; ++k) mma_ts(d2, a_hi + 8 * k, w_hi + 2 * k, (kg | g | k) != 0);
+              for (int k = 0; k < 2; ++k) mma(d1, a_hi + 2 * k, w_hi + 2 * k, (kg | j | g | k) != 0);
               if (NTERMS == 3) {
-                const uint32_t a_lo = a_hi + 16u;
+                const uint64_t a_lo = make_smem_desc<32>(sa + (uint32_t)(g * Cfg::kPlanes + 1) * kRuAChunkBytes + a_off);
                 const uint64_t w_lo = make_smem_desc<32>(sw + (uint32_t)(g * Cfg::kPlanes + 1) * Cfg::kWChunk);
 #pragma unroll
-                for (int k = 0; k < 2; ++k) mma_ts(d2, a_lo + 8 * k, w_hi + 2 * k, 1u);
+                for (int k = 0; k < 2; ++k) mma(d1, a_lo + 2 * k, w_hi + 2 * k, 1u);
 #pragma unroll
-                for (int k = 0; k < 2; ++k) mma_ts(d2, a_hi + 8 * k, w_lo + 2 * k, 1u);
+                for (int k = 0; k < 2; ++k) mma(d1, a_hi + 2 * k, w_lo + 2 * k, 1u);
               }
             }
             commit_w(w_empty(ws));
             if (++ws == SW) { ws = 0; wph ^= 1u; }
           }
-          commit(acc2_full(jt % NB2));
+          commit(a_empty(as));
+          if (++as == SA) { as = 0; aph ^= 1u; }
+        }
+        if (g1 == Cfg::kGroups) {
+          commit(acc1_full(it % NB1));
+          ru_trace(p, it, 1);
+          if (timed && it < kRuTraceTiles) { p.dbg[it * kRuTraceEvents + 27] = wa; p.dbg[it * kRuTraceEvents + 28] = ww; }
+          wa = ww = 0;
+        }
+      };
+      // ---- N half `half` of the 1x1 conv of tile jt: A = the mid chunks in tensor memory (split-K as the mid team
+      // publishes them), B = W1 rows [half * N2, +N2), D = acc2 buffer u % NB2 where u counts halves
+      auto one_by_one = [&](int jt, int half) {
+        const uint32_t u = (uint32_t)jt * NH + (uint32_t)half;
+        const uint32_t d2 = tmem_base + (uint32_t)(NB1 * C) + (u % NB2) * N2;
+        mbar_wait_t(acc2_empty(u % NB2), ((u / NB2) & 1u) ^ 1u, timed, w2);
+        tc_fence_after();
+        if (half == 0) ru_trace(p, jt, 2);
+        const uint32_t mid_tmem = tmem_base + (uint32_t)(jt % NB1) * C;   // acc1 buffer of tile jt, converted in place
+        const uint32_t mid_par = (uint32_t)(jt / NB1) & 1u;
+        for (int kg = 0; kg < Cfg::kGroups; ++kg) {
+          mbar_wait_t(w_full(ws), wph, timed, ww1);
+          const uint32_t sw = w_base + ws * Cfg::kWStage;
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            const int kc = kg * G + g;
+            if (half == 0) {
+              mbar_wait_t(mid_full(jt % NB1, kc), mid_par, timed, wm);
+              ru_trace(p, jt, 3 + kc);
+            }
+            tc_fence_after();
+            // A operand in tensor memory: lane = row, 16 K values = 8 columns of packed bf16 pairs
+            const uint32_t a_hi = mid_tmem + (uint32_t)kc * 32u;
+            const uint64_t w_hi = make_smem_desc<32>(sw + (uint32_t)(g * Cfg::kPlanes) * Cfg::kWChunk);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) mma_ts(d2, a_hi + 8 * k, w_hi + 2 * k, (kg | g | k) != 0);
+            if (NTERMS == 3) {
+              const uint32_t a_lo = a_hi + 16u;
+              const uint64_t w_lo = make_smem_desc<32>(sw + (uint32_t)(g * Cfg::kPlanes + 1) * Cfg::kWChunk);
+#pragma unroll
+              for (int k = 0; k < 2; ++k) mma_ts(d2, a_lo + 8 * k, w_hi + 2 * k, 1u);
+#pragma unroll
+              for (int k = 0; k < 2; ++k) mma_ts(d2, a_hi + 8 * k, w_lo + 2 * k, 1u);
+            }
+          }
+          commit_w(w_empty(ws));
+          if (++ws == SW) { ws = 0; wph ^= 1u; }
+        }
+        commit(acc2_full(u % NB2));
+        if (half == NH - 1) {
           ru_trace(p, jt, 9);
           if (timed && jt < kRuTraceTiles) {
             p.dbg[jt * kRuTraceEvents + 29] = ww1; p.dbg[jt * kRuTraceEvents + 30] = wm; p.dbg[jt * kRuTraceEvents + 31] = w2;
           }
+          ww1 = wm = w2 = 0;
         }
+      };
+      for (int it = 0; it < n_my + SKEW; ++it) {
+        if (it < n_my) k7_groups(it, 0, KG1);
+        if (it >= SKEW) one_by_one(it - SKEW, 0);
+        if (it < n_my && KG1 < Cfg::kGroups) k7_groups(it, KG1, Cfg::kGroups);
+        if (NH > 1 && it >= SKEW) one_by_one(it - SKEW, 1);
       }
     }
   } else if (warp == kRuResWarp) {
@@ -494,14 +530,18 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
       const int tile = tile_of(jt);
       const int b = tile_b(tile), l0 = tile_l0(tile);
       const bool has_out = p.out_hi != nullptr;
-      mbar_wait(acc2_full(jt % NB2), (uint32_t)(jt / NB2) & 1u);
-      tc_fence_after();
-      if (warp == kRuFinWarp0 && lane == 0) ru_trace(p, jt, 20);
-      const uint32_t t_row = tmem_base + ((uint32_t)(group * 32) << 16) + (uint32_t)(NB1 + jt % NB2) * C;
 #pragma unroll 1
-      for (int c = 0; c < C; c += 32, ++out_ctr) {
+      for (int nh = 0; nh < NH; ++nh) {            // N halves of the 1x1 conv (one accumulator each)
+      const uint32_t u = (uint32_t)jt * NH + (uint32_t)nh;
+      mbar_wait(acc2_full(u % NB2), (u / NB2) & 1u);
+      tc_fence_after();
+      if (warp == kRuFinWarp0 && lane == 0 && nh == 0) ru_trace(p, jt, 20);
+      const uint32_t t_row = tmem_base + ((uint32_t)(group * 32) << 16) + (uint32_t)(NB1 * C) + (u % NB2) * N2;
+#pragma unroll 1
+      for (int cc = 0; cc < N2; cc += 32, ++out_ctr) {
+        const int c = nh * N2 + cc;                // output column of the chunk
         uint32_t r[16];
-        tmem_ld_x16(t_row + c + 16 * half, r);
+        tmem_ld_x16(t_row + cc + 16 * half, r);
         // the stores issued two chunks ago have finished READING shared memory: their staging slot is ours
         // again and the residual slot they read can be refilled
         if (storer) {
@@ -574,7 +614,7 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
         if (storer) {
           // every thread of the team has drained its share of the accumulator (tcgen05.wait::ld before the barrier):
           // after the last chunk ONE thread hands the TMEM buffer back to the (leader's) MMA warp
-          if (c + 32 >= C) arrive_lead(acc2_empty(jt % NB2));
+          if (cc + 32 >= N2) arrive_lead(acc2_empty(u % NB2));
           tma_store_3d(&tm_res, slab, c, l0, b);
           if (has_out) {
             tma_store_3d(&tm_o_hi, st_hi, c, l0, b);
@@ -586,24 +626,16 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
         if (++rs == SR) { rs = 0; rph ^= 1u; }
         if (warp == kRuFinWarp0 && lane == 0) ru_trace(p, jt, 21 + c / 32);
       }
+      }
     };
 
     const int sub = (warp - kRuMidWarp0) >> 2;   // 0..1 mid team, 2..3 final team
-    if (SKEW) {
-      // the teams work on different tiles at the same time: mid of tile i, final of tile i - 1
-      if (!fin_team) {
-        for (int it = 0; it < n_my; ++it) mid_stage(it, sub, 2);
-      } else {
-        for (int jt = 0; jt < n_my; ++jt) final_stage(jt);
-      }
+    // the teams work on different tiles at the same time: mid of tile i, final of tile i - 1
+    static_assert(SKEW == 1, "the epilogue teams assume the skewed schedule");
+    if (!fin_team) {
+      for (int it = 0; it < n_my; ++it) mid_stage(it, sub, 2);
     } else {
-      // un-skewed: the tensor pipe waits for the mid stage and the final team has nothing to do before acc2
-      // completes, so BOTH teams convert mid chunks (4 in flight); the final team then finishes the tile
-      // while the next tile's k7 conv runs.
-      for (int it = 0; it < n_my; ++it) {
-        mid_stage(it, sub, 4);
-        if (fin_team) final_stage(it);
-      }
+      for (int jt = 0; jt < n_my; ++jt) final_stage(jt);
     }
     if (storer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output stores have landed
   }
@@ -640,13 +672,14 @@ int launch_ru(const GemmWeights& c7, const GemmWeights& c1, const OpBuf& a, int 
     if (p.out_lo) SC_TRY(encode_tmap(&to_lo, p.out_lo, 3, dims, strides, obox, 64, false, false));
     else to_lo = to_hi;
   }
-  // weight maps: (K, N) boxes of 32 x C / CL rows (each CTA of a cluster fetches its share of a stage)
+  // weight maps: (K, N) boxes of 32 columns x (N rows of one MMA) / CL rows: each CTA of a cluster fetches its share
+  // of a stage.  The 1x1 conv of the split schedule (C = 192) is N2 = 96 wide.
   CUtensorMap tw[4];
   const GemmWeights* gw[2] = {&c7, &c1};
   for (int i = 0; i < 2; ++i) {
     const uint64_t wd[2] = {(uint64_t)gw[i]->kt * C, (uint64_t)C};
     const uint64_t ws[1] = {(uint64_t)gw[i]->kt * C * 2};
-    const uint32_t wb[2] = {32u, (uint32_t)(C / CL)};
+    const uint32_t wb[2] = {32u, (uint32_t)((i == 0 ? C : Cfg::N2) / CL)};
     SC_TRY(encode_tmap(&tw[2 * i], gw[i]->w_hi, 2, wd, ws, wb, 64, true, false));
     SC_TRY(encode_tmap(&tw[2 * i + 1], NTERMS == 3 ? gw[i]->w_lo : gw[i]->w_hi, 2, wd, ws, wb, 64, true, false));
   }
