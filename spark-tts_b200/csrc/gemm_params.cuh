@@ -63,6 +63,17 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// bf16 mode: the operand is rounded to 8 mantissa bits right after, so the SFU sine's own range handling is enough
+// (its absolute error grows with |alpha x| but stays orders of magnitude below 2^-9 for any activation seen here).
+__device__ __forceinline__ float snake_fast(float x, float a, float inv) {
+  const float s = __sinf(a * x);
+  return fmaf(inv * s, s, x);
+}
+template <bool EXACT>
+__device__ __forceinline__ float snake_sel(float x, float a, float inv) {
+  return EXACT ? snake_f(x, a, inv) : snake_fast(x, a, inv);
+}
+
 __device__ __forceinline__ float gelu_erf(float v) {
 #ifdef SPARKCODEC_EXACT_ERF
   return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));

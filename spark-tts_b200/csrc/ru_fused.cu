@@ -488,10 +488,10 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
             const float4 b4 = *reinterpret_cast<const float4*>(s_par + c + 4 * q);
             const float4 a4 = *reinterpret_cast<const float4*>(s_par + C + c + 4 * q);
             const float4 i4 = *reinterpret_cast<const float4*>(s_par + 2 * C + c + 4 * q);
-            const float v0 = snake_f(__uint_as_float(r[4 * q + 0]) + b4.x, a4.x, i4.x);
-            const float v1 = snake_f(__uint_as_float(r[4 * q + 1]) + b4.y, a4.y, i4.y);
-            const float v2 = snake_f(__uint_as_float(r[4 * q + 2]) + b4.z, a4.z, i4.z);
-            const float v3 = snake_f(__uint_as_float(r[4 * q + 3]) + b4.w, a4.w, i4.w);
+            const float v0 = snake_sel<NTERMS == 3>(__uint_as_float(r[4 * q + 0]) + b4.x, a4.x, i4.x);
+            const float v1 = snake_sel<NTERMS == 3>(__uint_as_float(r[4 * q + 1]) + b4.y, a4.y, i4.y);
+            const float v2 = snake_sel<NTERMS == 3>(__uint_as_float(r[4 * q + 2]) + b4.z, a4.z, i4.z);
+            const float v3 = snake_sel<NTERMS == 3>(__uint_as_float(r[4 * q + 3]) + b4.w, a4.w, i4.w);
             const __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1), h1 = __floats2bfloat162_rn(v2, v3);
             hi[2 * qq] = pack_bf16(h0);
             hi[2 * qq + 1] = pack_bf16(h1);
@@ -593,8 +593,8 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
 #pragma unroll
             for (int h2 = 0; h2 < 2; ++h2) {
               const int j = 2 * jj + h2;
-              const float s0 = snake_f(v[j].x, a4[h2].x, i4[h2].x), s1 = snake_f(v[j].y, a4[h2].y, i4[h2].y);
-              const float s2 = snake_f(v[j].z, a4[h2].z, i4[h2].z), s3 = snake_f(v[j].w, a4[h2].w, i4[h2].w);
+              const float s0 = snake_sel<NTERMS == 3>(v[j].x, a4[h2].x, i4[h2].x), s1 = snake_sel<NTERMS == 3>(v[j].y, a4[h2].y, i4[h2].y);
+              const float s2 = snake_sel<NTERMS == 3>(v[j].z, a4[h2].z, i4[h2].z), s3 = snake_sel<NTERMS == 3>(v[j].w, a4[h2].w, i4[h2].w);
               const __nv_bfloat162 h0 = __floats2bfloat162_rn(s0, s1), h1 = __floats2bfloat162_rn(s2, s3);
               hpp[2 * h2] = pack_bf16(h0);
               hpp[2 * h2 + 1] = pack_bf16(h1);
