@@ -63,7 +63,8 @@ def test_matches_reference_golden(path, model, dev):
     _check(torch.from_numpy(g["prenet_plus_d_first8"]), x.cpu()[:, :8].transpose(1, 2).contiguous(), 1e-3, 80.0)
 
 
-@pytest.mark.parametrize("B,T,seed", [(1, 7, 1), (2, 127, 2), (2, 128, 3), (1, 129, 4), (5, 33, 5), (1, 500, 6)])
+@pytest.mark.parametrize("B,T,seed", [(1, 1, 7), (3, 2, 8), (1, 7, 1), (2, 127, 2), (2, 128, 3), (1, 129, 4), (5, 33, 5),
+                                      (1, 500, 6)])
 def test_matches_oracle(B, T, seed, model, cfg, state_dict, dev):
     """Ragged sizes around the 128-row tile boundary, vs the oracle on the same seeded inputs."""
     from oracle import bicodec_oracle as O
