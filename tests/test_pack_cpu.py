@@ -92,3 +92,43 @@ def test_product_path_has_no_cpu_fallback(cfg, state_dict):
         m.detokenize(sem, glob)
     with pytest.raises(RuntimeError):
         m.to("cpu")
+
+
+def test_header_is_plain_c_and_error_paths_answer_without_a_gpu(tmp_path):
+    """include/sparkcodec.h compiles as C99 (no C++ / CUDA / torch types in the ABI), and a C caller linked against
+    libsparkcodec.so gets error CODES + messages, not crashes, for calls that cannot succeed on this machine."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "sparkcodec.h"
+int main(void) {
+  sparkcodec_config cfg;
+  memset(&cfg, 0, sizeof cfg);
+  sparkcodec_handle* h = NULL;
+  if (sparkcodec_abi_version() != SPARKCODEC_ABI_VERSION) return 1;
+  if (sparkcodec_create(NULL, 0, &h) != SPARKCODEC_EINVAL) return 2;          /* null config */
+  if (sparkcodec_create(&cfg, 0, &h) != SPARKCODEC_EINVAL) return 3;          /* fsq_num_levels == 0 */
+  if (strlen(sparkcodec_last_error()) == 0) return 4;
+  if (sparkcodec_finalize(NULL) != SPARKCODEC_EINVAL) return 5;
+  size_t n = 0;
+  if (sparkcodec_workspace_bytes(NULL, 1, 1, &n) != SPARKCODEC_EINVAL) return 6;
+  if (sparkcodec_extract_codes(NULL, 7, 1, 1, 0, 8192, 0, 4096, NULL, NULL, NULL, 32, NULL, NULL) != SPARKCODEC_EINVAL) return 7;
+  if (sparkcodec_destroy(NULL) != SPARKCODEC_OK) return 8;
+  printf("abi ok\n");
+  return 0;
+}
+''')
+    inc = os.path.join(ROOT, "include")
+    libdir = os.path.join(ROOT, "spark-tts_b200")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-x", "c",
+                    os.path.join(inc, "sparkcodec.h")], check=True)
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", inc, str(src), "-o", str(exe), "-L", libdir,
+                    "-lsparkcodec", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and "abi ok" in out.stdout, (out.returncode, out.stdout, out.stderr)
