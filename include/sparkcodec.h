@@ -149,6 +149,20 @@ SPARKCODEC_API int sparkcodec_extract_codes(const void* token_ids, int id_dtype,
                              int32_t* semantic_out, int32_t* semantic_len, int32_t* global_out, int max_global,
                              int32_t* global_len, void* stream);
 
+/* Semantic half of BiCodec.tokenize, the encode-side mirror of the path (SURVEY.md section 8f-4;
+ * sparktts/models/bicodec.py:151-169: z = encoder(feat.transpose(1,2)); quantizer.tokenize(z);
+ * feat_encoder.py:79-90, factorized_vector_quantize.py:147-152,169-187).  Available only when the checkpoint
+ * handed to sparkcodec_set_tensor carried `encoder.*` and `quantizer.in_project.*` (else SPARKCODEC_ESTATE).
+ *   feat        : device, (batch, frames, d_model) fp32 -- the wav2vec2 feature mix the reference feeds
+ *   tokens_out  : device int64 (batch, frames): index of the nearest L2-normalised code, lowest index on ties
+ *   margin_out  : optional device fp32 (batch, frames): second-best minus best distance, so a caller can tell
+ *                 a numerical near-tie from a disagreement (NULL to skip)
+ * Uses the same workspace as sparkcodec_detokenize(batch, frames).  The speaker half (mel -> ECAPA -> FSQ
+ * global tokens) is not part of this library. */
+SPARKCODEC_API int sparkcodec_tokenize_semantic(sparkcodec_handle* h, const float* feat, int batch, int frames,
+                                 int precision, void* workspace, size_t workspace_bytes, int64_t* tokens_out,
+                                 float* margin_out, void* stream);
+
 /* ---- test / profiling hooks (not needed by a drop-in user) --------------------------------- */
 
 /* Selects tcgen05 (default) or the CUDA-core verification kernels for the dense contractions. */

@@ -172,6 +172,42 @@ def tokenizer_detokenize(sd, cfg, global_tokens: torch.Tensor, semantic_tokens: 
     return wav.detach().squeeze().cpu().numpy()
 
 
+# ---------------------------------------------------------------------------------------------
+# Encode side, semantic half: BiCodec.tokenize's `quantizer.tokenize(encoder(feat^T))`
+# ---------------------------------------------------------------------------------------------
+def feat_encoder(sd, feat: torch.Tensor, n_downsample: int = 2) -> torch.Tensor:
+    """sparktts/modules/encoder_decoder/feat_encoder.py:79-90 (Encoder.forward) with sample_ratios [1,1]:
+    VocosBackbone(D -> C, 12 layers) -> n x [SamplingBlock(ratio 1) = 3*x, VocosBackbone(2 layers)] -> Linear C -> D.
+    feat (B,T,D) -> z (B,D,T)."""
+    x = vocos_backbone(sd, "encoder.encoder", feat.transpose(1, 2), None)
+    for i in range(n_downsample):
+        xt = x.transpose(1, 2)
+        xt = xt + xt + xt                     # samper.py:79-100, both ratios 1
+        x = vocos_backbone(sd, f"encoder.downsample.{i}.1", xt, None)
+    return F.linear(x, sd["encoder.project.weight"], sd["encoder.project.bias"]).transpose(1, 2)
+
+
+def vq_tokenize(sd, z: torch.Tensor):
+    """sparktts/modules/vq/factorized_vector_quantize.py:147-152 (tokenize) and :169-187 (decode_latents):
+    in_project (weight-normed 1x1 conv D -> 8), L2-normalise encodings and codebook, squared distance,
+    indices = (-dist).max(1)[1].  z (B,D,T) -> (indices (B,T) int64, margin (B,T) fp32), margin = second-best
+    minus best distance (how far an index is from flipping under rounding noise)."""
+    z_e = F.conv1d(z, _wn_weight(sd, "quantizer.in_project"), sd["quantizer.in_project.bias"])
+    B = z_e.shape[0]
+    enc = F.normalize(z_e.transpose(1, 2).reshape(-1, z_e.shape[1]))
+    cb = F.normalize(sd["quantizer.codebook.weight"])
+    dist = enc.pow(2).sum(1, keepdim=True) - 2 * enc @ cb.t() + cb.pow(2).sum(1, keepdim=True).t()
+    idx = (-dist).max(1)[1]
+    two = dist.topk(2, dim=1, largest=False).values
+    return idx.reshape(B, -1), (two[:, 1] - two[:, 0]).reshape(B, -1)
+
+
+@torch.no_grad()
+def tokenize_semantic(sd, cfg, feat: torch.Tensor):
+    """The semantic half of sparktts/models/bicodec.py:151-169 (BiCodec.tokenize): feat (B,T,D) -> (indices, margin)."""
+    return vq_tokenize(sd, feat_encoder(sd, feat, len(cfg.sample_ratios)))
+
+
 def snr_db(ref: torch.Tensor, test: torch.Tensor) -> float:
     ref = ref.double().flatten()
     err = test.double().flatten() - ref

@@ -87,3 +87,35 @@ class ReferenceDetokenizer(torch.nn.Module):
         x = self.prenet(z_q, d_vector)
         x = x + d_vector.unsqueeze(-1)
         return self.decoder(x)
+
+
+class ReferenceSemanticTokenizer(torch.nn.Module):
+    """The reference modules behind the semantic half of BiCodec.tokenize (sparktts/models/bicodec.py:151-169):
+    ``Encoder`` (feat_encoder.py) and ``FactorizedVectorQuantize`` (its in_project + codebook search)."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        _import_reference()
+        from sparktts.modules.vq.factorized_vector_quantize import FactorizedVectorQuantize
+        from sparktts.modules.encoder_decoder.feat_encoder import Encoder
+
+        self.encoder = Encoder(
+            input_channels=cfg.d_model, vocos_dim=cfg.vocos_dim, vocos_intermediate_dim=cfg.vocos_intermediate_dim,
+            vocos_num_layers=cfg.vocos_num_layers, out_channels=cfg.d_model, sample_ratios=list(cfg.sample_ratios))
+        self.quantizer = FactorizedVectorQuantize(
+            input_dim=cfg.d_model, codebook_size=cfg.codebook_size, codebook_dim=cfg.codebook_dim,
+            commitment=0.25)
+        self.eval()
+
+    def load_checkpoint(self, sd):
+        own = {k: v for k, v in sd.items() if k.startswith("encoder.") or k.startswith("quantizer.")}
+        missing, unexpected = self.load_state_dict(own, strict=False)
+        assert not unexpected, unexpected
+        assert all(k == "quantizer.cluster_size" for k in missing), missing
+        return self
+
+    @torch.no_grad()
+    def tokenize(self, feat):
+        """feat (B,T,D) -> semantic tokens (B,T), exactly the two lines of bicodec.py:165-166."""
+        z = self.encoder(feat.transpose(1, 2))
+        return self.quantizer.tokenize(z)

@@ -50,6 +50,8 @@ SIGNATURES = {
     "sparkcodec_check_tokens": (C.c_int, [_H, C.c_void_p]),
     "sparkcodec_extract_codes": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "sparkcodec_tokenize_semantic": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+                                               C.c_void_p, C.c_void_p, C.c_void_p]),
     "sparkcodec_set_impl": (C.c_int, [_H, C.c_int]),
     "sparkcodec_detokenize_tap": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.c_void_p, C.c_size_t, C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t,

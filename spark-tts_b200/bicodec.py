@@ -255,6 +255,30 @@ class BiCodec:
             C.c_void_p(wav.data_ptr()), self._stream()))
         return wav
 
+    # ------------------------------------------------------------------ encode side, semantic half
+    @torch.no_grad()
+    def tokenize_semantic(self, feat: torch.Tensor, precision: Optional[str] = None, return_margin: bool = False):
+        """The semantic half of the reference's ``BiCodec.tokenize`` (bicodec.py:151-169):
+        ``quantizer.tokenize(encoder(feat.transpose(1, 2)))``.  feat (B, T, d_model) fp32 (the wav2vec2 feature
+        mix) -> semantic tokens (B, T) int64.  Needs a checkpoint that carries ``encoder.*`` and
+        ``quantizer.in_project.*``.  With ``return_margin`` also returns the (B, T) fp32 gap between the best and
+        the second-best code distance (a near-zero gap marks a numerical tie).  The speaker half (mel -> ECAPA ->
+        FSQ) is not built."""
+        self._ensure(feat)
+        if feat.dim() != 3 or feat.shape[2] != self.cfg.d_model or feat.dtype != torch.float32:
+            raise ValueError(f"feat must be float32 (B, T, {self.cfg.d_model})")
+        feat = feat.contiguous()
+        B, T, _ = feat.shape
+        tokens = torch.empty((B, T), dtype=torch.int64, device=self._device)
+        margin = torch.empty((B, T), dtype=torch.float32, device=self._device) if return_margin else None
+        if B and T:
+            ws, ws_bytes = self._workspace(B, T)
+            _lib.check(_lib.load().sparkcodec_tokenize_semantic(
+                self._handle, C.c_void_p(feat.data_ptr()), B, T, self._prec(precision), C.c_void_p(ws), ws_bytes,
+                C.c_void_p(tokens.data_ptr()), C.c_void_p(margin.data_ptr()) if return_margin else None,
+                self._stream()))
+        return (tokens, margin) if return_margin else tokens
+
     def halo_frames(self) -> Tuple[int, int]:
         if self._handle is None:
             raise _lib.SparkCodecError("model is not on a device yet")

@@ -84,6 +84,11 @@ struct sparkcodec_handle {
   // prenet
   std::vector<Backbone> backbones;
   GemmWeights linear;
+  // encode side (optional: only when the checkpoint carries encoder.* and quantizer.in_project.*)
+  bool has_encoder = false;
+  std::vector<Backbone> enc_backbones;
+  float *tok_mat = nullptr, *tok_vec = nullptr;        // in_project . encoder.project folded: (codebook_dim, C)
+  float *codes_n = nullptr, *codes_sq = nullptr;       // F.normalize(codebook) rows and their squared norms
   // wave generator
   GemmWeights conv_in;
   SnakeParams s_conv_in;   // first block's input snake (conv_in epilogue)
@@ -194,10 +199,10 @@ static int build_conv1d(sparkcodec_handle* h, const std::string& prefix, int c_o
 }
 
 static int build_backbone(sparkcodec_handle* h, const std::string& prefix, int layers, bool ada, float post_scale,
-                          Backbone* bb) {
+                          Backbone* bb, int c_in = 0) {
   const int C = h->cfg.vocos_dim, H = h->cfg.vocos_intermediate_dim;
   bb->ada = ada;
-  SC_TRY(build_conv1d(h, prefix + ".embed", C, C, 7, 1, false, nullptr, &bb->embed));
+  SC_TRY(build_conv1d(h, prefix + ".embed", C, c_in ? c_in : C, 7, 1, false, nullptr, &bb->embed));
   const HostTensor *t, *u;
   if (!ada) {
     SC_TRY(get(h, prefix + ".norm.weight", &t, {C}));
@@ -369,6 +374,56 @@ static int do_finalize(sparkcodec_handle* h) {
     h->head_bias = t->data[0];
     h->head_c = cin;
   }
+  // ---- encode side, semantic half (bicodec.py:151-169: encoder -> quantizer.tokenize); optional ----
+  if (h->host.count("encoder.encoder.embed.weight")) {
+    if (c.codebook_dim != 8) { set_error("semantic tokenize needs codebook_dim == 8"); return SPARKCODEC_EINVAL; }
+    h->enc_backbones.resize(c.num_downsample + 1);
+    // feat_encoder.py:66-77: VocosBackbone(input -> C, vocos_num_layers) then the down-sample stages; every
+    // SamplingBlock (ratio 1) returns 3 x, folded into the preceding final LayerNorm like in the prenet
+    SC_TRY(build_backbone(h, "encoder.encoder", c.vocos_num_layers, false, c.num_downsample > 0 ? 3.0f : 1.0f,
+                          &h->enc_backbones[0], D));
+    for (int i = 0; i < c.num_downsample; ++i)
+      SC_TRY(build_backbone(h, "encoder.downsample." + std::to_string(i) + ".1", c.downsample_layers, false,
+                            i + 1 < c.num_downsample ? 3.0f : 1.0f, &h->enc_backbones[i + 1]));
+    // z_e = W_in (W_p x + b_p) + b_in: project (Linear C -> D) and in_project (1x1 conv D -> 8) have nothing
+    // between them (feat_encoder.py:87-90, factorized_vector_quantize.py:147-150)
+    std::vector<float> win;
+    SC_TRY(conv_weight(h, "quantizer.in_project", {c.codebook_dim, D, 1}, &win));
+    const HostTensor *bin, *wp, *bp;
+    SC_TRY(get(h, "quantizer.in_project.bias", &bin, {c.codebook_dim}));
+    SC_TRY(get(h, "encoder.project.weight", &wp, {D, C}));
+    SC_TRY(get(h, "encoder.project.bias", &bp, {D}));
+    std::vector<float> mat((size_t)c.codebook_dim * C), vec(c.codebook_dim);
+    for (int j = 0; j < c.codebook_dim; ++j) {
+      for (int o = 0; o < C; ++o) {
+        double a = 0.0;
+        for (int d = 0; d < D; ++d) a += (double)win[(size_t)j * D + d] * (double)wp->data[(size_t)d * C + o];
+        mat[(size_t)j * C + o] = (float)a;
+      }
+      double a = bin->data[j];
+      for (int d = 0; d < D; ++d) a += (double)win[(size_t)j * D + d] * (double)bp->data[d];
+      vec[j] = (float)a;
+    }
+    SC_TRY(upload(h, mat, &h->tok_mat));
+    SC_TRY(upload(h, vec, &h->tok_vec));
+    SC_TRY(get(h, "quantizer.codebook.weight", &t, {c.codebook_size, c.codebook_dim}));
+    std::vector<float> cn(t->data.size()), csq(c.codebook_size);
+    for (int k = 0; k < c.codebook_size; ++k) {
+      float n2 = 0.f;
+      for (int j = 0; j < c.codebook_dim; ++j) n2 += t->data[(size_t)k * c.codebook_dim + j] * t->data[(size_t)k * c.codebook_dim + j];
+      const float inv = 1.0f / std::max(std::sqrt(n2), 1e-12f);
+      float s2 = 0.f;
+      for (int j = 0; j < c.codebook_dim; ++j) {
+        const float v = t->data[(size_t)k * c.codebook_dim + j] * inv;
+        cn[(size_t)k * c.codebook_dim + j] = v;
+        s2 += v * v;
+      }
+      csq[k] = s2;
+    }
+    SC_TRY(upload(h, cn, &h->codes_n));
+    SC_TRY(upload(h, csq, &h->codes_sq));
+    h->has_encoder = true;
+  }
   h->host.clear();
   h->finalized = true;
   return 0;
@@ -519,6 +574,62 @@ static OpBuf mode_op(OpBuf o, int prec) {
   return o;
 }
 
+// One VocosBackbone (vocos.py:324-335) over operand planes `in` (B, T, c_in): embed conv k7 -> norm -> ConvNeXt
+// blocks -> final LayerNorm, written as operand planes (out_op) or fp32 (out_f32).  Shared by the prenet and
+// the encoder; `ada` = per-utterance AdaLN scale/shift rows (stride ada_n) or null.
+static int run_backbone(Pass& P, Backbone& bb, const std::string& name, Workspace& W, const OpBuf& in, const float* ada,
+                        int ada_n, float* out_f32, const OpBuf& out_op) {
+  const int B = P.B, T = P.T, prec = P.prec, C = P.h->cfg.vocos_dim;
+  cudaStream_t st = P.st;
+  const OpBuf pa = mode_op(W.pa, prec), ph = mode_op(W.ph, prec);
+  Epilogue e;
+  e.out_f32 = W.py;
+  SC_TRY(P.gemm(bb.embed, in, T, e));                                             // embed conv k7 -> py
+  const float* sc = ada ? ada : bb.norm_w;
+  const float* sh = ada ? ada + C : bb.norm_b;
+  SC_TRY(P.prof_begin("ln", 0, (double)B * T * C * 8));
+  SC_TRY(launch_dwconv_ln(W.py, B, T, C, nullptr, nullptr, sc, sh, ada ? ada_n : 0, 1e-6f, W.px, OpBuf(), st));
+  SC_TRY(P.prof_end());
+  SC_TRY(P.tap_f32((name + ".norm").c_str(), W.px, T, C));
+  for (size_t i = 0; i < bb.blocks.size(); ++i) {
+    ConvNeXt& blk = bb.blocks[i];
+    sc = ada ? ada + (size_t)(i + 1) * 2 * C : blk.ln_w;
+    sh = ada ? ada + (size_t)(i + 1) * 2 * C + C : blk.ln_b;
+    SC_TRY(P.prof_begin("dwconv_ln", 0, (double)B * T * C * (4 + (prec == SPARKCODEC_PREC_FP32 ? 4 : 2))));
+    SC_TRY(launch_dwconv_ln(W.px, B, T, C, blk.dw_w, blk.dw_b, sc, sh, ada ? ada_n : 0, 1e-6f, nullptr, pa, st));
+    SC_TRY(P.prof_end());
+    Epilogue e1;
+    e1.act = ACT_GELU;
+    e1.out_op = ph;
+    SC_TRY(P.gemm(blk.pw1, pa, T, e1));                                            // 384 -> 2048, GELU
+    Epilogue e2;
+    e2.residual = W.px;
+    e2.out_f32 = W.px;
+    SC_TRY(P.gemm(blk.pw2, ph, T, e2));                                            // 2048 -> 384, gamma, + x
+    SC_TRY(P.tap_f32((name + ".convnext." + std::to_string(i)).c_str(), W.px, T, C));
+  }
+  return launch_dwconv_ln(W.px, B, T, C, nullptr, nullptr, bb.final_w, bb.final_b, 0, 1e-6f, out_f32, out_op, st);
+}
+
+// Semantic half of BiCodec.tokenize (bicodec.py:151-169): feat (B, T, D) fp32 -> encoder -> nearest code index.
+static int run_tokenize(Pass& P, const float* feat, Workspace& W, long long* idx_out, float* margin_out) {
+  sparkcodec_handle* h = P.h;
+  const sparkcodec_config& c = h->cfg;
+  const int B = P.B, T = P.T, prec = P.prec;
+  const OpBuf pa = mode_op(W.pa, prec), w_in = mode_op(W.w_in, prec);
+  SC_TRY(launch_split(feat, w_in, (size_t)B * T * c.d_model, P.st));
+  for (size_t bi = 0; bi < h->enc_backbones.size(); ++bi) {
+    const bool last = bi + 1 == h->enc_backbones.size();
+    const std::string name = bi == 0 ? std::string("encoder.encoder") : "encoder.downsample." + std::to_string(bi - 1) + ".1";
+    SC_TRY(run_backbone(P, h->enc_backbones[bi], name, W, bi == 0 ? w_in : pa, nullptr, 0, last ? W.py : nullptr,
+                        last ? OpBuf() : pa));
+  }
+  SC_TRY(P.prof_begin("vq_search", 2.0 * B * T * (double)c.codebook_size * c.codebook_dim, (double)B * T * (c.vocos_dim * 4 + 8)));
+  SC_TRY(launch_vq_search(W.py, (size_t)B * T, c.vocos_dim, h->tok_mat, h->tok_vec, h->codes_n, h->codes_sq,
+                          c.codebook_size, c.codebook_dim, idx_out, margin_out, P.st));
+  return P.prof_end();
+}
+
 // One pass over B utterances of T frames.  x_in != null: skip the token stages + prenet and start the
 // wave generator from x_in (B,T,D) fp32.  x_out != null: stop after prenet(+d) and write it as fp32.
 static int run_pass(Pass& P, const void* sem, int sem_dt, const void* glob, int glob_dt, Workspace& W,
@@ -553,33 +664,7 @@ static int run_pass(Pass& P, const void* sem, int sem_dt, const void* glob, int 
       Backbone& bb = h->backbones[bi];
       const std::string name = bb.ada ? std::string("prenet.vocos_backbone")
                                       : "prenet.downsample." + std::to_string(bi) + ".1";
-      Epilogue e;
-      e.out_f32 = W.py;
-      SC_TRY(P.gemm(bb.embed, pa, T, e));                                           // embed conv k7 -> py
-      const float* sc = bb.ada ? W.ada : bb.norm_w;
-      const float* sh = bb.ada ? W.ada + C : bb.norm_b;
-      SC_TRY(P.prof_begin("ln", 0, (double)B * T * C * 8));
-      SC_TRY(launch_dwconv_ln(W.py, B, T, C, nullptr, nullptr, sc, sh, bb.ada ? ada_n : 0, 1e-6f, W.px, OpBuf(), st));
-      SC_TRY(P.prof_end());
-      SC_TRY(P.tap_f32((name + ".norm").c_str(), W.px, T, C));
-      for (size_t i = 0; i < bb.blocks.size(); ++i) {
-        ConvNeXt& blk = bb.blocks[i];
-        sc = bb.ada ? W.ada + (size_t)(i + 1) * 2 * C : blk.ln_w;
-        sh = bb.ada ? W.ada + (size_t)(i + 1) * 2 * C + C : blk.ln_b;
-        SC_TRY(P.prof_begin("dwconv_ln", 0, (double)B * T * C * (4 + (prec == SPARKCODEC_PREC_FP32 ? 4 : 2))));
-        SC_TRY(launch_dwconv_ln(W.px, B, T, C, blk.dw_w, blk.dw_b, sc, sh, bb.ada ? ada_n : 0, 1e-6f, nullptr, pa, st));
-        SC_TRY(P.prof_end());
-        Epilogue e1;
-        e1.act = ACT_GELU;
-        e1.out_op = ph;
-        SC_TRY(P.gemm(blk.pw1, pa, T, e1));                                          // 384 -> 2048, GELU
-        Epilogue e2;
-        e2.residual = W.px;
-        e2.out_f32 = W.px;
-        SC_TRY(P.gemm(blk.pw2, ph, T, e2));                                          // 2048 -> 384, gamma, + x
-        SC_TRY(P.tap_f32((name + ".convnext." + std::to_string(i)).c_str(), W.px, T, C));
-      }
-      SC_TRY(launch_dwconv_ln(W.px, B, T, C, nullptr, nullptr, bb.final_w, bb.final_b, 0, 1e-6f, nullptr, pa, st));
+      SC_TRY(run_backbone(P, bb, name, W, pa, bb.ada ? W.ada : nullptr, ada_n, nullptr, pa));
       // oracle tap names; NOTE the x3 of the following SamplingBlock is already folded in for downsample.0
       const std::string out_name = bb.ada ? std::string("prenet.vocos_backbone") : "prenet.downsample." + std::to_string(bi);
       SC_TRY(P.tap_op(out_name.c_str(), pa, T, C));
@@ -771,7 +856,7 @@ int sparkcodec_set_tensor(sparkcodec_handle* h, const char* key, const float* da
   if (h->finalized) { set_error("weights are already finalized"); return SPARKCODEC_ESTATE; }
   const std::string k(key);
   static const char* used[] = {"quantizer.codebook.", "quantizer.out_project.", "speaker_encoder.quantizer.project_out.",
-                               "speaker_encoder.project.", "prenet.", "decoder."};
+                               "speaker_encoder.project.", "prenet.", "decoder.", "encoder.", "quantizer.in_project."};
   bool keep = false;
   for (const char* p : used) keep |= k.rfind(p, 0) == 0;
   if (!keep) return 0;   // encode-side / training-only tensor
@@ -819,6 +904,38 @@ int sparkcodec_wavegen(sparkcodec_handle* h, const float* x_in, int batch, int f
   if (batch > 0 && frames > 0 && (!x_in || !wav_out)) { set_error("null tensor pointer"); return SPARKCODEC_EINVAL; }
   return run_all(h, nullptr, SPARKCODEC_I32, nullptr, SPARKCODEC_I32, batch, frames, precision, workspace,
                  workspace_bytes, x_in, nullptr, wav_out, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int sparkcodec_tokenize_semantic(sparkcodec_handle* h, const float* feat, int batch, int frames, int precision,
+                                 void* workspace, size_t workspace_bytes, int64_t* tokens_out, float* margin_out,
+                                 void* stream) {
+  SC_TRY(check_common(h, batch, frames, precision));
+  if (!h->has_encoder) {
+    set_error("the checkpoint had no encoder.* / quantizer.in_project.* tensors: semantic tokenize is unavailable");
+    return SPARKCODEC_ESTATE;
+  }
+  if (batch == 0 || frames == 0) return 0;
+  if (!feat || !tokens_out) { set_error("null tensor pointer"); return SPARKCODEC_EINVAL; }
+  int per_pass = batch;
+  while (per_pass > 1 && workspace_needed(h, per_pass, frames) > workspace_bytes) per_pass = (per_pass + 1) / 2;
+  if (workspace_needed(h, per_pass, frames) > workspace_bytes || !workspace) {
+    set_error("workspace of %zu bytes cannot hold even one utterance of %d frames (%zu needed)", workspace_bytes,
+              frames, workspace_needed(h, 1, frames));
+    return SPARKCODEC_ENOMEM;
+  }
+  SC_CUDA(cudaSetDevice(h->device));
+  g_launch_counter = &h->launches;
+  for (int b0 = 0; b0 < batch; b0 += per_pass) {
+    const int B = std::min(per_pass, batch - b0);
+    Arena a{static_cast<char*>(workspace), 0, workspace_bytes};
+    Workspace W;
+    carve(h, a, B, frames, &W);
+    Pass P{h, B, frames, precision, static_cast<cudaStream_t>(stream), nullptr};
+    SC_TRY(run_tokenize(P, feat + (size_t)b0 * frames * h->cfg.d_model, W,
+                        reinterpret_cast<long long*>(tokens_out) + (size_t)b0 * frames,
+                        margin_out ? margin_out + (size_t)b0 * frames : nullptr));
+  }
+  return 0;
 }
 
 int sparkcodec_halo_frames(sparkcodec_handle* h, int* prenet_halo, int* wavegen_halo) {

@@ -111,6 +111,9 @@ int launch_extract_codes(const void* ids, int id_dtype, int batch, int n_tokens,
 int launch_vq_embed(const void* sem, int sem_dtype, int batch, int frames, int t0, int rows,
                     int codebook_size, int codebook_dim, const float* codebook, const float* mat,
                     const float* vec, int c_out, OpBuf out, int* err_flag, cudaStream_t s);
+int launch_vq_search(const float* x, size_t n_frames, int c, const float* mat, const float* vec, const float* codes_n,
+                     const float* codes_sq, int codebook_size, int codebook_dim, long long* idx_out, float* margin_out,
+                     cudaStream_t s);                                                       // encode side: nearest code
 int launch_vq_zq(const void* sem, int sem_dtype, int n_tok, int codebook_size, int codebook_dim,
                  const float* codebook, const float* w, const float* bias, int d_model, float* out,
                  cudaStream_t s);

@@ -102,6 +102,86 @@ __global__ void vq_zq_kernel(const void* __restrict__ sem, int sem_dtype, size_t
   out[i] = a + __ldg(bias + c);
 }
 
+// Semantic tokenize tail (encode side): z_e = in_project(project(x)) folded into one (cdim x C)
+// map, F.normalize, then the nearest normalised code: argmin_k |c_k|^2 - 2 e.c_k, lowest index on ties
+// (factorized_vector_quantize.py:147-152, 169-187: dist = |e|^2 - 2 e c^T + |c|^2, indices = (-dist).max(1)[1]).
+// One warp owns kVqFrames frames: the lanes split the channels for the projection and the codes for the search
+// (code k = 32 i + lane: coalesced 32 B rows; the 256 KB table stays in L1/L2).  Also returns the margin between
+// the best and second-best score so that callers can tell a real disagreement from a numerical near-tie.
+constexpr int kVqFrames = 8;
+constexpr int kVqDim = 8;
+__global__ void __launch_bounds__(256) vq_search_kernel(const float* __restrict__ x, size_t n_frames, int c,
+                                                        const float* __restrict__ mat, const float* __restrict__ vec,
+                                                        const float* __restrict__ codes_n,
+                                                        const float* __restrict__ codes_sq, int codebook_size,
+                                                        long long* __restrict__ idx_out,
+                                                        float* __restrict__ margin_out) {
+  const int lane = threadIdx.x & 31;
+  const size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+  const size_t f0 = warp * kVqFrames;
+  if (f0 >= n_frames) return;
+  float e[kVqFrames][kVqDim];
+#pragma unroll
+  for (int f = 0; f < kVqFrames; ++f) {
+    const size_t fr = f0 + f < n_frames ? f0 + f : n_frames - 1;
+    float acc[kVqDim];
+#pragma unroll
+    for (int j = 0; j < kVqDim; ++j) acc[j] = 0.f;
+    for (int ch = lane; ch < c; ch += 32) {
+      const float v = __ldg(x + fr * c + ch);
+#pragma unroll
+      for (int j = 0; j < kVqDim; ++j) acc[j] = fmaf(__ldg(mat + (size_t)j * c + ch), v, acc[j]);
+    }
+    float nrm = 0.f;
+#pragma unroll
+    for (int j = 0; j < kVqDim; ++j) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+      acc[j] += __ldg(vec + j);
+      nrm = fmaf(acc[j], acc[j], nrm);
+    }
+    const float inv = 1.0f / fmaxf(sqrtf(nrm), 1e-12f);   // F.normalize: x / max(||x||, eps)
+#pragma unroll
+    for (int j = 0; j < kVqDim; ++j) e[f][j] = acc[j] * inv;
+  }
+  float best[kVqFrames], second[kVqFrames];
+  int arg[kVqFrames];
+#pragma unroll
+  for (int f = 0; f < kVqFrames; ++f) { best[f] = INFINITY; second[f] = INFINITY; arg[f] = 0x7fffffff; }
+  for (int k = lane; k < codebook_size; k += 32) {
+    const float4 c0 = __ldg(reinterpret_cast<const float4*>(codes_n + (size_t)k * kVqDim));
+    const float4 c1 = __ldg(reinterpret_cast<const float4*>(codes_n + (size_t)k * kVqDim + 4));
+    const float sq = __ldg(codes_sq + k);
+#pragma unroll
+    for (int f = 0; f < kVqFrames; ++f) {
+      float d = e[f][0] * c0.x;
+      d = fmaf(e[f][1], c0.y, d); d = fmaf(e[f][2], c0.z, d); d = fmaf(e[f][3], c0.w, d);
+      d = fmaf(e[f][4], c1.x, d); d = fmaf(e[f][5], c1.y, d); d = fmaf(e[f][6], c1.z, d); d = fmaf(e[f][7], c1.w, d);
+      const float sc = fmaf(-2.0f, d, sq);
+      if (sc < best[f]) { second[f] = best[f]; best[f] = sc; arg[f] = k; }
+      else second[f] = fminf(second[f], sc);
+    }
+  }
+#pragma unroll
+  for (int f = 0; f < kVqFrames; ++f) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best[f], o), os = __shfl_xor_sync(0xffffffffu, second[f], o);
+      const int oa = __shfl_xor_sync(0xffffffffu, arg[f], o);
+      if (ob < best[f] || (ob == best[f] && oa < arg[f])) {
+        second[f] = fminf(best[f], os);
+        best[f] = ob; arg[f] = oa;
+      } else {
+        second[f] = fminf(second[f], ob);
+      }
+    }
+    if (lane == 0 && f0 + f < n_frames) {
+      idx_out[f0 + f] = arg[f];
+      if (margin_out) margin_out[f0 + f] = second[f] - best[f];
+    }
+  }
+}
+
 // FSQ: level_j = (idx / basis_j) % L_j, code_j = (level_j - L_j/2) / (L_j/2)   (exact in fp32)
 // z[c] = W_po[c,:] . code + b_po[c];  flat[b, c*N + n] = z[c]   (finite_scalar_quantization.py:143-162,
 // residual_fsq.py:191-199, speaker_encoder.py:107-111).  One block per (b, n), one thread per c.
@@ -531,6 +611,16 @@ int launch_vq_zq(const void* sem, int sem_dtype, int n_tok, int codebook_size, i
   const size_t n = (size_t)n_tok * d_model;
   vq_zq_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(sem, sem_dtype, (size_t)n_tok, codebook_size, codebook_dim,
                                                           codebook, w, bias, d_model, out);
+  SC_LAUNCH_CHECK();
+  return 0;
+}
+int launch_vq_search(const float* x, size_t n_frames, int c, const float* mat, const float* vec, const float* codes_n,
+                     const float* codes_sq, int codebook_size, int codebook_dim, long long* idx_out, float* margin_out,
+                     cudaStream_t s) {
+  if (codebook_dim != kVqDim) { set_error("vq_search: codebook_dim must be %d", kVqDim); return SPARKCODEC_EINVAL; }
+  const size_t warps = (n_frames + kVqFrames - 1) / kVqFrames;
+  vq_search_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, s>>>(x, n_frames, c, mat, vec, codes_n, codes_sq,
+                                                              codebook_size, idx_out, margin_out);
   SC_LAUNCH_CHECK();
   return 0;
 }

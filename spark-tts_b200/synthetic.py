@@ -41,6 +41,39 @@ def _wn(sd, g, prefix, shape, std=0.02):
     sd[prefix + ".weight_g"] = norm * (1.0 + _n(g, norm.shape, 0.1))
 
 
+def _backbone(sd, g, cfg, prefix: str, layers: int, ada: bool, c_in: int = 0):
+    """One VocosBackbone's tensors (vocos.py:293-322); c_in = input channels of the embed conv (default vocos_dim)."""
+    D, C, H = cfg.d_model, cfg.vocos_dim, cfg.vocos_intermediate_dim
+    sd[prefix + ".embed.weight"] = _tn(g, (C, c_in or C, 7), 0.02)
+    sd[prefix + ".embed.bias"] = _n(g, (C,), 0.05)
+
+    def norm(p):
+        if ada:
+            # reference init is ones_/zeros_ then overwritten by trunc_normal(0.02) (vocos.py:319-322);
+            # use a scale around 1 so conditioning matters but activations stay O(1)
+            sd[p + ".scale.weight"] = _tn(g, (C, D), 0.02)
+            sd[p + ".scale.bias"] = 1.0 + _n(g, (C,), 0.05)
+            sd[p + ".shift.weight"] = _tn(g, (C, D), 0.02)
+            sd[p + ".shift.bias"] = _n(g, (C,), 0.05)
+        else:
+            sd[p + ".weight"] = 1.0 + _n(g, (C,), 0.05)
+            sd[p + ".bias"] = _n(g, (C,), 0.05)
+
+    norm(prefix + ".norm")
+    for i in range(layers):
+        p = f"{prefix}.convnext.{i}"
+        sd[p + ".gamma"] = (1.0 / layers) * (1.0 + _n(g, (C,), 0.2))
+        sd[p + ".dwconv.weight"] = _tn(g, (C, 1, 7), 0.2)
+        sd[p + ".dwconv.bias"] = _n(g, (C,), 0.05)
+        norm(p + ".norm")
+        sd[p + ".pwconv1.weight"] = _tn(g, (H, C), 0.05)
+        sd[p + ".pwconv1.bias"] = _n(g, (H,), 0.05)
+        sd[p + ".pwconv2.weight"] = _tn(g, (C, H), 0.05)
+        sd[p + ".pwconv2.bias"] = _n(g, (C,), 0.05)
+    sd[prefix + ".final_layer_norm.weight"] = 1.0 + _n(g, (C,), 0.05)
+    sd[prefix + ".final_layer_norm.bias"] = _n(g, (C,), 0.05)
+
+
 def synthetic_state_dict(cfg: BiCodecConfig, seed: int = 0) -> Dict[str, torch.Tensor]:
     g = torch.Generator().manual_seed(seed)
     sd: Dict[str, torch.Tensor] = {}
@@ -63,34 +96,7 @@ def synthetic_state_dict(cfg: BiCodecConfig, seed: int = 0) -> Dict[str, torch.T
     sd["prenet.linear_pre.bias"] = _n(g, (C,), 0.05)
 
     def backbone(prefix: str, layers: int, ada: bool):
-        sd[prefix + ".embed.weight"] = _tn(g, (C, C, 7), 0.02)
-        sd[prefix + ".embed.bias"] = _n(g, (C,), 0.05)
-
-        def norm(p):
-            if ada:
-                # reference init is ones_/zeros_ then overwritten by trunc_normal(0.02) (vocos.py:319-322);
-                # use a scale around 1 so conditioning matters but activations stay O(1)
-                sd[p + ".scale.weight"] = _tn(g, (C, D), 0.02)
-                sd[p + ".scale.bias"] = 1.0 + _n(g, (C,), 0.05)
-                sd[p + ".shift.weight"] = _tn(g, (C, D), 0.02)
-                sd[p + ".shift.bias"] = _n(g, (C,), 0.05)
-            else:
-                sd[p + ".weight"] = 1.0 + _n(g, (C,), 0.05)
-                sd[p + ".bias"] = _n(g, (C,), 0.05)
-
-        norm(prefix + ".norm")
-        for i in range(layers):
-            p = f"{prefix}.convnext.{i}"
-            sd[p + ".gamma"] = (1.0 / layers) * (1.0 + _n(g, (C,), 0.2))
-            sd[p + ".dwconv.weight"] = _tn(g, (C, 1, 7), 0.2)
-            sd[p + ".dwconv.bias"] = _n(g, (C,), 0.05)
-            norm(p + ".norm")
-            sd[p + ".pwconv1.weight"] = _tn(g, (H, C), 0.05)
-            sd[p + ".pwconv1.bias"] = _n(g, (H,), 0.05)
-            sd[p + ".pwconv2.weight"] = _tn(g, (C, H), 0.05)
-            sd[p + ".pwconv2.bias"] = _n(g, (C,), 0.05)
-        sd[prefix + ".final_layer_norm.weight"] = 1.0 + _n(g, (C,), 0.05)
-        sd[prefix + ".final_layer_norm.bias"] = _n(g, (C,), 0.05)
+        _backbone(sd, g, cfg, prefix, layers, ada)
 
     for i in range(len(cfg.sample_ratios)):
         backbone(f"prenet.downsample.{i}.1", cfg.downsample_layers, ada=False)
@@ -137,3 +143,31 @@ def synthetic_tokens(cfg: BiCodecConfig, batch: int, frames: int, seed: int = 12
     sem = torch.randint(0, cfg.codebook_size, (batch, frames), generator=g, dtype=torch.int64)
     glob = torch.randint(0, n_glob, (batch, 1, cfg.token_num), generator=g, dtype=torch.int64).to(torch.int32)
     return sem, glob
+
+
+def synthetic_encoder_state_dict(cfg: BiCodecConfig, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Encode-side tensors of the semantic half of ``BiCodec.tokenize`` (bicodec.py:151-169): the feature encoder
+    (feat_encoder.py:27-77, same widths as the prenet) and the quantizer's ``in_project``
+    (factorized_vector_quantize.py:59-61).  Drawn from its own generator so that ``synthetic_state_dict`` -- and
+    every golden made from it -- stays bit-identical; merge the two dicts to get a checkpoint that can do both."""
+    g = torch.Generator().manual_seed(seed + 7919)
+    sd: Dict[str, torch.Tensor] = {}
+    D, C = cfg.d_model, cfg.vocos_dim
+    _backbone(sd, g, cfg, "encoder.encoder", cfg.vocos_num_layers, ada=False, c_in=D)
+    for i in range(len(cfg.sample_ratios)):
+        _backbone(sd, g, cfg, f"encoder.downsample.{i}.1", cfg.downsample_layers, ada=False)
+    sd["encoder.project.weight"] = _tn(g, (D, C), 0.05)
+    sd["encoder.project.bias"] = _n(g, (D,), 0.05)
+    _wn(sd, g, "quantizer.in_project", (cfg.codebook_dim, D, 1), std=0.05)
+    sd["quantizer.in_project.bias"] = _n(g, (cfg.codebook_dim,), 0.05)
+    return sd
+
+
+def synthetic_features(cfg: BiCodecConfig, batch: int, frames: int, seed: int = 4321) -> torch.Tensor:
+    """(B, T, d_model) fp32 stand-in for the wav2vec2 feature mix ``BiCodec.tokenize`` receives, with the
+    frame-to-frame correlation a real feature sequence has (so the 7-tap convolutions see structure)."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn((batch, frames, cfg.d_model), generator=g)
+    if frames > 1:
+        x[:, 1:] = 0.6 * x[:, 1:] + 0.4 * x[:, :-1]
+    return x.contiguous()

@@ -19,9 +19,11 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
-from oracle.reference_loader import ReferenceDetokenizer            # noqa: E402
+from oracle import bicodec_oracle as O                                          # noqa: E402
+from oracle.reference_loader import ReferenceDetokenizer, ReferenceSemanticTokenizer   # noqa: E402
 from spark_tts_b200.config import BiCodecConfig                     # noqa: E402
-from spark_tts_b200.synthetic import synthetic_state_dict, synthetic_tokens  # noqa: E402
+from spark_tts_b200.synthetic import (synthetic_encoder_state_dict, synthetic_features,   # noqa: E402
+                                      synthetic_state_dict, synthetic_tokens)
 
 # name, batch, frames, token seed, semantic dtype, global dtype
 CASES = [
@@ -31,6 +33,8 @@ CASES = [
     ("d_b2_t130", 2, 130, 104, torch.int64, torch.int32),
 ]
 WEIGHT_SEED = 0
+# semantic tokenize (encode side): name, batch, frames, feature seed
+TOKENIZE_CASES = [("a_b2_t60", 2, 60, 201), ("b_b1_t7", 1, 7, 202), ("c_b3_t1", 3, 1, 203), ("d_b1_t300", 1, 300, 204)]
 
 
 def main():
@@ -60,6 +64,19 @@ def main():
             prenet_plus_d_first8=x[:, :, :8].numpy(), output_waveform=wav.numpy(),
         )
         print(name, "wav", tuple(wav.shape), "rms", float(wav.pow(2).mean().sqrt()))
+    # semantic half of BiCodec.tokenize (bicodec.py:151-169) through the reference's Encoder + quantizer.tokenize;
+    # the features are regenerated from the seed (synthetic_features), only the answers are stored
+    sd_all = {**sd, **synthetic_encoder_state_dict(cfg, seed=WEIGHT_SEED)}
+    tok = ReferenceSemanticTokenizer(cfg).load_checkpoint(sd_all)
+    for name, B, T, seed in TOKENIZE_CASES:
+        feat = synthetic_features(cfg, B, T, seed)
+        idx = tok.tokenize(feat)
+        _, margin = O.tokenize_semantic(sd_all, cfg, feat)
+        np.savez_compressed(os.path.join(out_dir, f"tokenize_{name}.npz"), weight_seed=np.int64(WEIGHT_SEED),
+                            feat_seed=np.int64(seed), batch=np.int64(B), frames=np.int64(T),
+                            feat_checksum=np.float64(feat.double().sum().item()),
+                            semantic_tokens=idx.numpy(), margin=margin.numpy())
+        print("tokenize", name, tuple(idx.shape), "min margin", float(margin.min()))
 
 
 if __name__ == "__main__":
