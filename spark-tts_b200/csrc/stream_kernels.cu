@@ -298,11 +298,6 @@ constexpr int kLnRows = 32;        // output rows per tile
 constexpr int kLnWarpRows = 4;     // consecutive rows per warp (8 warps x 4 = 32)
 constexpr int kLnStages = 3;       // tiles in shared memory
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
-  const int sz = valid ? 16 : 0;   // src-size 0 => 16 zero bytes (the conv's zero padding)
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
-}
-
 template <int NV, bool DW>
 __global__ void __launch_bounds__(256, 1)
 dwconv_ln_kernel(const float* __restrict__ x, int rows, const float* __restrict__ dw_w /* [7][C] */,
