@@ -90,9 +90,15 @@ struct RuCfg {
   static constexpr int kW1Stage = G * kPlanes * (N2 / PG) * 64;    // bytes of a W1 stage in this CTA (chunk stride stays kWChunk)
   // ring depths (227 KB budget)
   static constexpr int SA = (NTERMS == 3) ? 2 : (C <= 96 ? 2 : 3);
-  static constexpr int SR = 3;
+  // Output side of the final stage.  Every 32-column chunk ends with TMA stores (x slab + operand planes) issued by
+  // one thread; the team may run kOutSlots - 2 chunks ahead of the stores' shared-memory reads.  C = 96 has
+  // shared memory to spare, so it gets three staging slots and a fourth residual slab (worth 1-2 %: its limit is
+  // the tensor pipe itself, whose N = 96 MMAs take 56 instead of 48 cycles reading operands from shared memory,
+  // plus ~20 % weight-ring waits).  C = 192 keeps the shared memory for the weight ring.
+  static constexpr int kOutSlots = C <= 96 ? 3 : 2;
+  static constexpr int SR = C <= 96 ? 4 : 3;
   static constexpr int kParBytes = 3 * C * 4;
-  static constexpr int kStageOut = 2 * kPlanes * kRuPlaneTile;      // staging of the operand-plane TMA stores (2 slots)
+  static constexpr int kStageOut = kOutSlots * kPlanes * kRuPlaneTile;   // staging of the operand-plane TMA stores
   static constexpr int kFixed = SA * kAStage + SR * kRuSlabBytes + kStageOut + kParBytes + 1024 /* barriers */ +
                                 1024 /* alignment */;
   static constexpr int SWRaw = (227 * 1024 - kFixed) / kWStage;
@@ -524,8 +530,11 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
     const int ew = (warp - kRuFinWarp0) & 7;    // 0..7 within the final team
     const int half = ew >> 2;                   // which 16 of a chunk's 32 columns this warp drains from TMEM
     const bool storer = warp == kRuFinWarp0 && lane == 0;
-    uint32_t rs = 0, rph = 0, out_ctr = 0;
-    int prev_rs = -1;                           // residual slot whose x store is still reading it
+    constexpr int kPend = Cfg::kOutSlots - 2;   // store groups that may still be reading shared memory at a chunk start
+    uint32_t rs = 0, rph = 0, out_slot = 0;
+    int pend_rs[kPend + 1];                     // residual slots whose x stores may still be reading them (oldest first)
+#pragma unroll
+    for (int i = 0; i <= kPend; ++i) pend_rs[i] = -1;
     auto final_stage = [&](int jt) {
       const int tile = tile_of(jt);
       const int b = tile_b(tile), l0 = tile_l0(tile);
@@ -538,20 +547,20 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
       if (warp == kRuFinWarp0 && lane == 0 && nh == 0) ru_trace(p, jt, 20);
       const uint32_t t_row = tmem_base + ((uint32_t)(group * 32) << 16) + (uint32_t)(NB1 * C) + (u % NB2) * N2;
 #pragma unroll 1
-      for (int cc = 0; cc < N2; cc += 32, ++out_ctr) {
+      for (int cc = 0; cc < N2; cc += 32) {
         const int c = nh * N2 + cc;                // output column of the chunk
         uint32_t r[16];
         tmem_ld_x16(t_row + cc + 16 * half, r);
-        // the stores issued two chunks ago have finished READING shared memory: their staging slot is ours
-        // again and the residual slot they read can be refilled
+        // all but the newest kPend store groups have finished READING shared memory: the oldest pending residual
+        // slot can be refilled, and (after this chunk's barrier) the staging slot of the NEXT chunk is free again
         if (storer) {
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          if (prev_rs >= 0) mbar_arrive(res_empty(prev_rs));
+          asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPend) : "memory");
+          if (pend_rs[0] >= 0) mbar_arrive(res_empty(pend_rs[0]));
         }
         tmem_ld_wait();
         tc_fence_before();
         const uint32_t slab = res_base + rs * kRuSlabBytes;
-        const uint32_t st_hi = out_base + (out_ctr & 1u) * (uint32_t)(Cfg::kPlanes * kRuPlaneTile);
+        const uint32_t st_hi = out_base + out_slot * (uint32_t)(Cfg::kPlanes * kRuPlaneTile);
         const uint32_t st_lo = st_hi + kRuPlaneTile;
         mbar_wait(res_full(rs), rph);
         // the previous chunk's barrier ordered this thread after the storer's wait above (one chunk earlier)
@@ -621,9 +630,12 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
             if (NTERMS == 3) tma_store_3d(&tm_o_lo, st_lo, c, l0, b);
           }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          prev_rs = (int)rs;
+#pragma unroll
+          for (int i = 0; i < kPend; ++i) pend_rs[i] = pend_rs[i + 1];
+          pend_rs[kPend] = (int)rs;
         }
         if (++rs == SR) { rs = 0; rph ^= 1u; }
+        if (++out_slot == (uint32_t)Cfg::kOutSlots) out_slot = 0;
         if (warp == kRuFinWarp0 && lane == 0) ru_trace(p, jt, 21 + c / 32);
       }
       }
