@@ -260,3 +260,16 @@ def test_long_utterance_runs_in_split_passes(cfg, state_dict, dev, model):
     small = BiCodec.from_state_dict(cfg, state_dict, device=dev, workspace_limit_bytes=1 << 30)
     got = small.detokenize(sem.to(dev), glob.to(dev))
     assert torch.equal(ref, got)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_repeated_runs_are_bit_identical(prec, model, cfg, dev):
+    """Race detector: the kernels have no atomics and a fixed reduction order, so the same call must give the same
+    bits every time, whatever the CTA scheduling (persistent tiles, CTA pairs, two epilogue teams)."""
+    from spark_tts_b200.synthetic import synthetic_tokens
+    sem, glob = synthetic_tokens(cfg, 5, 301, 41)
+    sem, glob = sem.to(dev), glob.to(dev)
+    first = model.detokenize(sem, glob, precision=prec).clone()
+    for _ in range(25):
+        again = model.detokenize(sem, glob, precision=prec)
+        assert torch.equal(again, first)
