@@ -639,8 +639,8 @@ static int run_pass(Pass& P, const void* sem, int sem_dt, const void* glob, int 
   const int B = P.B, T = P.T, prec = P.prec;
   const int C = c.vocos_dim, D = c.d_model;
   cudaStream_t st = P.st;
-  const OpBuf pa = mode_op(W.pa, prec), ph = mode_op(W.ph, prec), w_in = mode_op(W.w_in, prec),
-              w_c0 = mode_op(W.w_c0, prec), op2 = mode_op(W.op2, prec);
+  const OpBuf pa = mode_op(W.pa, prec), w_in = mode_op(W.w_in, prec), w_c0 = mode_op(W.w_c0, prec),
+              op2 = mode_op(W.op2, prec);
   const OpBuf op1[2] = {mode_op(W.op1[0], prec), mode_op(W.op1[1], prec)};
 
   if (!x_in) {

@@ -105,21 +105,25 @@ __global__ void vq_zq_kernel(const void* __restrict__ sem, int sem_dtype, size_t
 // Semantic tokenize tail (encode side): z_e = in_project(project(x)) folded into one (cdim x C)
 // map, F.normalize, then the nearest normalised code: argmin_k |c_k|^2 - 2 e.c_k, lowest index on ties
 // (factorized_vector_quantize.py:147-152, 169-187: dist = |e|^2 - 2 e c^T + |c|^2, indices = (-dist).max(1)[1]).
-// One warp owns kVqFrames frames: the lanes split the channels for the projection and the codes for the search
-// (code k = 32 i + lane: coalesced 32 B rows; the 256 KB table stays in L1/L2).  Also returns the margin between
-// the best and second-best score so that callers can tell a real disagreement from a numerical near-tie.
+// One warp owns kVqFrames frames: the lanes split the channels for the projection and the codes for the search.
+// The 8 warps of a CTA walk the table together in kVqChunk-code pieces staged in shared memory (two 16 B planes
+// per code so that consecutive lanes read consecutive 16 B: conflict-free), so every table byte is fetched from
+// L2 once per 64 frames instead of once per 8.  Also returns the margin between the best and second-best score so
+// that callers can tell a real disagreement from a numerical near-tie.
 constexpr int kVqFrames = 8;
 constexpr int kVqDim = 8;
+constexpr int kVqChunk = 512;
 __global__ void __launch_bounds__(256) vq_search_kernel(const float* __restrict__ x, size_t n_frames, int c,
                                                         const float* __restrict__ mat, const float* __restrict__ vec,
                                                         const float* __restrict__ codes_n,
                                                         const float* __restrict__ codes_sq, int codebook_size,
                                                         long long* __restrict__ idx_out,
                                                         float* __restrict__ margin_out) {
+  __shared__ float4 s_c0[kVqChunk], s_c1[kVqChunk];
+  __shared__ float s_sq[kVqChunk];
   const int lane = threadIdx.x & 31;
   const size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
-  const size_t f0 = warp * kVqFrames;
-  if (f0 >= n_frames) return;
+  const size_t f0 = warp * kVqFrames;      // may be >= n_frames in the last CTA: such warps only help with staging
   float e[kVqFrames][kVqDim];
 #pragma unroll
   for (int f = 0; f < kVqFrames; ++f) {
@@ -148,18 +152,27 @@ __global__ void __launch_bounds__(256) vq_search_kernel(const float* __restrict_
   int arg[kVqFrames];
 #pragma unroll
   for (int f = 0; f < kVqFrames; ++f) { best[f] = INFINITY; second[f] = INFINITY; arg[f] = 0x7fffffff; }
-  for (int k = lane; k < codebook_size; k += 32) {
-    const float4 c0 = __ldg(reinterpret_cast<const float4*>(codes_n + (size_t)k * kVqDim));
-    const float4 c1 = __ldg(reinterpret_cast<const float4*>(codes_n + (size_t)k * kVqDim + 4));
-    const float sq = __ldg(codes_sq + k);
+  for (int k0 = 0; k0 < codebook_size; k0 += kVqChunk) {
+    const int nk = min(kVqChunk, codebook_size - k0);
+    __syncthreads();   // the previous chunk has been consumed
+    for (int i = threadIdx.x; i < nk; i += blockDim.x) {
+      s_c0[i] = __ldg(reinterpret_cast<const float4*>(codes_n + (size_t)(k0 + i) * kVqDim));
+      s_c1[i] = __ldg(reinterpret_cast<const float4*>(codes_n + (size_t)(k0 + i) * kVqDim + 4));
+      s_sq[i] = __ldg(codes_sq + k0 + i);
+    }
+    __syncthreads();
+    for (int i = lane; i < nk; i += 32) {   // ascending code index per lane: `<` keeps the lowest index on ties
+      const float4 c0 = s_c0[i], c1 = s_c1[i];
+      const float sq = s_sq[i];
 #pragma unroll
-    for (int f = 0; f < kVqFrames; ++f) {
-      float d = e[f][0] * c0.x;
-      d = fmaf(e[f][1], c0.y, d); d = fmaf(e[f][2], c0.z, d); d = fmaf(e[f][3], c0.w, d);
-      d = fmaf(e[f][4], c1.x, d); d = fmaf(e[f][5], c1.y, d); d = fmaf(e[f][6], c1.z, d); d = fmaf(e[f][7], c1.w, d);
-      const float sc = fmaf(-2.0f, d, sq);
-      if (sc < best[f]) { second[f] = best[f]; best[f] = sc; arg[f] = k; }
-      else second[f] = fminf(second[f], sc);
+      for (int f = 0; f < kVqFrames; ++f) {
+        float d = e[f][0] * c0.x;
+        d = fmaf(e[f][1], c0.y, d); d = fmaf(e[f][2], c0.z, d); d = fmaf(e[f][3], c0.w, d);
+        d = fmaf(e[f][4], c1.x, d); d = fmaf(e[f][5], c1.y, d); d = fmaf(e[f][6], c1.z, d); d = fmaf(e[f][7], c1.w, d);
+        const float sc = fmaf(-2.0f, d, sq);
+        if (sc < best[f]) { second[f] = best[f]; best[f] = sc; arg[f] = k0 + i; }
+        else second[f] = fminf(second[f], sc);
+      }
     }
   }
 #pragma unroll
