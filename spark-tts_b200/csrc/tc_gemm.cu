@@ -353,9 +353,12 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(group * 32) << 16) + acc * BLOCK_N;
-      const int my_last = ((kChunks - 1 - team) & ~1) + team;   // last chunk of this team (may be < 0: no chunk)
+      // chunks alternate between the teams; with an odd chunk count (BLOCK_N = 96: 3) the team that takes two
+      // of them alternates from tile to tile, so both teams drain three chunks per two tiles
+      const int first = (kChunks & 1) ? ((team + (int)iter) & 1) : team;
+      const int my_last = ((kChunks - 1 - first) & ~1) + first;   // last chunk of this team (may be < 0: no chunk)
 #pragma unroll 1
-      for (int ci = team; ci < kChunks; ci += kEpiTeams) {
+      for (int ci = first; ci < kChunks; ci += kEpiTeams) {
         const int c = ci * 32;
         // per-column parameters of this lane's 4 columns: issued first so their latency hides behind the
         // TMEM load, the slab write and the barrier
