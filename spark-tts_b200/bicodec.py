@@ -19,6 +19,43 @@ from .config import BiCodecConfig, load_bicodec_yaml
 _TOKEN_DTYPES = {torch.int32: _lib.I32, torch.int64: _lib.I64}
 
 
+class _GraphedCall:
+    """One captured CUDA graph of ``sparkcodec_detokenize`` for a fixed (batch, frames, precision): static token
+    buffers in, static waveform out, its own workspace (a captured pointer must never be reallocated)."""
+
+    def __init__(self, model: "BiCodec", batch: int, frames: int, prec: int):
+        dev = model._device
+        lib = _lib.load()
+        self.sem = torch.zeros((batch, frames), dtype=torch.int64, device=dev)
+        self.glob = torch.zeros((batch, model.cfg.token_num), dtype=torch.int32, device=dev)
+        self.wav = torch.empty((batch, 1, model.hop * frames), dtype=torch.float32, device=dev)
+        need = C.c_size_t()
+        _lib.check(lib.sparkcodec_workspace_bytes(model._handle, batch, frames, C.byref(need)))
+        self.ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
+
+        def call():
+            _lib.check(lib.sparkcodec_detokenize(
+                model._handle, C.c_void_p(self.sem.data_ptr()), _lib.I64, C.c_void_p(self.glob.data_ptr()), _lib.I32,
+                batch, frames, prec, C.c_void_p(self.ws.data_ptr()), self.ws.numel(),
+                C.c_void_p(self.wav.data_ptr()), model._stream()))
+
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):          # warm-up outside capture (one-time function attributes)
+            call()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            call()
+
+    def run(self, sem: torch.Tensor, glob: torch.Tensor) -> torch.Tensor:
+        self.sem.copy_(sem, non_blocking=True)
+        self.glob.copy_(glob.reshape(self.glob.shape), non_blocking=True)
+        self.graph.replay()
+        return self.wav.clone()                # the caller owns its waveform, like in the reference
+
+
 class BiCodec:
     """B200-native BiCodec vocoder (semantic + global tokens -> waveform)."""
 
@@ -36,6 +73,13 @@ class BiCodec:
         self._device: Optional[torch.device] = None
         self._ws: Optional[torch.Tensor] = None
         self._impl = "tc"
+        # Opt-in CUDA-graph replay for small calls (the CLI's one utterance per call is launch-latency bound: ~80
+        # kernels for a few ms of work).  Calls of at most graph_max_frames token frames are captured once per
+        # (batch, frames, precision) and replayed; at most graph_cache_size shapes are kept.
+        self.use_graphs = False
+        self.graph_max_frames = 4096
+        self.graph_cache_size = 4
+        self._graphs: "Dict[Tuple[int, int, int], _GraphedCall]" = {}
         if device is not None:
             self.to(device)
 
@@ -73,10 +117,12 @@ class BiCodec:
             lib.sparkcodec_destroy(h)
             raise
         self._free()
+        self._graphs = {}
         self._handle, self._device, self._ws = h, device, None
         self.set_impl(self._impl)
 
     def _free(self) -> None:
+        self._graphs = {}
         if self._handle is not None:
             _lib.load().sparkcodec_destroy(self._handle)
             self._handle = None
@@ -177,6 +223,18 @@ class BiCodec:
         sem, glob, B, T = self._tokens(semantic_tokens, global_tokens)
         wav = torch.empty((B, 1, self.hop * T), dtype=torch.float32, device=self._device)
         if B == 0 or T == 0:
+            return wav
+        if self.use_graphs and B * T <= self.graph_max_frames and self._impl == "tc":
+            key = (B, T, self._prec(precision))
+            g = self._graphs.pop(key, None)
+            if g is None:
+                while len(self._graphs) >= self.graph_cache_size:
+                    self._graphs.pop(next(iter(self._graphs)))      # least recently used
+                g = _GraphedCall(self, B, T, key[2])
+            self._graphs[key] = g
+            wav = g.run(sem, glob)
+            if self.validate_tokens:
+                self.check_tokens()
             return wav
         ws, ws_bytes = self._workspace(B, T)
         _lib.check(_lib.load().sparkcodec_detokenize(

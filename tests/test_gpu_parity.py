@@ -273,3 +273,31 @@ def test_repeated_runs_are_bit_identical(prec, model, cfg, dev):
     for _ in range(25):
         again = model.detokenize(sem, glob, precision=prec)
         assert torch.equal(again, first)
+
+
+def test_graph_replay_option_is_bit_identical_and_bounded(cfg, state_dict, dev):
+    """BiCodec.use_graphs: small calls are captured once per shape and replayed; same bits as the eager path, the
+    cache stays bounded, out-of-range ids still raise."""
+    from spark_tts_b200 import BiCodec
+    from spark_tts_b200.synthetic import synthetic_tokens
+    m = BiCodec.from_state_dict(cfg, state_dict, device=dev)
+    shapes = [(1, 37), (2, 50), (1, 129), (3, 16), (1, 64)]
+    eager = {}
+    for i, (B, T) in enumerate(shapes):
+        sem, glob = synthetic_tokens(cfg, B, T, 60 + i)
+        eager[(B, T)] = (sem.to(dev), glob.to(dev), m.detokenize(sem.to(dev), glob.to(dev)).clone())
+    m.use_graphs = True
+    for _ in range(2):                                  # second round replays (and re-captures evicted shapes)
+        for (B, T), (sem, glob, ref) in eager.items():
+            out = m.detokenize(sem.to(torch.int32), glob.to(torch.int64))       # other legal dtypes
+            assert torch.equal(out, ref)
+            assert len(m._graphs) <= m.graph_cache_size
+    big_sem, big_glob = synthetic_tokens(cfg, 9, 500, 70)    # above graph_max_frames: eager path
+    m.detokenize(big_sem.to(dev), big_glob.to(dev))
+    assert (9, 500, 0) not in m._graphs
+    sem, glob, _ = eager[(1, 37)]
+    bad = sem.clone()
+    bad[0, 5] = cfg.codebook_size
+    with pytest.raises(IndexError):
+        m.detokenize(bad, glob)
+    assert torch.equal(m.detokenize(sem, glob), eager[(1, 37)][2])             # and the model is still usable

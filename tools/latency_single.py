@@ -15,7 +15,9 @@ sd = synthetic_state_dict(cfg, 0)
 for prec in ("fp32", "bf16"):
     m = BiCodec.from_state_dict(cfg, sd, device=dev, precision=prec)
     m.validate_tokens = False
-    for B, T in ((1, 50), (1, 500), (1, 1500), (8, 500)):
+    for B, T, graphs in ((1, 50, False), (1, 50, True), (1, 500, False), (1, 500, True), (1, 1500, False),
+                         (1, 1500, True), (8, 500, False), (8, 500, True)):
+        m.use_graphs = graphs
         sem, glob = synthetic_tokens(cfg, B, T, 5)
         sem, glob = sem.to(dev), glob.to(dev)
         for _ in range(10):
@@ -29,5 +31,5 @@ for prec in ("fp32", "bf16"):
             e1.synchronize()
             ts.append(e0.elapsed_time(e1))
         ts.sort()
-        print(f"{prec} B={B} T={T} ({B * T / 50:.0f} s audio): median {ts[25]:.3f} ms  p95 {ts[47]:.3f} ms  "
+        print(f"{prec} {'graph' if graphs else 'eager'} B={B} T={T} ({B * T / 50:.0f} s audio): median {ts[25]:.3f} ms  p95 {ts[47]:.3f} ms  "
               f"-> {B * T / 50 / (ts[25] * 1e-3):.0f} audio-s/s, RTF {ts[25] * 1e-3 / (B * T / 50):.2e}")
