@@ -3,6 +3,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <atomic>
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -103,6 +104,19 @@ int launch_resunit_fused(const GemmWeights& c7, const GemmWeights& c1, const OpB
                          const float* inv_out, OpBuf out, int precision, int num_sms, cudaStream_t stream);
 
 // streaming / token kernels
+// One-time per-DEVICE launch state (function attributes are per context, so a process that drives several GPUs must
+// set them on each; relaxed atomics because two host threads may race to the same value).
+constexpr int kMaxDevices = 64;
+struct PerDevice {
+  std::atomic<int> v[kMaxDevices];
+  PerDevice() { for (auto& x : v) x.store(0, std::memory_order_relaxed); }
+  std::atomic<int>& here() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return v[(d >= 0 && d < kMaxDevices) ? d : 0];
+  }
+};
+
 int launch_split(const float* x, OpBuf out, size_t n, cudaStream_t s);                 // fp32 -> hi/lo
 int launch_merge(const OpBuf& in, float* out, size_t n, cudaStream_t s);               // hi(+lo) -> fp32
 int launch_extract_codes(const void* ids, int id_dtype, int batch, int n_tokens, long long sem_base, int sem_size,

@@ -696,7 +696,8 @@ int launch_ru(const GemmWeights& c7, const GemmWeights& c1, const OpBuf& a, int 
     SC_TRY(encode_tmap(&tw[2 * i + 1], NTERMS == 3 ? gw[i]->w_lo : gw[i]->w_hi, 2, wd, ws, wb, 64, true, false));
   }
   auto kern = resunit_fused_kernel<C, NTERMS, CL, PAIR>;
-  static int max_clusters = 0;   // per instantiation
+  static PerDevice cache;   // per instantiation and device: clusters that fit (0 = not initialised yet)
+  int max_clusters = cache.here().load(std::memory_order_relaxed);
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -715,6 +716,7 @@ int launch_ru(const GemmWeights& c7, const GemmWeights& c1, const OpBuf& a, int 
     } else {
       max_clusters = num_sms;
     }
+    cache.here().store(max_clusters, std::memory_order_relaxed);
   }
   const int groups = (p.num_tiles + CL - 1) / CL;
   const int clusters = std::min(std::min(groups, max_clusters), num_sms / CL);

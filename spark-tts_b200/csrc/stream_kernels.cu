@@ -656,26 +656,26 @@ static int launch_dwconv_ln_t(const float* x, int batch, int rows, const float* 
   const bool dw = dw_w != nullptr;
   const size_t smem = kLnStages * (size_t)(kLnRows + (dw ? 6 : 0)) * NV * 128 * sizeof(float);
   if (smem > 226 * 1024) { set_error("dwconv_ln: %d channels do not fit the shared-memory pipeline", NV * 128); return SPARKCODEC_EINVAL; }
-  static int num_sms = 0;
+  static PerDevice sms, done_dw, done_ln;
+  int num_sms = sms.here().load(std::memory_order_relaxed);
   if (!num_sms) {
     int dev = 0;
     SC_CUDA(cudaGetDevice(&dev));
     SC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    sms.here().store(num_sms, std::memory_order_relaxed);
   }
   const int grid = std::min(total, num_sms);   // one persistent CTA per SM
   if (dw) {
-    static bool done = false;
-    if (!done) {
+    if (!done_dw.here().load(std::memory_order_relaxed)) {
       SC_CUDA(cudaFuncSetAttribute(dwconv_ln_kernel<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      done = true;
+      done_dw.here().store(1, std::memory_order_relaxed);
     }
     dwconv_ln_kernel<NV, true><<<grid, 256, smem, s>>>(x, rows, dw_w, dw_b, scale, shift, ss, eps, out_f32, out_op,
                                                        tiles, total);
   } else {
-    static bool done = false;
-    if (!done) {
+    if (!done_ln.here().load(std::memory_order_relaxed)) {
       SC_CUDA(cudaFuncSetAttribute(dwconv_ln_kernel<NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      done = true;
+      done_ln.here().store(1, std::memory_order_relaxed);
     }
     dwconv_ln_kernel<NV, false><<<grid, 256, smem, s>>>(x, rows, dw_w, dw_b, scale, shift, ss, eps, out_f32, out_op,
                                                         tiles, total);
@@ -701,10 +701,10 @@ static int launch_head_t(const float* x, int batch, int rows, const float* alpha
   const int runs = (rows + kHeadRun - 1) / kHeadRun, total = batch * runs;
   const int grid = (total + kHeadWarps - 1) / kHeadWarps, blk = kHeadWarps * 32;
   const size_t smem = (size_t)kHeadWarps * (kHeadGranRows * kHeadRingGran * NCH * 32 + 32 * 33) * sizeof(float);
-  static bool done = false;
-  if (!done) {
+  static PerDevice done;
+  if (!done.here().load(std::memory_order_relaxed)) {
     SC_CUDA(cudaFuncSetAttribute(head_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    done = true;
+    done.here().store(1, std::memory_order_relaxed);
   }
   head_kernel<NCH><<<grid, blk, smem, s>>>(x, rows, alpha, inv_alpha, w, bias, wav, runs, total);
   SC_LAUNCH_CHECK();

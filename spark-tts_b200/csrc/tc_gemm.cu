@@ -492,7 +492,8 @@ int launch_inst(const GemmWeights& w, const OpBuf& a, int batch, int L, const Co
     else tw_lo = tw_hi;
   }
   auto kern = conv_gemm_tc_kernel<BLOCK_N, BK, NTERMS, RES, HALO, CG>;
-  static int max_clusters = 0;   // per instantiation
+  static PerDevice cache;   // per instantiation and device: clusters that fit (0 = not initialised yet)
+  int max_clusters = cache.here().load(std::memory_order_relaxed);
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -511,6 +512,7 @@ int launch_inst(const GemmWeights& w, const OpBuf& a, int batch, int L, const Co
     } else {
       max_clusters = num_sms;
     }
+    cache.here().store(max_clusters, std::memory_order_relaxed);
   }
   const int supers = ((p.num_m_tiles + CG - 1) / CG) * p.num_n_tiles;
   const int clusters = std::min(std::min(supers, max_clusters), num_sms / CG);
