@@ -89,3 +89,26 @@ def test_token_feed_refuses_cpu_tensors():
     from spark_tts_b200.token_feed import codes_from_token_ids
     with pytest.raises(RuntimeError):
         codes_from_token_ids(torch.zeros((1, 4), dtype=torch.int64), 100, 9000)
+
+
+def test_example_wav_writer_round_trips(tmp_path):
+    """examples/vocode_tokens.py writes what the reference CLI hands to soundfile: 16 kHz mono, here as 16-bit PCM."""
+    import importlib.util
+    import os
+    import wave
+
+    import numpy as np
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("vocode_tokens", os.path.join(root, "examples", "vocode_tokens.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    x = np.sin(np.linspace(0, 40, 3200)).astype(np.float32) * 0.5
+    x[:3] = [1.5, -1.5, 0.0]                       # clipped, not wrapped
+    mod.write_wav(str(tmp_path / "a.wav"), x, 16000)
+    with wave.open(str(tmp_path / "a.wav")) as w:
+        assert (w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()) == (1, 2, 16000, 3200)
+        pcm = np.frombuffer(w.readframes(3200), dtype="<i2")
+    assert pcm[0] == 32767 and pcm[1] == -32767 and pcm[2] == 0
+    assert np.abs(pcm[3:] / 32767.0 - x[3:]).max() < 1e-4
+    with __import__("pytest").raises(SystemExit):
+        mod.main(["--out", str(tmp_path / "b.wav")])      # neither --synthetic nor a model dir
