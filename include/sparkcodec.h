@@ -127,6 +127,20 @@ SPARKCODEC_API int sparkcodec_prenet(sparkcodec_handle* h, const void* semantic,
                       void* workspace, size_t workspace_bytes, float* x_out, void* stream);
 SPARKCODEC_API int sparkcodec_wavegen(sparkcodec_handle* h, const float* x_in, int batch, int frames, int precision,
                        void* workspace, size_t workspace_bytes, float* wav_out, void* stream);
+/* The same WaveGenerator call with its input STAGED in pieces, so that a time-sharded rank can overlap the NCCL
+ * halo exchange with the interior rows: sparkcodec_wavegen_stage converts rows [row_offset, row_offset + rows) of
+ * the (batch, frames_total, d_model) window into the kernels' operand format inside `workspace` (x_rows is
+ * (batch, rows, d_model) fp32 with `src_batch_stride` floats between utterances, so a slice of a wider tensor
+ * needs no copy); the rank stages its own rows while the neighbours' halo rows are in flight, stages the halos when
+ * they have landed, and sparkcodec_wavegen_staged then runs the WaveGenerator over the whole window.  All calls
+ * of one window must pass the same (batch, frames_total, precision, workspace) and the workspace must hold the
+ * whole batch (sparkcodec_workspace_bytes(batch, frames_total)); the result is bit-identical to
+ * sparkcodec_wavegen on the concatenated rows. */
+SPARKCODEC_API int sparkcodec_wavegen_stage(sparkcodec_handle* h, const float* x_rows, int batch, int rows,
+                             int64_t src_batch_stride, int frames_total, int row_offset, int precision,
+                             void* workspace, size_t workspace_bytes, void* stream);
+SPARKCODEC_API int sparkcodec_wavegen_staged(sparkcodec_handle* h, int batch, int frames_total, int precision,
+                              void* workspace, size_t workspace_bytes, float* wav_out, void* stream);
 /* Receptive-field half-widths in token frames: prenet (57 for the released config) and
  * WaveGenerator (conservative ceil; SURVEY.md §8e measured 9.82 frames). */
 SPARKCODEC_API int sparkcodec_halo_frames(sparkcodec_handle* h, int* prenet_halo, int* wavegen_halo);
@@ -143,7 +157,9 @@ SPARKCODEC_API int sparkcodec_check_tokens(sparkcodec_handle* h, void* stream);
  *   token_ids     : device, (batch, n_tokens) generated ids (prompt already trimmed), dtype id_dtype
  *   semantic_out  : device int32 (batch, n_tokens): row b holds semantic_len[b] codes in generation order
  *   global_out    : device int32 (batch, max_global): row b holds min(global_len[b], max_global) codes
- * `*_base` = tokenizer id of "<|bicodec_semantic_0|>" / "<|bicodec_global_0|>".  Stateless, asynchronous. */
+ * `*_base` = tokenizer id of "<|bicodec_semantic_0|>" / "<|bicodec_global_0|>".  Stateless, asynchronous; it has no
+ * handle, so it runs on the CALLER's current CUDA device (the one the pointers and the stream belong to).  Every
+ * entry point that takes a handle switches to the handle's device for the call and restores the caller's. */
 SPARKCODEC_API int sparkcodec_extract_codes(const void* token_ids, int id_dtype, int batch, int n_tokens,
                              int64_t semantic_base, int codebook_size, int64_t global_base, int global_size,
                              int32_t* semantic_out, int32_t* semantic_len, int32_t* global_out, int max_global,

@@ -46,6 +46,10 @@ SIGNATURES = {
                                     C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "sparkcodec_wavegen": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
                                      C.c_void_p, C.c_void_p]),
+    "sparkcodec_wavegen_stage": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                           C.c_void_p, C.c_size_t, C.c_void_p]),
+    "sparkcodec_wavegen_staged": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p,
+                                            C.c_void_p]),
     "sparkcodec_halo_frames": (C.c_int, [_H, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "sparkcodec_check_tokens": (C.c_int, [_H, C.c_void_p]),
     "sparkcodec_extract_codes": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_int,

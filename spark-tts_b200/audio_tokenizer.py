@@ -38,8 +38,21 @@ class BiCodecTokenizer:
         """global (B,32), semantic (B,T) -> float32 numpy (B, hop*T), squeezed like the reference's
         ``wav_rec.detach().squeeze().cpu().numpy()`` (audio_tokenizer.py:144-146)."""
         global_tokens = global_tokens.unsqueeze(1)
-        wav_rec = self.model.detokenize(semantic_tokens, global_tokens)
-        return wav_rec.detach().squeeze().cpu().numpy()
+        m = self.model
+        check, m.validate_tokens = m.validate_tokens, False
+        try:
+            wav_rec = m.detokenize(semantic_tokens, global_tokens)
+        finally:
+            m.validate_tokens = check
+        # D2H through a pinned block of torch's caching host allocator (a pageable .cpu() of a 64 x 10 s batch is a
+        # staged, blocking copy); the caller gets a fresh array that owns the block, like the reference's result
+        host = torch.empty(wav_rec.shape, dtype=torch.float32, pin_memory=True)
+        host.copy_(wav_rec, non_blocking=True)
+        if check:
+            m.check_tokens()                        # one stream sync serves the copy and the id check
+        else:
+            torch.cuda.current_stream(wav_rec.device).synchronize()
+        return host.squeeze().numpy()
 
     def detokenize_pinned(self, global_tokens: torch.Tensor, semantic_tokens: torch.Tensor) -> torch.Tensor:
         """Same call, but host tokens (pinned or pageable) in, reusable pinned host waveform (B, hop*T) out:

@@ -21,14 +21,21 @@ _TOKEN_DTYPES = {torch.int32: _lib.I32, torch.int64: _lib.I64}
 
 class _GraphedCall:
     """One captured CUDA graph of ``sparkcodec_detokenize`` for a fixed (batch, frames, precision): static token
-    buffers in, static waveform out, its own workspace (a captured pointer must never be reallocated)."""
+    buffers in, static waveform out, its OWN workspace (a captured pointer must never be reallocated; the model's
+    shared ``_ws`` is dropped and re-allocated whenever a later call needs more space).  With ``pinned_out`` the
+    device->host copy of the waveform into a pinned buffer is part of the graph (the streaming server's chunk
+    round).  ``generation`` is the model's handle generation at capture time: a graph captured against a handle
+    that has since been destroyed (``.to(other_device)``) points at freed weights and must not be replayed."""
 
-    def __init__(self, model: "BiCodec", batch: int, frames: int, prec: int):
+    def __init__(self, model: "BiCodec", batch: int, frames: int, prec: int, pinned_out: bool = False):
         dev = model._device
         lib = _lib.load()
+        self.generation = model._generation
         self.sem = torch.zeros((batch, frames), dtype=torch.int64, device=dev)
         self.glob = torch.zeros((batch, model.cfg.token_num), dtype=torch.int32, device=dev)
         self.wav = torch.empty((batch, 1, model.hop * frames), dtype=torch.float32, device=dev)
+        self.host = (torch.empty((batch, frames * model.hop), dtype=torch.float32, pin_memory=True)
+                     if pinned_out else None)
         need = C.c_size_t()
         _lib.check(lib.sparkcodec_workspace_bytes(model._handle, batch, frames, C.byref(need)))
         self.ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
@@ -48,11 +55,16 @@ class _GraphedCall:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             call()
+            if self.host is not None:
+                self.host.copy_(self.wav.view(batch, -1), non_blocking=True)
 
-    def run(self, sem: torch.Tensor, glob: torch.Tensor) -> torch.Tensor:
+    def replay(self, sem: torch.Tensor, glob: torch.Tensor) -> None:
         self.sem.copy_(sem, non_blocking=True)
         self.glob.copy_(glob.reshape(self.glob.shape), non_blocking=True)
         self.graph.replay()
+
+    def run(self, sem: torch.Tensor, glob: torch.Tensor) -> torch.Tensor:
+        self.replay(sem, glob)
         return self.wav.clone()                # the caller owns its waveform, like in the reference
 
 
@@ -80,6 +92,9 @@ class BiCodec:
         self.graph_max_frames = 4096
         self.graph_cache_size = 4
         self._graphs: "Dict[Tuple[int, int, int], _GraphedCall]" = {}
+        # bumped whenever the native handle is (re)built or destroyed: holders of captured graphs
+        # (StreamingDetokenizer) compare it with _GraphedCall.generation before every replay
+        self._generation = 0
         if device is not None:
             self.to(device)
 
@@ -118,11 +133,13 @@ class BiCodec:
             raise
         self._free()
         self._graphs = {}
+        self._generation += 1
         self._handle, self._device, self._ws = h, device, None
         self.set_impl(self._impl)
 
     def _free(self) -> None:
         self._graphs = {}
+        self._generation += 1
         if self._handle is not None:
             _lib.load().sparkcodec_destroy(self._handle)
             self._handle = None
@@ -310,6 +327,44 @@ class BiCodec:
         ws, ws_bytes = self._workspace(B, T)
         _lib.check(_lib.load().sparkcodec_wavegen(
             self._handle, C.c_void_p(x.data_ptr()), B, T, self._prec(precision), C.c_void_p(ws), ws_bytes,
+            C.c_void_p(wav.data_ptr()), self._stream()))
+        return wav
+
+    # staged WaveGenerator input: lets a time-sharded rank overlap its halo exchange with the interior rows
+    def can_stage(self, batch: int, frames_total: int) -> bool:
+        """True when one workspace (under ``workspace_limit_bytes``) holds the whole (batch, frames_total) window."""
+        if self._handle is None or batch <= 0 or frames_total <= 0:
+            return False
+        need = C.c_size_t()
+        _lib.check(_lib.load().sparkcodec_workspace_bytes(self._handle, batch, frames_total, C.byref(need)))
+        return need.value <= max(self.workspace_limit_bytes, 1)
+
+    @torch.no_grad()
+    def wavegen_stage(self, x_rows: torch.Tensor, frames_total: int, row_offset: int,
+                      precision: Optional[str] = None) -> None:
+        """Stage rows [row_offset, row_offset + rows) of a (B, frames_total, d_model) WaveGenerator input.  ``x_rows``
+        is (B, rows, d_model) fp32 and may be a time slice of a wider tensor (no copy is made)."""
+        self._ensure(x_rows)
+        D = self.cfg.d_model
+        if x_rows.dim() != 3 or x_rows.shape[2] != D or x_rows.dtype != torch.float32:
+            raise ValueError(f"x_rows must be float32 (B, rows, {D})")
+        B, rows, _ = x_rows.shape
+        if rows == 0:
+            return
+        if x_rows.stride(2) != 1 or x_rows.stride(1) != D or (B > 1 and x_rows.stride(0) < rows * D):
+            x_rows = x_rows.contiguous()
+        ws, ws_bytes = self._workspace(B, frames_total)
+        _lib.check(_lib.load().sparkcodec_wavegen_stage(
+            self._handle, C.c_void_p(x_rows.data_ptr()), B, rows, x_rows.stride(0) if B > 1 else rows * D,
+            frames_total, row_offset, self._prec(precision), C.c_void_p(ws), ws_bytes, self._stream()))
+
+    @torch.no_grad()
+    def wavegen_staged(self, batch: int, frames_total: int, precision: Optional[str] = None) -> torch.Tensor:
+        """Runs the WaveGenerator over the rows staged by ``wavegen_stage`` -> waveform (B, 1, hop*frames_total)."""
+        wav = torch.empty((batch, 1, self.hop * frames_total), dtype=torch.float32, device=self._device)
+        ws, ws_bytes = self._workspace(batch, frames_total)
+        _lib.check(_lib.load().sparkcodec_wavegen_staged(
+            self._handle, batch, frames_total, self._prec(precision), C.c_void_p(ws), ws_bytes,
             C.c_void_p(wav.data_ptr()), self._stream()))
         return wav
 

@@ -57,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if failed:
         raise RuntimeError("nvcc failed building libsparkcodec")
     tmp = LIB + ".tmp"
-    subprocess.check_call([_nvcc(), "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a"])
+    subprocess.check_call([_nvcc(), "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"])
     os.replace(tmp, LIB)
     return LIB
 

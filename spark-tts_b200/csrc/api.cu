@@ -8,6 +8,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges cost a predicted branch when no tool is attached
+
 #include "common.cuh"
 #include "gemm_params.cuh"
 #include "pack.h"
@@ -23,6 +25,36 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+// Every C-ABI entry point that touches the handle's device switches to it for the duration of the call only: the
+// caller's current device is restored on every exit path (a PyTorch process that drives several GPUs keeps its
+// own notion of "current device").
+struct DeviceGuard {
+  int prev = -1, target;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int dev) : target(dev) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0 && prev != target) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define SC_ON_DEVICE(dev)                 \
+  ::sparkcodec::DeviceGuard _dev_guard(dev); \
+  SC_CUDA(_dev_guard.err)
+
+// NVTX range per stage of a pass (token stages, each backbone, conv-in, each up-block, head): what a timeline tool
+// (Nsight Systems, ncu --nvtx) groups the launches by.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  explicit NvtxRange(const std::string& name) { nvtxRangePushA(name.c_str()); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 struct HostTensor {
   std::vector<int64_t> shape;
@@ -581,6 +613,7 @@ static int run_backbone(Pass& P, Backbone& bb, const std::string& name, Workspac
                         int ada_n, float* out_f32, const OpBuf& out_op) {
   const int B = P.B, T = P.T, prec = P.prec, C = P.h->cfg.vocos_dim;
   cudaStream_t st = P.st;
+  NvtxRange range("sparkcodec." + name);
   const OpBuf pa = mode_op(W.pa, prec), ph = mode_op(W.ph, prec);
   Epilogue e;
   e.out_f32 = W.py;
@@ -632,8 +665,9 @@ static int run_tokenize(Pass& P, const float* feat, Workspace& W, long long* idx
 
 // One pass over B utterances of T frames.  x_in != null: skip the token stages + prenet and start the
 // wave generator from x_in (B,T,D) fp32.  x_out != null: stop after prenet(+d) and write it as fp32.
+// staged: the operand planes of x are already in W.w_in (sparkcodec_wavegen_stage): start at the wave generator.
 static int run_pass(Pass& P, const void* sem, int sem_dt, const void* glob, int glob_dt, Workspace& W,
-                    const float* x_in, float* x_out, float* wav_out) {
+                    const float* x_in, float* x_out, float* wav_out, bool staged = false) {
   sparkcodec_handle* h = P.h;
   const sparkcodec_config& c = h->cfg;
   const int B = P.B, T = P.T, prec = P.prec;
@@ -643,15 +677,28 @@ static int run_pass(Pass& P, const void* sem, int sem_dt, const void* glob, int 
               op2 = mode_op(W.op2, prec);
   const OpBuf op1[2] = {mode_op(W.op1[0], prec), mode_op(W.op1[1], prec)};
 
-  if (!x_in) {
+  if (staged) {
+    // nothing to do: W.w_in was filled by sparkcodec_wavegen_stage
+  } else if (!x_in) {
+    NvtxRange range_tok("sparkcodec.token_stages+prenet");
     // ---- speaker tokens -> d_vector, AdaLN scale/shift for all 1 + vocos_num_layers norms ----
     SC_TRY(launch_fsq_project(glob, glob_dt, B, c.token_num, c.fsq_num_levels, h->fsq_levels, h->fsq_wpo, h->fsq_bpo,
                               c.latent_dim, W.flat, h->err_flag, st));
+    if (P.want("fsq_codes")) {   // the index stage by itself: (B, token_num, n_levels) level codes, bit-exact
+      SC_TRY(P.tap_check(c.token_num, c.fsq_num_levels));
+      SC_TRY(launch_fsq_codes(glob, glob_dt, B * c.token_num, c.fsq_num_levels, h->fsq_levels,
+                              P.tap->out + P.tap->b0 * (size_t)c.token_num * c.fsq_num_levels, st));
+    }
     SC_TRY(launch_small_linear(W.flat, h->spk_w, h->spk_b, W.d, B, c.latent_dim * c.token_num, D, st));
     SC_TRY(P.tap_f32("d_vector", W.d, 1, D));
     const int ada_n = h->n_ada * 2 * C;
     SC_TRY(launch_small_linear(W.d, h->ada_w, h->ada_b, W.ada, B, D, ada_n, st));
     // ---- semantic tokens -> 3 * linear_pre(out_project(codebook[idx])) as operand planes ----
+    if (P.want("codebook_rows")) {   // the index stage by itself: (B, T, codebook_dim) gathered rows, bit-exact
+      SC_TRY(P.tap_check(T, c.codebook_dim));
+      SC_TRY(launch_vq_rows(sem, sem_dt, B * T, c.codebook_size, c.codebook_dim, h->codebook,
+                            P.tap->out + P.tap->b0 * (size_t)T * c.codebook_dim, st));
+    }
     if (P.want("z_q")) {
       SC_TRY(P.tap_check(T, D));
       SC_TRY(launch_vq_zq(sem, sem_dt, B * T, c.codebook_size, c.codebook_dim, h->codebook, h->vq_w, h->vq_b, D,
@@ -682,7 +729,9 @@ static int run_pass(Pass& P, const void* sem, int sem_dt, const void* glob, int 
   }
 
   // ---- WaveGenerator ----
+  NvtxRange range_wg("sparkcodec.wavegen");
   {
+    NvtxRange range("sparkcodec.decoder.model.0");
     Epilogue e;
     e.act = ACT_SNAKE; e.alpha = h->s_conv_in.alpha; e.inv_alpha = h->s_conv_in.inv;
     e.out_op = w_c0;
@@ -695,6 +744,7 @@ static int run_pass(Pass& P, const void* sem, int sem_dt, const void* glob, int 
   for (size_t i = 0; i < h->ups.size(); ++i) {
     UpBlock& ub = h->ups[i];
     const std::string name = "decoder.model." + std::to_string(i + 1) + ".block";
+    NvtxRange range("sparkcodec." + name);
     {
       if (cur.hi == op1[pp].hi) pp ^= 1;   // the transposed conv must not write over its own input
       Epilogue e;
@@ -744,6 +794,7 @@ static int run_pass(Pass& P, const void* sem, int sem_dt, const void* glob, int 
     }
     cur = op1[pp];
   }
+  NvtxRange range_head("sparkcodec.head");
   SC_TRY(P.prof_begin("head", 0, (double)B * L * (h->head_c * 4 + 4)));
   SC_TRY(launch_head(W.x, B, L, h->head_c, h->s_head.alpha, h->s_head.inv, h->head_w, h->head_bias, wav_out, 0, L, st));
   SC_TRY(P.prof_end());
@@ -778,7 +829,7 @@ static int run_all(sparkcodec_handle* h, const void* sem, int sem_dt, const void
               workspace_needed(h, 1, frames));
     return SPARKCODEC_ENOMEM;
   }
-  SC_CUDA(cudaSetDevice(h->device));
+  SC_ON_DEVICE(h->device);
   g_launch_counter = &h->launches;
   const sparkcodec_config& c = h->cfg;
   const size_t sem_sz = sem_dt == SPARKCODEC_I64 ? 8 : 4, glob_sz = glob_dt == SPARKCODEC_I64 ? 8 : 4;
@@ -788,6 +839,7 @@ static int run_all(sparkcodec_handle* h, const void* sem, int sem_dt, const void
     Workspace W;
     carve(h, a, B, frames, &W);
     Pass P{h, B, frames, precision, st, tap};
+    NvtxRange range_pass(x_out ? "sparkcodec.prenet_pass" : x_in ? "sparkcodec.wavegen_pass" : "sparkcodec.detokenize_pass");
     if (tap) tap->b0 = b0;
     const char* semp = sem ? static_cast<const char*>(sem) + (size_t)b0 * frames * sem_sz : nullptr;
     const char* globp = glob ? static_cast<const char*>(glob) + (size_t)b0 * c.token_num * glob_sz : nullptr;
@@ -827,7 +879,7 @@ int sparkcodec_create(const sparkcodec_config* cfg, int device, sparkcodec_handl
   int ndev = 0;
   SC_CUDA(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) { set_error("device %d out of range (%d devices)", device, ndev); return SPARKCODEC_EINVAL; }
-  SC_CUDA(cudaSetDevice(device));
+  SC_ON_DEVICE(device);
   cudaDeviceProp prop;
   SC_CUDA(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) {
@@ -844,7 +896,9 @@ int sparkcodec_create(const sparkcodec_config* cfg, int device, sparkcodec_handl
 
 int sparkcodec_destroy(sparkcodec_handle* h) {
   if (!h) return 0;
-  cudaSetDevice(h->device);
+  DeviceGuard guard(h->device);
+  for (auto& r : h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  h->prof.clear();
   for (void* p : h->allocs) cudaFree(p);
   if (g_launch_counter == &h->launches) g_launch_counter = nullptr;
   delete h;
@@ -872,7 +926,7 @@ int sparkcodec_set_tensor(sparkcodec_handle* h, const char* key, const float* da
 int sparkcodec_finalize(sparkcodec_handle* h) {
   if (!h) { set_error("null handle"); return SPARKCODEC_EINVAL; }
   if (h->finalized) return 0;
-  SC_CUDA(cudaSetDevice(h->device));
+  SC_ON_DEVICE(h->device);
   return do_finalize(h);
 }
 
@@ -906,6 +960,51 @@ int sparkcodec_wavegen(sparkcodec_handle* h, const float* x_in, int batch, int f
                  workspace_bytes, x_in, nullptr, wav_out, nullptr, static_cast<cudaStream_t>(stream));
 }
 
+// ---- staged WaveGenerator input (time sharding with the halo exchange overlapped, include/sparkcodec.h) ----
+static int staged_workspace(sparkcodec_handle* h, int batch, int frames_total, int precision, void* workspace,
+                            size_t workspace_bytes, Workspace* W) {
+  SC_TRY(check_common(h, batch, frames_total, precision));
+  if (batch == 0 || frames_total == 0) { set_error("empty staged call"); return SPARKCODEC_EINVAL; }
+  if (!workspace || workspace_needed(h, batch, frames_total) > workspace_bytes) {
+    set_error("staged wavegen needs the whole batch in one pass: workspace of %zu bytes, %zu needed", workspace_bytes,
+              workspace_needed(h, batch, frames_total));
+    return SPARKCODEC_ENOMEM;
+  }
+  Arena a{static_cast<char*>(workspace), 0, workspace_bytes};
+  carve(h, a, batch, frames_total, W);
+  return 0;
+}
+
+int sparkcodec_wavegen_stage(sparkcodec_handle* h, const float* x_rows, int batch, int rows, int64_t src_batch_stride,
+                             int frames_total, int row_offset, int precision, void* workspace, size_t workspace_bytes,
+                             void* stream) {
+  Workspace W;
+  SC_TRY(staged_workspace(h, batch, frames_total, precision, workspace, workspace_bytes, &W));
+  if (rows == 0) return 0;
+  if (!x_rows || rows < 0 || row_offset < 0 || row_offset + rows > frames_total ||
+      src_batch_stride < (int64_t)rows * h->cfg.d_model) {
+    set_error("wavegen_stage: rows [%d, %d) outside the %d-frame window or bad stride", row_offset, row_offset + rows,
+              frames_total);
+    return SPARKCODEC_EINVAL;
+  }
+  SC_ON_DEVICE(h->device);
+  g_launch_counter = &h->launches;
+  return launch_split_rows(x_rows, (size_t)src_batch_stride, mode_op(W.w_in, precision), batch, rows, h->cfg.d_model,
+                           frames_total, row_offset, static_cast<cudaStream_t>(stream));
+}
+
+int sparkcodec_wavegen_staged(sparkcodec_handle* h, int batch, int frames_total, int precision, void* workspace,
+                              size_t workspace_bytes, float* wav_out, void* stream) {
+  Workspace W;
+  SC_TRY(staged_workspace(h, batch, frames_total, precision, workspace, workspace_bytes, &W));
+  if (!wav_out) { set_error("null tensor pointer"); return SPARKCODEC_EINVAL; }
+  SC_ON_DEVICE(h->device);
+  g_launch_counter = &h->launches;
+  Pass P{h, batch, frames_total, precision, static_cast<cudaStream_t>(stream), nullptr};
+  NvtxRange range_pass("sparkcodec.wavegen_staged_pass");
+  return run_pass(P, nullptr, SPARKCODEC_I32, nullptr, SPARKCODEC_I32, W, nullptr, nullptr, wav_out, /*staged=*/true);
+}
+
 int sparkcodec_tokenize_semantic(sparkcodec_handle* h, const float* feat, int batch, int frames, int precision,
                                  void* workspace, size_t workspace_bytes, int64_t* tokens_out, float* margin_out,
                                  void* stream) {
@@ -923,7 +1022,7 @@ int sparkcodec_tokenize_semantic(sparkcodec_handle* h, const float* feat, int ba
               frames, workspace_needed(h, 1, frames));
     return SPARKCODEC_ENOMEM;
   }
-  SC_CUDA(cudaSetDevice(h->device));
+  SC_ON_DEVICE(h->device);
   g_launch_counter = &h->launches;
   for (int b0 = 0; b0 < batch; b0 += per_pass) {
     const int B = std::min(per_pass, batch - b0);
@@ -965,6 +1064,7 @@ int sparkcodec_halo_frames(sparkcodec_handle* h, int* prenet_halo, int* wavegen_
 
 int sparkcodec_check_tokens(sparkcodec_handle* h, void* stream) {
   if (!h || !h->finalized) { set_error("handle not ready"); return SPARKCODEC_ESTATE; }
+  SC_ON_DEVICE(h->device);
   int e[4];
   SC_CUDA(cudaMemcpyAsync(e, h->err_flag, sizeof(e), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
   SC_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
@@ -1011,6 +1111,7 @@ int sparkcodec_detokenize_tap(sparkcodec_handle* h, const void* semantic, int se
 
 int sparkcodec_profile(sparkcodec_handle* h, int enable) {
   if (!h) { set_error("null handle"); return SPARKCODEC_EINVAL; }
+  SC_ON_DEVICE(h->device);
   for (auto& r : h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   h->prof.clear();
   h->profile = enable != 0;
@@ -1019,7 +1120,7 @@ int sparkcodec_profile(sparkcodec_handle* h, int enable) {
 
 int sparkcodec_profile_read(sparkcodec_handle* h, char* buf, size_t cap, size_t* needed) {
   if (!h || !needed) { set_error("null argument"); return SPARKCODEC_EINVAL; }
-  SC_CUDA(cudaSetDevice(h->device));
+  SC_ON_DEVICE(h->device);
   std::string out;
   for (auto& r : h->prof) {
     SC_CUDA(cudaEventSynchronize(r.e1));
@@ -1066,7 +1167,7 @@ int sparkcodec_op_conv(int device, int kind, const float* w_host, const int64_t*
                        int act, const float* alpha_host, int precision, int impl, void* stream) {
   if (!w_host || !wshape || !x_dev || !y_dev) { set_error("null argument"); return SPARKCODEC_EINVAL; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  SC_CUDA(cudaSetDevice(device));
+  SC_ON_DEVICE(device);
   sparkcodec_handle tmp;   // only used as an allocation list
   tmp.device = device;
   cudaDeviceProp prop;

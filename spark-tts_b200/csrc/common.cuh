@@ -119,6 +119,10 @@ struct PerDevice {
 
 int launch_split(const float* x, OpBuf out, size_t n, cudaStream_t s);                 // fp32 -> hi/lo
 int launch_merge(const OpBuf& in, float* out, size_t n, cudaStream_t s);               // hi(+lo) -> fp32
+// rows (batch, rows, c) fp32 with batch stride `src_batch_stride` floats -> planes of a (batch, rows_total, c)
+// tensor at row offset `row_off`
+int launch_split_rows(const float* x, size_t src_batch_stride, OpBuf out, int batch, int rows, int c, int rows_total,
+                      int row_off, cudaStream_t s);
 int launch_extract_codes(const void* ids, int id_dtype, int batch, int n_tokens, long long sem_base, int sem_size,
                          long long glob_base, int glob_size, int* sem_out, int* sem_len, int* glob_out, int max_global,
                          int* glob_len, cudaStream_t s);
@@ -131,6 +135,10 @@ int launch_vq_search(const float* x, size_t n_frames, int c, const float* mat, c
 int launch_vq_zq(const void* sem, int sem_dtype, int n_tok, int codebook_size, int codebook_dim,
                  const float* codebook, const float* w, const float* bias, int d_model, float* out,
                  cudaStream_t s);
+int launch_vq_rows(const void* sem, int sem_dtype, int n_tok, int codebook_size, int codebook_dim,
+                   const float* codebook, float* out, cudaStream_t s);                      // tap: codebook[idx]
+int launch_fsq_codes(const void* glob, int glob_dtype, int n_tok, int n_levels, const int* levels, float* out,
+                     cudaStream_t s);                                                        // tap: FSQ level codes
 int launch_fsq_project(const void* glob, int glob_dtype, int batch, int token_num, int n_levels,
                        const int* levels, const float* w_po, const float* b_po, int latent,
                        float* flat_out, int* err_flag, cudaStream_t s);

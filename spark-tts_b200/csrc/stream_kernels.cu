@@ -36,6 +36,15 @@ __global__ void split_kernel(const float4* __restrict__ x, OpBuf out, size_t n4)
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
     store_op4(out, i * 4, __ldg(x + i));
 }
+__global__ void split_rows_kernel(const float* __restrict__ x, size_t src_batch_stride, OpBuf out, int rows, int c4,
+                                  int rows_total, int row_off, size_t n4) {
+  const size_t per_b = (size_t)rows * c4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / per_b, r = i % per_b;     // r = row * c4 + quad
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + b * src_batch_stride) + r);
+    store_op4(out, ((b * rows_total + row_off) * (size_t)c4 + r) * 4, v);
+  }
+}
 __global__ void merge_kernel(OpBuf in, float* __restrict__ out, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float v = __bfloat162float(in.hi[i]);
@@ -58,6 +67,23 @@ __device__ __forceinline__ void report_bad_token(int* err, int which, size_t pos
   }
 }
 
+// THE codebook gather (factorized_vector_quantize.py:163-164 embed_code = F.embedding(idx, codebook)): pointer to row
+// `id` of the (codebook_size, cdim) table.  vq_embed_kernel (product), vq_zq_kernel and the `codebook_rows` tap all
+// go through this function and through load_token, so the bit-exact tap checks the product's own indexing.
+__device__ __forceinline__ const float* codebook_row(const float* __restrict__ codebook, long long id, int cdim) {
+  return codebook + (size_t)id * cdim;
+}
+// tap: rows[tok, :] = codebook[idx[tok], :]
+__global__ void vq_rows_kernel(const void* __restrict__ sem, int sem_dtype, size_t n_tok, int codebook_size, int cdim,
+                               const float* __restrict__ codebook, float* __restrict__ out) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n_tok * cdim) return;
+  const size_t tok = i / cdim;
+  long long id = load_token(sem, sem_dtype, tok);
+  if (id < 0 || id >= codebook_size) id = 0;
+  out[i] = __ldg(codebook_row(codebook, id, cdim) + (int)(i % cdim));
+}
+
 // x0[tok, c] = mat[c, :] . codebook[idx[tok], :] + vec[c]   (mat/vec fold out_project, linear_pre and
 // the first SamplingBlock's x3: a purely linear chain, factorized_vector_quantize.py:157 ->
 // feat_decoder.py:87 -> samper.py:98).  One thread per (token, 4 channels).
@@ -74,7 +100,7 @@ __global__ void vq_embed_kernel(const void* __restrict__ sem, int sem_dtype, siz
     if (c == 0) report_bad_token(err, 0, tok, id);
     id = 0;
   }
-  const float* e = codebook + (size_t)id * cdim;
+  const float* e = codebook_row(codebook, id, cdim);
   float acc[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -95,7 +121,7 @@ __global__ void vq_zq_kernel(const void* __restrict__ sem, int sem_dtype, size_t
   const int c = (int)(i % d_model);
   long long id = load_token(sem, sem_dtype, tok);
   if (id < 0 || id >= codebook_size) id = 0;
-  const float* e = codebook + (size_t)id * cdim;
+  const float* e = codebook_row(codebook, id, cdim);
   // same association order as a 1x1 conv over 8 input channels: bias added last
   float a = 0.f;
   for (int j = 0; j < cdim; ++j) a = fmaf(__ldg(w + (size_t)c * cdim + j), __ldg(e + j), a);
@@ -198,18 +224,8 @@ __global__ void __launch_bounds__(256) vq_search_kernel(const float* __restrict_
 // FSQ: level_j = (idx / basis_j) % L_j, code_j = (level_j - L_j/2) / (L_j/2)   (exact in fp32)
 // z[c] = W_po[c,:] . code + b_po[c];  flat[b, c*N + n] = z[c]   (finite_scalar_quantization.py:143-162,
 // residual_fsq.py:191-199, speaker_encoder.py:107-111).  One block per (b, n), one thread per c.
-__global__ void fsq_project_kernel(const void* __restrict__ glob, int glob_dtype, int token_num, int n_levels,
-                                   const int* __restrict__ levels, const float* __restrict__ w_po,
-                                   const float* __restrict__ b_po, int latent, float* __restrict__ flat, int* err) {
-  const int bn = blockIdx.x, b = bn / token_num, n = bn % token_num;
-  long long id = load_token(glob, glob_dtype, (size_t)bn);
-  long long total = 1;
-  for (int j = 0; j < n_levels; ++j) total *= levels[j];
-  if (id < 0 || id >= total) {
-    if (threadIdx.x == 0) report_bad_token(err, 1, (size_t)bn, id);
-    id = 0;
-  }
-  float code[8];
+// THE FSQ index decode, shared by the product kernel and the `fsq_codes` tap.
+__device__ __forceinline__ void fsq_decode(long long id, const int* __restrict__ levels, int n_levels, float (&code)[8]) {
   long long basis = 1;
   for (int j = 0; j < n_levels; ++j) {
     const int L = levels[j], half = L / 2;
@@ -217,6 +233,35 @@ __global__ void fsq_project_kernel(const void* __restrict__ glob, int glob_dtype
     code[j] = (float)(level - half) / (float)half;
     basis *= L;
   }
+}
+__device__ __forceinline__ long long fsq_total(const int* __restrict__ levels, int n_levels) {
+  long long total = 1;
+  for (int j = 0; j < n_levels; ++j) total *= levels[j];
+  return total;
+}
+// tap: codes[b, n, j] (residual_fsq.py get_codes_from_indices, one quantizer, scale 1)
+__global__ void fsq_codes_kernel(const void* __restrict__ glob, int glob_dtype, int n_tok, int n_levels,
+                                 const int* __restrict__ levels, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_tok) return;
+  long long id = load_token(glob, glob_dtype, (size_t)i);
+  if (id < 0 || id >= fsq_total(levels, n_levels)) id = 0;
+  float code[8];
+  fsq_decode(id, levels, n_levels, code);
+  for (int j = 0; j < n_levels; ++j) out[(size_t)i * n_levels + j] = code[j];
+}
+
+__global__ void fsq_project_kernel(const void* __restrict__ glob, int glob_dtype, int token_num, int n_levels,
+                                   const int* __restrict__ levels, const float* __restrict__ w_po,
+                                   const float* __restrict__ b_po, int latent, float* __restrict__ flat, int* err) {
+  const int bn = blockIdx.x, b = bn / token_num, n = bn % token_num;
+  long long id = load_token(glob, glob_dtype, (size_t)bn);
+  if (id < 0 || id >= fsq_total(levels, n_levels)) {
+    if (threadIdx.x == 0) report_bad_token(err, 1, (size_t)bn, id);
+    id = 0;
+  }
+  float code[8];
+  fsq_decode(id, levels, n_levels, code);
   for (int c = threadIdx.x; c < latent; c += blockDim.x) {
     float a = 0.f;
     for (int j = 0; j < n_levels; ++j) a = fmaf(__ldg(w_po + c * n_levels + j), code[j], a);
@@ -591,6 +636,16 @@ int launch_split(const float* x, OpBuf out, size_t n, cudaStream_t s) {
   SC_LAUNCH_CHECK();
   return 0;
 }
+int launch_split_rows(const float* x, size_t src_batch_stride, OpBuf out, int batch, int rows, int c, int rows_total,
+                      int row_off, cudaStream_t s) {
+  if (c % 4 || src_batch_stride % 4) { set_error("split_rows: channel count / stride must be multiples of 4"); return SPARKCODEC_EINVAL; }
+  const size_t n4 = (size_t)batch * rows * (c / 4);
+  if (n4 == 0) return 0;
+  const int grid = (int)std::min<size_t>((n4 + 255) / 256, 148 * 16);
+  split_rows_kernel<<<grid, 256, 0, s>>>(x, src_batch_stride, out, rows, c / 4, rows_total, row_off, n4);
+  SC_LAUNCH_CHECK();
+  return 0;
+}
 int launch_merge(const OpBuf& in, float* out, size_t n, cudaStream_t s) {
   const int grid = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
   merge_kernel<<<grid, 256, 0, s>>>(in, out, n);
@@ -619,6 +674,20 @@ int launch_vq_zq(const void* sem, int sem_dtype, int n_tok, int codebook_size, i
   const size_t n = (size_t)n_tok * d_model;
   vq_zq_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(sem, sem_dtype, (size_t)n_tok, codebook_size, codebook_dim,
                                                           codebook, w, bias, d_model, out);
+  SC_LAUNCH_CHECK();
+  return 0;
+}
+int launch_vq_rows(const void* sem, int sem_dtype, int n_tok, int codebook_size, int codebook_dim,
+                   const float* codebook, float* out, cudaStream_t s) {
+  const size_t n = (size_t)n_tok * codebook_dim;
+  vq_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(sem, sem_dtype, (size_t)n_tok, codebook_size, codebook_dim,
+                                                            codebook, out);
+  SC_LAUNCH_CHECK();
+  return 0;
+}
+int launch_fsq_codes(const void* glob, int glob_dtype, int n_tok, int n_levels, const int* levels, float* out,
+                     cudaStream_t s) {
+  fsq_codes_kernel<<<(n_tok + 127) / 128, 128, 0, s>>>(glob, glob_dtype, n_tok, n_levels, levels, out);
   SC_LAUNCH_CHECK();
   return 0;
 }

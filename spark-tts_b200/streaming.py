@@ -10,8 +10,10 @@ flushed at end of stream.  ``cross_fade`` is the client's reconstruction
 
 Many streams are served together: chunks of equal length that are ready at the same time are decoded as
 one batch (the reference's dynamic batcher can only ``torch.cat`` equal-length requests,
-model_repo/vocoder/1/model.py:91-92).  Fixed shapes -- the common (n_streams, 50) first-chunk round --
-are replayed from a CUDA graph: the ~90 kernel launches of a pass cost one graph launch.
+model_repo/vocoder/1/model.py:91-92).  Recurring shapes -- the (n_streams, 50) first-chunk round and the other
+sizes of the deterministic chunk schedule -- are replayed from a CUDA graph (one graph launch instead of ~80
+kernel launches).  Every graph owns its workspace and output buffers (``bicodec._GraphedCall``), the cache is a
+bounded LRU, and one-off shapes (end-of-stream flushes of arbitrary length) run eagerly.
 """
 from __future__ import annotations
 
@@ -79,47 +81,34 @@ def cross_fade(chunks: List[np.ndarray], overlap_samples: int) -> np.ndarray:
     return np.concatenate([out, chunks[-1][-overlap_samples:]]).astype(np.float32)
 
 
-class _GraphedShape:
-    """One CUDA graph per (batch, frames): static token buffers in, static waveform + pinned copy out."""
-
-    def __init__(self, model, batch: int, frames: int):
-        dev = model.device
-        cfg = model.cfg
-        self.sem = torch.zeros((batch, frames), dtype=torch.int64, device=dev)
-        self.glob = torch.zeros((batch, 1, cfg.token_num), dtype=torch.int32, device=dev)
-        self.host = torch.empty((batch, frames * cfg.hop), dtype=torch.float32, pin_memory=True)
-        check, model.validate_tokens = model.validate_tokens, False
-        try:
-            side = torch.cuda.Stream(dev)
-            side.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(side):      # warm-up outside capture (workspace, function attributes)
-                for _ in range(2):
-                    model.detokenize(self.sem, self.glob)
-            torch.cuda.current_stream(dev).wait_stream(side)
-            torch.cuda.synchronize(dev)
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
-                self.wav = model.detokenize(self.sem, self.glob)
-                self.host.copy_(self.wav.view(batch, -1), non_blocking=True)
-        finally:
-            model.validate_tokens = check
-
-    def run(self, sem: torch.Tensor, glob: torch.Tensor) -> torch.Tensor:
-        self.sem.copy_(sem, non_blocking=True)
-        self.glob.copy_(glob.view(self.glob.shape), non_blocking=True)
-        self.graph.replay()
-        return self.host
+def schedule_sizes(policy: ChunkPolicy) -> List[int]:
+    """The chunk lengths the growth rule can produce (50, 400, 1500 with the reference's run.sh values)."""
+    out, size = [], policy.first_chunk
+    while size not in out:
+        out.append(size)
+        size = min(policy.max_chunk, int(size * policy.scale))
+    return out
 
 
 class StreamingDetokenizer:
     def __init__(self, model, policy: Optional[ChunkPolicy] = None, use_graphs: bool = True,
-                 graph_min_batch: int = 8):
+                 graph_min_batch: int = 8, graph_cache_size: int = 6, graph_after: int = 3,
+                 graph_max_frames: int = 32768):
+        """``use_graphs``: shapes (B >= graph_min_batch, B*T <= graph_max_frames) are captured when T is one of the
+        schedule's chunk sizes, or once the same (B, T) has been seen ``graph_after`` times; at most
+        ``graph_cache_size`` graphs (each with a private workspace + pinned output) are kept, least recently used
+        evicted first."""
         self.model = model
         self.policy = policy or ChunkPolicy(frame_rate=model.cfg.frame_rate)
         self.use_graphs = use_graphs
         self.graph_min_batch = graph_min_batch
+        self.graph_cache_size = graph_cache_size
+        self.graph_after = graph_after
+        self.graph_max_frames = graph_max_frames
         self.streams: Dict[int, _Stream] = {}
-        self._graphs: Dict[Tuple[int, int], _GraphedShape] = {}
+        self._graphs: "Dict[Tuple[int, int, int], object]" = {}     # insertion order = recency (LRU at the front)
+        self._seen: Dict[Tuple[int, int], int] = {}
+        self._sched = set(schedule_sizes(self.policy))
 
     # ---- stream management ----
     def open(self, stream_id: int, global_tokens: torch.Tensor) -> None:
@@ -160,17 +149,38 @@ class StreamingDetokenizer:
             del self.streams[sid]
         return out
 
+    def _graph_for(self, B: int, T: int):
+        """The captured graph of shape (B, T) if the policy wants one, else None (eager)."""
+        from .bicodec import _GraphedCall
+        model = self.model
+        if not self.use_graphs or B < self.graph_min_batch or B * T > self.graph_max_frames:
+            return None
+        key = (B, T, model._prec(None))
+        g = self._graphs.pop(key, None)
+        if g is not None and g.generation != model._generation:
+            g = None                                   # captured against a handle that no longer exists
+            self._graphs = {k: v for k, v in self._graphs.items() if v.generation == model._generation}
+        if g is None:
+            n = self._seen[(B, T)] = self._seen.get((B, T), 0) + 1
+            if len(self._seen) > 4096:
+                self._seen.clear()
+            if T not in self._sched and n < self.graph_after:
+                return None
+            while len(self._graphs) >= max(self.graph_cache_size, 1):
+                self._graphs.pop(next(iter(self._graphs)))          # least recently used
+            g = _GraphedCall(model, B, T, key[2], pinned_out=True)
+        self._graphs[key] = g                                        # most recently used at the back
+        return g
+
     def decode_batch(self, sem: torch.Tensor, glob: torch.Tensor) -> torch.Tensor:
         """(B,T) host/device tokens + (B,N) globals -> pinned host waveform (B, hop*T); one sync."""
         model, dev = self.model, self.model.device
         B, T = sem.shape
-        key = (B, T)
-        if self.use_graphs and B >= self.graph_min_batch:
-            if key not in self._graphs:
-                self._graphs[key] = _GraphedShape(model, B, T)
-            host = self._graphs[key].run(sem.to(dev, non_blocking=True), glob.to(dev, non_blocking=True))
+        g = self._graph_for(B, T)
+        if g is not None:
+            g.replay(sem.to(dev, non_blocking=True), glob.to(dev, non_blocking=True))
             torch.cuda.current_stream(dev).synchronize()
-            return host
+            return g.host
         check, model.validate_tokens = model.validate_tokens, False
         try:
             wav = model.detokenize(sem.to(dev, non_blocking=True), glob.to(dev, non_blocking=True).unsqueeze(1))

@@ -63,6 +63,38 @@ def test_matches_reference_golden(path, model, dev):
     _check(torch.from_numpy(g["prenet_plus_d_first8"]), x.cpu()[:, :8].transpose(1, 2).contiguous(), 1e-3, 80.0)
 
 
+@pytest.mark.parametrize("path", golden_cases(), ids=lambda p: p.split("detok_")[-1][:-4])
+def test_index_stages_are_bit_exact_vs_reference_golden(path, model, dev):
+    """north_star: "codebook and FSQ indexing bit-exact".  The gathered codebook rows (B,T,8)
+    (factorized_vector_quantize.py:163-164) and the FSQ level codes (B,32,6)
+    (finite_scalar_quantization.py:143-162) come out of the same device functions the product kernels use and
+    must equal the reference's tensors bit for bit."""
+    g = np.load(path)
+    sem = torch.from_numpy(g["semantic_tokens"]).to(dev)
+    glob = torch.from_numpy(g["global_tokens"]).to(dev)
+    _, rows = model.detokenize_tap(sem, glob, "codebook_rows")
+    assert rows.dtype == torch.float32 and np.array_equal(rows.cpu().numpy(), g["codebook_rows"])
+    _, codes = model.detokenize_tap(sem, glob, "fsq_codes")
+    assert codes.dtype == torch.float32 and np.array_equal(codes.cpu().numpy(), g["fsq_codes"])
+
+
+@pytest.mark.parametrize("sdt,gdt", [(torch.int64, torch.int32), (torch.int32, torch.int64)])
+def test_index_stages_are_bit_exact_vs_oracle_at_size(sdt, gdt, model, cfg, state_dict, dev):
+    """Same check on 8 x 500 random tokens (every dtype combination the callers use), vs the oracle's gather / decode;
+    includes the extreme ids 0 and size-1."""
+    from oracle import bicodec_oracle as O
+    from spark_tts_b200.synthetic import synthetic_tokens
+    sem, glob = synthetic_tokens(cfg, 8, 500, 555)
+    sem[0, 0], sem[0, 1] = 0, cfg.codebook_size - 1
+    glob[0, 0, 0], glob[0, 0, 1] = 0, 4 ** len(cfg.fsq_levels) - 1
+    rows_ref = torch.nn.functional.embedding(sem.long(), state_dict["quantizer.codebook.weight"])
+    codes_ref = O.fsq_codes(glob.long().transpose(1, 2).squeeze(-1), cfg.fsq_levels)
+    semd, globd = sem.to(dev, sdt), glob.to(dev, gdt)
+    _, rows = model.detokenize_tap(semd, globd, "codebook_rows")
+    _, codes = model.detokenize_tap(semd, globd, "fsq_codes")
+    assert torch.equal(rows.cpu(), rows_ref) and torch.equal(codes.cpu(), codes_ref.float())
+
+
 @pytest.mark.parametrize("B,T,seed", [(1, 1, 7), (3, 2, 8), (1, 7, 1), (2, 127, 2), (2, 128, 3), (1, 129, 4), (5, 33, 5),
                                       (1, 500, 6)])
 def test_matches_oracle(B, T, seed, model, cfg, state_dict, dev):
@@ -301,3 +333,63 @@ def test_graph_replay_option_is_bit_identical_and_bounded(cfg, state_dict, dev):
     with pytest.raises(IndexError):
         m.detokenize(bad, glob)
     assert torch.equal(m.detokenize(sem, glob), eager[(1, 37)][2])             # and the model is still usable
+
+
+def test_config3_shape_matches_oracle(model, cfg, state_dict, dev):
+    """BASELINE config 3's per-utterance shape (30 s = 1500 frames) against the oracle itself, fp32 and bf16."""
+    from oracle import bicodec_oracle as O
+    from spark_tts_b200.synthetic import synthetic_tokens
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    sem, glob = synthetic_tokens(cfg, 2, 1500, 3003)
+    ref = O.detokenize(state_dict, cfg, sem, glob)
+    _check(ref, model.detokenize(sem.to(dev), glob.to(dev), precision="fp32").cpu(), FP32_MAX_ABS, FP32_SNR)
+    _check(ref, model.detokenize(sem.to(dev), glob.to(dev), precision="bf16").cpu(), BF16_MAX_ABS, BF16_SNR)
+
+
+def test_bf16_mode_at_config_shapes(model, cfg, state_dict, dev):
+    """bf16 mode at 1 x 500 (config 1/2 shape) against its stated bound (the goldens only reach T = 130)."""
+    from oracle import bicodec_oracle as O
+    from spark_tts_b200.synthetic import synthetic_tokens
+    sem, glob = synthetic_tokens(cfg, 1, 500, 3004)
+    ref = O.detokenize(state_dict, cfg, sem, glob)
+    _check(ref, model.detokenize(sem.to(dev), glob.to(dev), precision="bf16").cpu(), BF16_MAX_ABS, BF16_SNR)
+
+
+@pytest.mark.parametrize("exchange", [True, False])
+def test_config5_long_form_windows_on_one_gpu(exchange, model, cfg, state_dict, dev):
+    """BASELINE config 5's logic on the CUDA path: one 120 s utterance (6000 frames) decoded as 8 time windows of
+    750 frames through prenet / staged wavegen + halo rows (exactly what 8 ranks do, run by one process) must equal
+    the un-sharded decode, and both must match the oracle."""
+    from oracle import bicodec_oracle as O
+    from spark_tts_b200 import sharding
+    from spark_tts_b200.synthetic import synthetic_tokens
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    sem, glob = synthetic_tokens(cfg, 1, 6000, 5005)
+    semd, globd = sem.to(dev), glob.to(dev)
+    whole = model.detokenize(semd, globd)
+    n0 = model.launch_count()
+    win = sharding.detokenize_time_windows(model, semd, globd, 8, exchange=exchange)
+    assert model.launch_count() > n0
+    assert win.shape == whole.shape == (1, 1, 6000 * cfg.hop)
+    # the kernels are tile-position invariant and rows inside a window's halo are discarded
+    assert (win - whole).abs().max().item() <= 2e-6
+    if exchange:
+        ref = O.detokenize(state_dict, cfg, sem, glob)
+        _check(ref, win.cpu(), FP32_MAX_ABS, FP32_SNR)
+        _check(ref, whole.cpu(), FP32_MAX_ABS, FP32_SNR)
+
+
+def test_staged_wavegen_equals_wavegen(model, cfg, dev):
+    """sparkcodec_wavegen_stage x3 + sparkcodec_wavegen_staged == sparkcodec_wavegen on the concatenated rows (bits),
+    also when the pieces are slices of a wider tensor."""
+    from spark_tts_b200.synthetic import synthetic_tokens
+    sem, glob = synthetic_tokens(cfg, 3, 90, 5006)
+    x = model.prenet(sem.to(dev), glob.to(dev))                       # (3, 90, 1024)
+    ref = model.wavegen(x[:, 10:80].contiguous())
+    model.wavegen_stage(x[:, 21:69], 70, 11)                           # interior first (a strided slice)
+    model.wavegen_stage(x[:, 10:21].contiguous(), 70, 0)
+    model.wavegen_stage(x[:, 69:80], 70, 59)
+    got = model.wavegen_staged(3, 70)
+    assert torch.equal(ref, got)
+    with pytest.raises(ValueError):
+        model.wavegen_stage(x[:, :30], 20, 0)

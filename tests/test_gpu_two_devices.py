@@ -26,3 +26,26 @@ def test_two_handles_on_two_devices_agree(cfg, state_dict):
     m0.to(d1)                                                          # nn.Module-style move: handle rebuilt on cuda:1
     assert m0.device == d1
     assert torch.equal(m0.detokenize(sem.to(d1), glob.to(d1)).cpu(), a)
+
+
+def test_calls_restore_the_callers_current_device(cfg, state_dict):
+    """every C-ABI entry point switches to the handle's device for the call only."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    from spark_tts_b200 import BiCodec
+    from spark_tts_b200.synthetic import synthetic_tokens
+    d1 = torch.device("cuda:1")
+    torch.cuda.set_device(0)
+    m1 = BiCodec.from_state_dict(cfg, state_dict, device=d1)          # create + finalize on cuda:1
+    assert torch.cuda.current_device() == 0
+    sem, glob = synthetic_tokens(cfg, 2, 30, 92)
+    m1.detokenize(sem.to(d1), glob.to(d1))                             # detokenize + check_tokens
+    assert torch.cuda.current_device() == 0
+    m1.prenet(sem.to(d1), glob.to(d1))
+    m1.profile(True); m1.detokenize(sem.to(d1), glob.to(d1)); m1.profile_read(); m1.profile(False)
+    assert torch.cuda.current_device() == 0
+    assert torch.empty(1, device="cuda").device.index == 0
+    del m1                                                             # destroy
+    import gc
+    gc.collect()
+    assert torch.cuda.current_device() == 0

@@ -37,6 +37,33 @@ class OracleBackend:
             return O.wave_generator(self.sd, x.transpose(1, 2), self.cfg.rates, self.cfg.kernel_sizes)
 
 
+class StagedOracleBackend(OracleBackend):
+    """Adds the staged-input surface of the native BiCodec (can_stage / wavegen_stage / wavegen_staged), so the
+    interior-first ordering of spark_tts_b200.sharding is exercised on CPU too."""
+
+    def __init__(self, cfg, sd):
+        super().__init__(cfg, sd)
+        self.buf, self.filled, self.log = None, None, []
+
+    def can_stage(self, batch, frames_total):
+        return True
+
+    def wavegen_stage(self, x_rows, frames_total, row_offset):
+        B, rows, D = x_rows.shape
+        if self.buf is None or self.buf.shape != (B, frames_total, D):
+            self.buf = torch.full((B, frames_total, D), float("nan"))
+            self.filled = torch.zeros(frames_total, dtype=torch.bool)
+        assert not self.filled[row_offset:row_offset + rows].any(), "rows staged twice"
+        self.buf[:, row_offset:row_offset + rows] = x_rows
+        self.filled[row_offset:row_offset + rows] = True
+        self.log.append((row_offset, rows))
+
+    def wavegen_staged(self, batch, frames_total):
+        assert self.buf.shape[:2] == (batch, frames_total) and bool(self.filled.all()), "window not fully staged"
+        x, self.buf, self.filled = self.buf, None, None
+        return self.wavegen(x)
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -52,7 +79,8 @@ def _worker(rank, world, port, mode, out_dir):
         from spark_tts_b200.config import BiCodecConfig
         from spark_tts_b200.synthetic import synthetic_state_dict, synthetic_tokens
         cfg = BiCodecConfig()
-        model = OracleBackend(cfg, synthetic_state_dict(cfg, 0))
+        staged = mode == "time_exchange_staged"
+        model = (StagedOracleBackend if staged else OracleBackend)(cfg, synthetic_state_dict(cfg, 0))
         if mode == "utterance":
             sem, glob = synthetic_tokens(cfg, 3, 12, 21)
             full, rng = sharding.detokenize_utterance_sharded(model, sem, glob, gather=True)
@@ -63,8 +91,10 @@ def _worker(rank, world, port, mode, out_dir):
                 torch.save(dict(wav=full, sem=sem, glob=glob), os.path.join(out_dir, "out.pt"))
         else:
             sem, glob = synthetic_tokens(cfg, 1, 150, 22)
-            wav, (a, b) = sharding.detokenize_time_sharded(model, sem, glob, exchange=(mode == "time_exchange"))
+            wav, (a, b) = sharding.detokenize_time_sharded(model, sem, glob, exchange=mode.startswith("time_exchange"))
             assert wav.shape == (1, 1, (b - a) * cfg.hop)
+            if staged:   # the own (interior) rows were staged BEFORE the halo that arrived over the wire
+                assert model.log[0][1] == b - a and len(model.log) == 2 and model.log[1][1] == 11
             gathered = [None] * world
             dist.all_gather_object(gathered, (a, b, wav))
             if rank == 0:
@@ -76,7 +106,7 @@ def _worker(rank, world, port, mode, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["utterance", "time_exchange", "time_recompute"])
+@pytest.mark.parametrize("mode", ["utterance", "time_exchange", "time_exchange_staged", "time_recompute"])
 def test_two_rank_sharding_matches_unsharded(mode, tmp_path, cfg, state_dict):
     from oracle import bicodec_oracle as O
     mp.spawn(_worker, args=(2, _free_port(), mode, str(tmp_path)), nprocs=2, join=True)
@@ -86,6 +116,24 @@ def test_two_rank_sharding_matches_unsharded(mode, tmp_path, cfg, state_dict):
     # same fp32 ATen ops on a different window: only oneDNN blocking round-off differs
     assert O.snr_db(ref, out["wav"]) > 95.0
     assert (ref - out["wav"]).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("backend", [OracleBackend, StagedOracleBackend])
+@pytest.mark.parametrize("exchange", [True, False])
+def test_single_process_time_windows_match_unsharded(backend, exchange, cfg, state_dict):
+    """detokenize_time_windows = the N-rank time-sharded schedule run by one process (long-form on one GPU)."""
+    from oracle import bicodec_oracle as O
+    from spark_tts_b200 import sharding
+    from spark_tts_b200.synthetic import synthetic_tokens
+    torch.set_num_threads(8)
+    sem, glob = synthetic_tokens(cfg, 2, 100, 23)
+    model = backend(cfg, state_dict)
+    got = sharding.detokenize_time_windows(model, sem, glob, 3, exchange=exchange)
+    ref = O.detokenize(state_dict, cfg, sem, glob)
+    assert got.shape == ref.shape
+    assert O.snr_db(ref, got) > 95.0 and (ref - got).abs().max().item() < 1e-4
+    with pytest.raises(ValueError):
+        sharding.detokenize_time_windows(model, sem[:, :20], glob, 3)          # windows shorter than the halo
 
 
 def test_shard_bounds_cover_everything():

@@ -5,7 +5,7 @@ import math
 import numpy as np
 import pytest
 
-from spark_tts_b200.streaming import ChunkPolicy, chunk_schedule, cross_fade
+from spark_tts_b200.streaming import ChunkPolicy, chunk_schedule, cross_fade, schedule_sizes
 
 
 def _reference_chunks(n_tokens, frame_rate=50, dur=1.0, max_dur=30.0, scale=8.0, ov=0.1):
@@ -35,6 +35,12 @@ def test_chunk_schedule_matches_reference_loop(n):
 def test_policy_defaults_are_run_sh_values():
     p = ChunkPolicy()
     assert (p.first_chunk, p.overlap, p.max_chunk) == (50, 5, 1500)
+
+
+def test_schedule_sizes_are_the_only_graphed_chunk_lengths():
+    """The growth rule 50 -> 400 -> 1500 (x8, capped at 30 s): the shapes the streaming server captures as graphs."""
+    assert schedule_sizes(ChunkPolicy()) == [50, 400, 1500]
+    assert schedule_sizes(ChunkPolicy(scale=1.0)) == [50]
 
 
 def test_cross_fade_reconstruction():
