@@ -173,13 +173,40 @@ SPARKCODEC_API int sparkcodec_extract_codes(const void* token_ids, int id_dtype,
  *   tokens_out  : device int64 (batch, frames): index of the nearest L2-normalised code, lowest index on ties
  *   margin_out  : optional device fp32 (batch, frames): second-best minus best distance, so a caller can tell
  *                 a numerical near-tie from a disagreement (NULL to skip)
- * Uses the same workspace as sparkcodec_detokenize(batch, frames).  The speaker half (mel -> ECAPA -> FSQ
- * global tokens) is not part of this library. */
+ * Uses the same workspace as sparkcodec_detokenize(batch, frames).  (The speaker half is
+ * sparkcodec_tokenize_speaker below.) */
 SPARKCODEC_API int sparkcodec_tokenize_semantic(sparkcodec_handle* h, const float* feat, int batch, int frames,
                                  int precision, void* workspace, size_t workspace_bytes, int64_t* tokens_out,
                                  float* margin_out, void* stream);
 
+/* Speaker half of BiCodec.tokenize (sparktts/models/bicodec.py:162-167: mel = mel_transformer(ref_wav);
+ * global_tokens = speaker_encoder.tokenize(mel^T); speaker/speaker_encoder.py:100-105 = ECAPA-TDNN latent
+ * (speaker/ecapa_tdnn.py:196-208) -> perceiver resampler (speaker/perceiver_encoder.py:335-350) -> ResidualFSQ indices
+ * (fsq/residual_fsq.py:213-283)).  Available only when the checkpoint carried `speaker_encoder.speaker_encoder.*`,
+ * `speaker_encoder.perceiver_sampler.*` and `speaker_encoder.quantizer.project_in.*` (else SPARKCODEC_ESTATE).
+ *   ref_wav     : device, (batch, n_samples) fp32 -- the reference clip (BiCodecTokenizer.get_ref_clip: 6 s at 16 kHz)
+ *   tokens_out  : device int32 (batch, token_num) [== the reference's (B, 1, token_num)], ids in [0, prod(fsq_levels))
+ *   margin_out  : optional device fp32 (batch, token_num): distance of the closest pre-rounding FSQ coordinate to a
+ *                 rounding boundary, so a caller can tell a numerical near-tie from a disagreement (NULL to skip)
+ * The mel transform is torchaudio's MelSpectrogram as bicodec.py:191-211 builds it (power 1, slaney scale and norm,
+ * centred reflect-padded STFT, periodic Hann window); its parameters default to the released config.yaml
+ * `mel_params` (16 kHz, n_fft 1024, win 640, hop 320, 128 mels, 10 Hz .. Nyquist) and can be set BEFORE finalize
+ * with sparkcodec_set_mel_params (f_max < 0 = Nyquist).  Everything runs in fp32 FMA arithmetic. */
+SPARKCODEC_API int sparkcodec_set_mel_params(sparkcodec_handle* h, int sample_rate, int n_fft, int win_length,
+                              int hop_length, int n_mels, float f_min, float f_max);
+SPARKCODEC_API int sparkcodec_speaker_workspace_bytes(sparkcodec_handle* h, int batch, int n_samples, size_t* bytes);
+SPARKCODEC_API int sparkcodec_tokenize_speaker(sparkcodec_handle* h, const float* ref_wav, int batch, int n_samples,
+                                void* workspace, size_t workspace_bytes, int32_t* tokens_out, float* margin_out,
+                                void* stream);
+
 /* ---- test / profiling hooks (not needed by a drop-in user) --------------------------------- */
+
+/* sparkcodec_tokenize_speaker that also copies an intermediate ("mel" (T, n_mels), "ecapa_latent" (T, 1536),
+ * "perceiver" (token_num, latent_dim)) as fp32 (batch, rows, channels) into tap_out. */
+SPARKCODEC_API int sparkcodec_tokenize_speaker_tap(sparkcodec_handle* h, const float* ref_wav, int batch, int n_samples,
+                                    void* workspace, size_t workspace_bytes, int32_t* tokens_out, const char* tap,
+                                    float* tap_out, size_t tap_capacity, int64_t* tap_shape, void* stream);
+
 
 /* Selects tcgen05 (default) or the CUDA-core verification kernels for the dense contractions. */
 SPARKCODEC_API int sparkcodec_set_impl(sparkcodec_handle* h, int impl);

@@ -208,6 +208,161 @@ def tokenize_semantic(sd, cfg, feat: torch.Tensor):
     return vq_tokenize(sd, feat_encoder(sd, feat, len(cfg.sample_ratios)))
 
 
+# ---------------------------------------------------------------------------------------------
+# Encode side, speaker half: BiCodec.tokenize's
+# `speaker_encoder.tokenize(mel_transformer(ref_wav).squeeze(1).transpose(1, 2))`
+# ---------------------------------------------------------------------------------------------
+def _hz_to_mel_slaney(f):
+    """torchaudio.functional._hz_to_mel(mel_scale="slaney")."""
+    import math
+    f_sp = 200.0 / 3
+    min_log_hz, logstep = 1000.0, math.log(6.4) / 27.0
+    min_log_mel = min_log_hz / f_sp
+    return min_log_mel + math.log(f / min_log_hz) / logstep if f >= min_log_hz else f / f_sp
+
+
+def mel_filterbank(n_freqs: int, f_min: float, f_max: float, n_mels: int, sample_rate: int) -> torch.Tensor:
+    """torchaudio.functional.melscale_fbanks(norm="slaney", mel_scale="slaney"): (n_freqs, n_mels) triangular filters,
+    area-normalised.  (The reference builds it with torchaudio.transforms.MelSpectrogram, bicodec.py:191-211.)"""
+    import math
+    all_freqs = torch.linspace(0, sample_rate // 2, n_freqs)
+    m_pts = torch.linspace(_hz_to_mel_slaney(f_min), _hz_to_mel_slaney(f_max), n_mels + 2)
+    f_sp = 200.0 / 3
+    min_log_hz, logstep = 1000.0, math.log(6.4) / 27.0
+    min_log_mel = min_log_hz / f_sp
+    f_pts = f_sp * m_pts
+    log_t = m_pts >= min_log_mel
+    f_pts[log_t] = min_log_hz * torch.exp(logstep * (m_pts[log_t] - min_log_mel))
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts.unsqueeze(0) - all_freqs.unsqueeze(1)
+    down = (-1.0 * slopes[:, :-2]) / f_diff[:-1]
+    up = slopes[:, 2:] / f_diff[1:]
+    fb = torch.max(torch.zeros(1), torch.min(down, up))
+    enorm = 2.0 / (f_pts[2:n_mels + 2] - f_pts[:n_mels])
+    return fb * enorm.unsqueeze(0)
+
+
+def mel_spectrogram(wav: torch.Tensor, cfg) -> torch.Tensor:
+    """TT.MelSpectrogram(sample_rate, n_fft, win_length, hop_length, f_min, f_max, n_mels, power=1, norm="slaney",
+    mel_scale="slaney") as BiCodec.init_mel_transformer builds it (bicodec.py:191-211): centred reflect-padded STFT
+    with a periodic Hann window of win_length (zero-padded to n_fft by torch.stft), magnitude, mel filterbank.
+    wav (B, n) -> (B, n_mels, 1 + n // hop)."""
+    win = torch.hann_window(cfg.mel_win_length, periodic=True, dtype=torch.float32)
+    spec = torch.stft(wav, cfg.mel_n_fft, hop_length=cfg.mel_hop_length, win_length=cfg.mel_win_length, window=win,
+                      center=True, pad_mode="reflect", normalized=False, onesided=True, return_complex=True).abs()
+    f_max = cfg.mel_fmax if cfg.mel_fmax is not None else float(cfg.sample_rate // 2)
+    fb = mel_filterbank(cfg.mel_n_fft // 2 + 1, cfg.mel_fmin, f_max, cfg.num_mels, cfg.sample_rate)
+    return torch.matmul(spec.transpose(-1, -2), fb).transpose(-1, -2)
+
+
+def _bn(sd, p, x):
+    """nn.BatchNorm1d in eval mode on (B, C, T)."""
+    return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"],
+                        False, 0.0, 1e-5)
+
+
+def _conv_relu_bn(sd, p, x, padding=0, dilation=1):
+    """Conv1dReluBn (ecapa_tdnn.py:89-113): bn(relu(conv(x)))."""
+    return _bn(sd, p + ".bn", F.relu(F.conv1d(x, sd[p + ".conv.weight"], sd[p + ".conv.bias"], padding=padding,
+                                             dilation=dilation)))
+
+
+def _se_res2block(sd, p, x, dilation: int, scale: int = 8):
+    """SE_Res2Block (ecapa_tdnn.py:135-149) = x + SE(Conv1dReluBn(Res2Conv1dReluBn(Conv1dReluBn(x))))."""
+    y = _conv_relu_bn(sd, p + ".se_res2block.0", x)
+    width = y.shape[1] // scale
+    spx = torch.split(y, width, 1)
+    out, sp = [], spx[0]
+    for i in range(scale - 1):                                    # Res2Conv1dReluBn (ecapa_tdnn.py:28-83)
+        if i >= 1:
+            sp = sp + spx[i]
+        q = f"{p}.se_res2block.1"
+        sp = F.conv1d(sp, sd[f"{q}.convs.{i}.weight"], sd[f"{q}.convs.{i}.bias"], padding=dilation, dilation=dilation)
+        sp = _bn(sd, f"{q}.bns.{i}", F.relu(sp))
+        out.append(sp)
+    out.append(spx[scale - 1])
+    y = torch.cat(out, dim=1)
+    y = _conv_relu_bn(sd, p + ".se_res2block.2", y)
+    q = p + ".se_res2block.3"                                     # SE_Connect (ecapa_tdnn.py:119-132)
+    s = y.mean(dim=2)
+    s = F.relu(F.linear(s, sd[q + ".linear1.weight"], sd[q + ".linear1.bias"]))
+    s = torch.sigmoid(F.linear(s, sd[q + ".linear2.weight"], sd[q + ".linear2.bias"]))
+    return x + y * s.unsqueeze(2)
+
+
+def ecapa_latent(sd, mels: torch.Tensor) -> torch.Tensor:
+    """The `latent` output of ECAPA_TDNN.forward(x, return_latent=True) (ecapa_tdnn.py:196-214), which is all that
+    SpeakerEncoder.tokenize keeps (speaker_encoder.py:100-105).  mels (B, T, F) -> (B, 1536, T)."""
+    p = "speaker_encoder.speaker_encoder"
+    x = mels.permute(0, 2, 1)
+    out1 = _conv_relu_bn(sd, p + ".layer1", x, padding=2)
+    out2 = _se_res2block(sd, p + ".layer2", out1, 2)
+    out3 = _se_res2block(sd, p + ".layer3", out2, 3)
+    out4 = _se_res2block(sd, p + ".layer4", out3, 4)
+    out = torch.cat([out2, out3, out4], dim=1)
+    return F.relu(F.conv1d(out, sd[p + ".conv.weight"], sd[p + ".conv.bias"]))
+
+
+def perceiver_resampler(sd, x: torch.Tensor, heads: int = 8) -> torch.Tensor:
+    """PerceiverResampler.forward (perceiver_encoder.py:297-350): proj_context, then depth x [cross attention of the
+    latents over cat(latents, context) (no pre-norm, cross_attn_include_queries) + GEGLU feed-forward], RMSNorm.
+    x (B, T, dim_context) -> (B, num_latents, dim)."""
+    p = "speaker_encoder.perceiver_sampler"
+    x = F.linear(x, sd[p + ".proj_context.weight"], sd[p + ".proj_context.bias"])
+    B = x.shape[0]
+    lat = sd[p + ".latents"].unsqueeze(0).expand(B, -1, -1)
+    i = 0
+    while f"{p}.layers.{i}.0.to_q.weight" in sd:
+        a = f"{p}.layers.{i}.0"
+        ctx = torch.cat((lat, x), dim=-2)
+        q = F.linear(lat, sd[a + ".to_q.weight"])
+        k, v = F.linear(ctx, sd[a + ".to_kv.weight"]).chunk(2, dim=-1)
+        sp = lambda t: t.reshape(B, t.shape[1], heads, -1).transpose(1, 2)          # b n (h d) -> b h n d
+        q, k, v = sp(q), sp(k), sp(v)
+        sim = torch.einsum("bhid,bhjd->bhij", q, k) * q.shape[-1] ** -0.5
+        o = torch.einsum("bhij,bhjd->bhid", sim.softmax(dim=-1), v)
+        o = o.transpose(1, 2).reshape(B, lat.shape[1], -1)
+        lat = F.linear(o, sd[a + ".to_out.weight"]) + lat
+        f = f"{p}.layers.{i}.1"
+        h, gate = F.linear(lat, sd[f + ".0.weight"], sd[f + ".0.bias"]).chunk(2, dim=-1)
+        lat = F.linear(F.gelu(gate) * h, sd[f + ".2.weight"], sd[f + ".2.bias"]) + lat
+        i += 1
+    return F.normalize(lat, dim=-1) * (lat.shape[-1] ** 0.5) * sd[p + ".norm.gamma"]
+
+
+def fsq_quantize_indices(sd, x: torch.Tensor, levels):
+    """ResidualFSQ.forward with one quantizer (residual_fsq.py:213-283) -> FSQ.forward
+    (finite_scalar_quantization.py:101-118, 126-141, 190-250): project_in, bound (tanh with the half-level shift of
+    even level counts), round, codes_to_indices.  x (B, N, dim) -> (indices (B, N) int32, margin (B, N)): margin =
+    distance of the closest pre-rounding coordinate to a rounding boundary (how far an index is from flipping)."""
+    p = "speaker_encoder.quantizer"
+    z = F.linear(x, sd[p + ".project_in.weight"], sd[p + ".project_in.bias"])
+    lv = torch.tensor(levels, dtype=torch.int32)
+    half_l = (lv - 1) * (1 + 1e-3) / 2
+    offset = torch.where(lv % 2 == 0, 0.5, 0.0)
+    shift = (offset / half_l).atanh()
+    bounded = (z + shift).tanh() * half_l - offset
+    q = bounded.round()
+    half_width = lv // 2
+    codes = q / half_width
+    basis = torch.cumprod(torch.tensor([1] + list(levels[:-1])), dim=0).to(torch.int32)
+    idx = ((codes * half_width + half_width) * basis).sum(dim=-1).to(torch.int32)
+    frac = bounded - torch.floor(bounded)
+    margin = (frac - 0.5).abs().min(dim=-1).values
+    return idx, margin
+
+
+@torch.no_grad()
+def tokenize_speaker(sd, cfg, ref_wav: torch.Tensor):
+    """The speaker half of BiCodec.tokenize (bicodec.py:162-167): ref_wav (B, n) -> (global_tokens (B, 1, N) int32,
+    margin (B, N))."""
+    mel = mel_spectrogram(ref_wav, cfg)                                        # (B, n_mels, T)
+    feats = ecapa_latent(sd, mel.transpose(1, 2))                              # (B, 1536, T)
+    lat = perceiver_resampler(sd, feats.transpose(1, 2))                       # (B, N, latent)
+    idx, margin = fsq_quantize_indices(sd, lat, cfg.fsq_levels)
+    return idx.unsqueeze(1), margin
+
+
 def snr_db(ref: torch.Tensor, test: torch.Tensor) -> float:
     ref = ref.double().flatten()
     err = test.double().flatten() - ref

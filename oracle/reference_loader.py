@@ -119,3 +119,39 @@ class ReferenceSemanticTokenizer(torch.nn.Module):
         """feat (B,T,D) -> semantic tokens (B,T), exactly the two lines of bicodec.py:165-166."""
         z = self.encoder(feat.transpose(1, 2))
         return self.quantizer.tokenize(z)
+
+
+class ReferenceSpeakerTokenizer(torch.nn.Module):
+    """The reference modules behind the speaker half of BiCodec.tokenize (sparktts/models/bicodec.py:162-167):
+    the torchaudio MelSpectrogram that ``init_mel_transformer`` builds (:191-211) and ``SpeakerEncoder.tokenize``
+    (speaker_encoder.py:100-105: ECAPA-TDNN latent -> perceiver resampler -> ResidualFSQ indices)."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        _import_reference()
+        import torchaudio.transforms as TT
+        from sparktts.modules.speaker.speaker_encoder import SpeakerEncoder
+
+        self.mel_transformer = TT.MelSpectrogram(
+            cfg.sample_rate, cfg.mel_n_fft, cfg.mel_win_length, cfg.mel_hop_length, cfg.mel_fmin, cfg.mel_fmax,
+            n_mels=cfg.num_mels, power=1, norm="slaney", mel_scale="slaney")
+        self.speaker_encoder = SpeakerEncoder(
+            input_dim=cfg.num_mels, out_dim=cfg.d_model, latent_dim=cfg.latent_dim, token_num=cfg.token_num,
+            fsq_levels=list(cfg.fsq_levels), fsq_num_quantizers=1)
+        self.eval()
+
+    def load_checkpoint(self, sd):
+        own = {k: v for k, v in sd.items() if k.startswith("speaker_encoder.")}
+        missing, unexpected = self.load_state_dict(own, strict=False)
+        assert not unexpected, unexpected
+        # only the x-vector head (attentive pooling, bn, linear), which tokenize computes and discards, may be absent
+        head = ("speaker_encoder.speaker_encoder.pool.", "speaker_encoder.speaker_encoder.bn.",
+                "speaker_encoder.speaker_encoder.linear.", "mel_transformer.")   # (the mel buffers are derived, not loaded)
+        assert all(k.startswith(head) for k in missing), missing
+        return self
+
+    @torch.no_grad()
+    def tokenize(self, ref_wav):
+        """ref_wav (B, n) -> global tokens (B, 1, N) int32, exactly bicodec.py:163 + :167 (ref_wav as (B, 1, n))."""
+        mel = self.mel_transformer(ref_wav.unsqueeze(1)).squeeze(1)
+        return self.speaker_encoder.tokenize(mel.transpose(1, 2))

@@ -56,6 +56,12 @@ SIGNATURES = {
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "sparkcodec_tokenize_semantic": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
                                                C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sparkcodec_set_mel_params": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float]),
+    "sparkcodec_speaker_workspace_bytes": (C.c_int, [_H, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
+    "sparkcodec_tokenize_speaker": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p,
+                                              C.c_void_p, C.c_void_p]),
+    "sparkcodec_tokenize_speaker_tap": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p,
+                                                  C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int64), C.c_void_p]),
     "sparkcodec_set_impl": (C.c_int, [_H, C.c_int]),
     "sparkcodec_detokenize_tap": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.c_void_p, C.c_size_t, C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t,

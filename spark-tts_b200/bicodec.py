@@ -127,6 +127,10 @@ class BiCodec:
                 t = t.detach().to("cpu", torch.float32).contiguous()
                 shape = (C.c_int64 * max(t.dim(), 1))(*t.shape)
                 _lib.check(lib.sparkcodec_set_tensor(h, key.encode(), C.c_void_p(t.data_ptr()), shape, t.dim()))
+            c = self.cfg
+            _lib.check(lib.sparkcodec_set_mel_params(
+                h, c.sample_rate, c.mel_n_fft, c.mel_win_length, c.mel_hop_length, c.num_mels, float(c.mel_fmin),
+                -1.0 if c.mel_fmax is None else float(c.mel_fmax)))
             _lib.check(lib.sparkcodec_finalize(h))
         except Exception:
             lib.sparkcodec_destroy(h)
@@ -375,8 +379,7 @@ class BiCodec:
         ``quantizer.tokenize(encoder(feat.transpose(1, 2)))``.  feat (B, T, d_model) fp32 (the wav2vec2 feature
         mix) -> semantic tokens (B, T) int64.  Needs a checkpoint that carries ``encoder.*`` and
         ``quantizer.in_project.*``.  With ``return_margin`` also returns the (B, T) fp32 gap between the best and
-        the second-best code distance (a near-zero gap marks a numerical tie).  The speaker half (mel -> ECAPA ->
-        FSQ) is not built."""
+        the second-best code distance (a near-zero gap marks a numerical tie).  (Speaker half: ``tokenize_speaker``.)"""
         self._ensure(feat)
         if feat.dim() != 3 or feat.shape[2] != self.cfg.d_model or feat.dtype != torch.float32:
             raise ValueError(f"feat must be float32 (B, T, {self.cfg.d_model})")
@@ -391,6 +394,64 @@ class BiCodec:
                 C.c_void_p(tokens.data_ptr()), C.c_void_p(margin.data_ptr()) if return_margin else None,
                 self._stream()))
         return (tokens, margin) if return_margin else tokens
+
+    # ------------------------------------------------------------------ encode side, speaker half
+    @torch.no_grad()
+    def tokenize_speaker(self, ref_wav: torch.Tensor, return_margin: bool = False, tap: Optional[str] = None):
+        """The speaker half of the reference's ``BiCodec.tokenize`` (bicodec.py:162-167):
+        ``speaker_encoder.tokenize(mel_transformer(ref_wav).squeeze(1).transpose(1, 2))``.  ref_wav (B, n) or (B, 1, n)
+        fp32 on the model's device -> global tokens (B, 1, token_num) int32.  Needs a checkpoint that carries the
+        ECAPA-TDNN / perceiver / FSQ ``project_in`` tensors.  ``return_margin``: also the (B, token_num) distance of the
+        closest FSQ coordinate to a rounding boundary.  ``tap`` (tests): also an intermediate as (B, rows, channels)."""
+        self._ensure(ref_wav)
+        if ref_wav.dim() == 3 and ref_wav.shape[1] == 1:
+            ref_wav = ref_wav[:, 0]
+        if ref_wav.dim() != 2 or ref_wav.dtype != torch.float32:
+            raise ValueError("ref_wav must be float32 (B, n) or (B, 1, n)")
+        ref_wav = ref_wav.contiguous()
+        B, n = ref_wav.shape
+        N = self.cfg.token_num
+        tokens = torch.empty((B, 1, N), dtype=torch.int32, device=self._device)
+        margin = torch.empty((B, N), dtype=torch.float32, device=self._device) if return_margin else None
+        lib = _lib.load()
+        tapped = None
+        if B:
+            need = C.c_size_t()
+            _lib.check(lib.sparkcodec_speaker_workspace_bytes(self._handle, B, n, C.byref(need)))
+            ws = torch.empty(need.value, dtype=torch.uint8, device=self._device)
+            if tap is None:
+                _lib.check(lib.sparkcodec_tokenize_speaker(
+                    self._handle, C.c_void_p(ref_wav.data_ptr()), B, n, C.c_void_p(ws.data_ptr()), ws.numel(),
+                    C.c_void_p(tokens.data_ptr()), C.c_void_p(margin.data_ptr()) if return_margin else None,
+                    self._stream()))
+            else:
+                cap = B * (n // self.cfg.mel_hop_length + 1) * 1536 + 4096
+                out = torch.empty(cap, dtype=torch.float32, device=self._device)
+                shape = (C.c_int64 * 2)()
+                _lib.check(lib.sparkcodec_tokenize_speaker_tap(
+                    self._handle, C.c_void_p(ref_wav.data_ptr()), B, n, C.c_void_p(ws.data_ptr()), ws.numel(),
+                    C.c_void_p(tokens.data_ptr()), tap.encode(), C.c_void_p(out.data_ptr()), cap, shape, self._stream()))
+                rows, ch = int(shape[0]), int(shape[1])
+                tapped = out[: B * rows * ch].view(B, rows, ch).clone()
+            torch.cuda.current_stream(self._device).synchronize()      # `ws` is freed on return
+        res = (tokens,)
+        if return_margin:
+            res += (margin,)
+        if tap is not None:
+            res += (tapped,)
+        return res[0] if len(res) == 1 else res
+
+    @torch.no_grad()
+    def tokenize(self, batch: Dict[str, torch.Tensor], precision: Optional[str] = None):
+        """``BiCodec.tokenize`` of the reference (bicodec.py:151-169): ``batch["feat"]`` (B, T, d_model) wav2vec2
+        feature mix and ``batch["ref_wav"]`` (B, n) reference clip -> (semantic_tokens (B, T) int64,
+        global_tokens (B, 1, token_num) int32), both on the model's device."""
+        dev = self._device if self._device is not None else torch.device("cuda")
+        feat = batch["feat"].to(dev, torch.float32)
+        ref_wav = batch["ref_wav"].to(dev, torch.float32)
+        semantic_tokens = self.tokenize_semantic(feat, precision)
+        global_tokens = self.tokenize_speaker(ref_wav)
+        return semantic_tokens, global_tokens
 
     def halo_frames(self) -> Tuple[int, int]:
         if self._handle is None:

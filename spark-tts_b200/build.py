@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsparkcodec.so")
-SOURCES = ["api.cu", "tc_gemm.cu", "ru_fused.cu", "simt_gemm.cu", "stream_kernels.cu", "pack.cpp"]
+SOURCES = ["api.cu", "tc_gemm.cu", "ru_fused.cu", "simt_gemm.cu", "stream_kernels.cu", "speaker_kernels.cu", "pack.cpp"]
 HEADERS = ["common.cuh", "gemm_params.cuh", "tc_ptx.cuh", "pack.h", os.path.join("..", "..", "include", "sparkcodec.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

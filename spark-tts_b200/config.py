@@ -32,6 +32,17 @@ class BiCodecConfig:
     rates: List[int] = field(default_factory=lambda: [8, 5, 4, 2])
     kernel_sizes: List[int] = field(default_factory=lambda: [16, 11, 8, 4])
     sample_rate: int = 16000
+    # mel_params of config.yaml (BiCodec.init_mel_transformer, sparktts/models/bicodec.py:191-211): input of the
+    # speaker half of tokenize; and the reference-clip rule of BiCodecTokenizer.get_ref_clip (audio_tokenizer.py:57-71)
+    mel_n_fft: int = 1024
+    mel_win_length: int = 640
+    mel_hop_length: int = 320
+    mel_fmin: float = 10.0
+    mel_fmax: Any = None
+    num_mels: int = 128
+    ref_segment_duration: float = 6.0
+    latent_hop_length: int = 320
+    volume_normalize: bool = True
 
     @property
     def hop(self) -> int:
@@ -69,7 +80,20 @@ class BiCodecConfig:
             dec_channels=int(d["channels"]),
             rates=[int(v) for v in d["rates"]],
             kernel_sizes=[int(v) for v in d["kernel_sizes"]],
+            **cls._mel_fields(cfg),
         )
+
+    @staticmethod
+    def _mel_fields(cfg: Dict[str, Any]) -> Dict[str, Any]:
+        m = cfg.get("mel_params")
+        if not m:
+            return {}
+        out = dict(mel_n_fft=int(m["n_fft"]), mel_win_length=int(m.get("win_length", m["n_fft"])),
+                   mel_hop_length=int(m.get("hop_length", int(m["n_fft"]) // 4)), mel_fmin=float(m.get("mel_fmin", 0.0)),
+                   mel_fmax=(None if m.get("mel_fmax") is None else float(m["mel_fmax"])), num_mels=int(m["num_mels"]))
+        if "sample_rate" in m:
+            out["sample_rate"] = int(m["sample_rate"])
+        return out
 
 
 def load_bicodec_yaml(path: str) -> BiCodecConfig:

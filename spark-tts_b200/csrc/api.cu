@@ -90,6 +90,35 @@ struct UpBlock {
   ResUnit ru[3];
 };
 
+// ---- speaker half of tokenize: ECAPA-TDNN trunk, perceiver resampler, FSQ project_in (all fp32 on the device) ----
+struct SpkConv {                 // Conv1d (+ ReLU + BatchNorm(eval) folded into scale / shift)
+  float *w = nullptr, *b = nullptr, *scale = nullptr, *shift = nullptr;
+  int c_out = 0, c_in = 0, k = 1;
+};
+struct SpkRes2Block {
+  SpkConv c0, c2;
+  std::vector<SpkConv> convs;    // Res2Conv1dReluBn: scale - 1 convs of `width` channels
+  float *se_w1 = nullptr, *se_b1 = nullptr, *se_w2 = nullptr, *se_b2 = nullptr;
+  int dilation = 1, se_dim = 0;
+};
+struct SpkPercLayer {
+  float *wq = nullptr, *wkv = nullptr, *wo = nullptr, *w_ff0 = nullptr, *b_ff0 = nullptr, *w_ff2 = nullptr, *b_ff2 = nullptr;
+};
+struct SpeakerModel {
+  bool present = false;
+  // mel front end (defaults: the released config.yaml mel_params; sparkcodec_set_mel_params overrides before finalize)
+  int sample_rate = 16000, n_fft = 1024, win = 640, hop = 320, n_mels = 128;
+  float fmin = 10.f, fmax = -1.f;            // fmax < 0: sample_rate / 2
+  float *dft = nullptr, *fb = nullptr;       // (2 * bins, win) windowed DFT rows [re | im]; (n_mels, bins) filterbank
+  int bins = 0;
+  SpkConv layer1, conv_cat;
+  std::vector<SpkRes2Block> blocks;
+  int channels = 0, width = 0;
+  float *latents = nullptr, *pc_w = nullptr, *pc_b = nullptr, *norm_gamma = nullptr, *fsq_win = nullptr, *fsq_bin = nullptr;
+  std::vector<SpkPercLayer> layers;
+  int dim = 0, n_lat = 0, heads = 8, dim_head = 64, ff_inner = 0;
+};
+
 }  // namespace sparkcodec
 
 using namespace sparkcodec;
@@ -121,6 +150,7 @@ struct sparkcodec_handle {
   std::vector<Backbone> enc_backbones;
   float *tok_mat = nullptr, *tok_vec = nullptr;        // in_project . encoder.project folded: (codebook_dim, C)
   float *codes_n = nullptr, *codes_sq = nullptr;       // F.normalize(codebook) rows and their squared norms
+  SpeakerModel spk;                                    // optional: only when the checkpoint carries the ECAPA / perceiver tensors
   // wave generator
   GemmWeights conv_in;
   SnakeParams s_conv_in;   // first block's input snake (conv_in epilogue)
@@ -271,6 +301,152 @@ static int build_backbone(sparkcodec_handle* h, const std::string& prefix, int l
   for (auto& v : fb) v *= post_scale;
   SC_TRY(upload(h, fw, &bb->final_w));
   SC_TRY(upload(h, fb, &bb->final_b));
+  return 0;
+}
+
+// ---- speaker half of tokenize (bicodec.py:162-167), optional --------------------------------------------------
+static int spk_conv(sparkcodec_handle* h, const std::string& conv, const std::string& bn, SpkConv* out) {
+  const HostTensor *w, *b;
+  SC_TRY(get(h, conv + ".weight", &w));
+  if (w->shape.size() != 3) { set_error("tensor '%s.weight' must be (C_out, C_in, k)", conv.c_str()); return SPARKCODEC_EINVAL; }
+  out->c_out = (int)w->shape[0]; out->c_in = (int)w->shape[1]; out->k = (int)w->shape[2];
+  SC_TRY(get(h, conv + ".bias", &b, {out->c_out}));
+  // (C_out, C_in, k) -> [n][j * C_in + c]: the layout the fp32 conv kernel reads
+  std::vector<float> wt((size_t)out->c_out * out->k * out->c_in);
+  for (int n = 0; n < out->c_out; ++n)
+    for (int c = 0; c < out->c_in; ++c)
+      for (int j = 0; j < out->k; ++j)
+        wt[((size_t)n * out->k + j) * out->c_in + c] = w->data[((size_t)n * out->c_in + c) * out->k + j];
+  SC_TRY(upload(h, wt, &out->w));
+  SC_TRY(upload(h, b->data, &out->b));
+  if (!bn.empty()) {   // BatchNorm1d(eval): y = (x - mean) / sqrt(var + 1e-5) * weight + bias  (ecapa_tdnn.py:63,113)
+    const HostTensor *g, *be, *mu, *var;
+    SC_TRY(get(h, bn + ".weight", &g, {out->c_out}));
+    SC_TRY(get(h, bn + ".bias", &be, {out->c_out}));
+    SC_TRY(get(h, bn + ".running_mean", &mu, {out->c_out}));
+    SC_TRY(get(h, bn + ".running_var", &var, {out->c_out}));
+    std::vector<float> sc(out->c_out), sh(out->c_out);
+    for (int n = 0; n < out->c_out; ++n) {
+      sc[n] = g->data[n] / std::sqrt(var->data[n] + 1e-5f);
+      sh[n] = be->data[n] - mu->data[n] * sc[n];
+    }
+    SC_TRY(upload(h, sc, &out->scale));
+    SC_TRY(upload(h, sh, &out->shift));
+  }
+  return 0;
+}
+
+static double hz_to_mel_slaney(double f) {
+  const double f_sp = 200.0 / 3, min_log_hz = 1000.0, logstep = std::log(6.4) / 27.0;
+  return f >= min_log_hz ? min_log_hz / f_sp + std::log(f / min_log_hz) / logstep : f / f_sp;
+}
+static double mel_to_hz_slaney(double m) {
+  const double f_sp = 200.0 / 3, min_log_hz = 1000.0, logstep = std::log(6.4) / 27.0, min_log_mel = min_log_hz / f_sp;
+  return m >= min_log_mel ? min_log_hz * std::exp(logstep * (m - min_log_mel)) : f_sp * m;
+}
+
+static int build_speaker(sparkcodec_handle* h) {
+  SpeakerModel& S = h->spk;
+  const sparkcodec_config& c = h->cfg;
+  const std::string e = "speaker_encoder.speaker_encoder", ps = "speaker_encoder.perceiver_sampler";
+  const HostTensor *t, *u;
+  // ---- mel front end: windowed DFT rows and the slaney filterbank (torchaudio melscale_fbanks, norm = "slaney") ----
+  if (S.win > S.n_fft || S.hop < 1 || S.n_mels < 1) { set_error("bad mel parameters"); return SPARKCODEC_EINVAL; }
+  S.bins = S.n_fft / 2 + 1;
+  {
+    const double pi = 3.14159265358979323846;
+    const int pad = (S.n_fft - S.win) / 2;      // torch.stft centres the window inside n_fft
+    std::vector<float> dft((size_t)2 * S.bins * S.win);
+    for (int k = 0; k < S.bins; ++k)
+      for (int i = 0; i < S.win; ++i) {
+        const double wv = 0.5 - 0.5 * std::cos(2.0 * pi * i / S.win);          // periodic Hann
+        const double ang = 2.0 * pi * (double)k * (double)(i + pad) / S.n_fft;
+        dft[(size_t)k * S.win + i] = (float)(wv * std::cos(ang));
+        dft[(size_t)(S.bins + k) * S.win + i] = (float)(-wv * std::sin(ang));
+      }
+    SC_TRY(upload(h, dft, &S.dft));
+    const double f_max = S.fmax < 0 ? S.sample_rate / 2 : S.fmax;
+    const double m_lo = hz_to_mel_slaney(S.fmin), m_hi = hz_to_mel_slaney(f_max);
+    std::vector<double> f_pts(S.n_mels + 2);
+    for (int i = 0; i < S.n_mels + 2; ++i) f_pts[i] = mel_to_hz_slaney(m_lo + (m_hi - m_lo) * i / (S.n_mels + 1));
+    std::vector<float> fb((size_t)S.n_mels * S.bins);
+    for (int m = 0; m < S.n_mels; ++m) {
+      const double enorm = 2.0 / (f_pts[m + 2] - f_pts[m]);
+      for (int k = 0; k < S.bins; ++k) {
+        const double f = (double)(S.sample_rate / 2) * k / (S.bins - 1);
+        const double down = (f - f_pts[m]) / (f_pts[m + 1] - f_pts[m]), up = (f_pts[m + 2] - f) / (f_pts[m + 2] - f_pts[m + 1]);
+        fb[(size_t)m * S.bins + k] = (float)(std::max(0.0, std::min(down, up)) * enorm);
+      }
+    }
+    SC_TRY(upload(h, fb, &S.fb));
+  }
+  // ---- ECAPA-TDNN trunk (ecapa_tdnn.py:152-195) ----
+  SC_TRY(spk_conv(h, e + ".layer1.conv", e + ".layer1.bn", &S.layer1));
+  if (S.layer1.c_in != S.n_mels) { set_error("ECAPA layer1 expects %d mel bins, mel parameters give %d", S.layer1.c_in, S.n_mels); return SPARKCODEC_EINVAL; }
+  S.channels = S.layer1.c_out;
+  const int dil[3] = {2, 3, 4};
+  S.blocks.resize(3);
+  for (int i = 0; i < 3; ++i) {
+    SpkRes2Block& B = S.blocks[i];
+    const std::string p = e + ".layer" + std::to_string(i + 2) + ".se_res2block";
+    B.dilation = dil[i];
+    SC_TRY(spk_conv(h, p + ".0.conv", p + ".0.bn", &B.c0));
+    for (int j = 0; h->host.count(p + ".1.convs." + std::to_string(j) + ".weight"); ++j) {
+      B.convs.emplace_back();
+      SC_TRY(spk_conv(h, p + ".1.convs." + std::to_string(j), p + ".1.bns." + std::to_string(j), &B.convs.back()));
+    }
+    if (B.convs.empty() || B.convs[0].k != 3) { set_error("unexpected Res2 block layout in '%s'", p.c_str()); return SPARKCODEC_EINVAL; }
+    S.width = B.convs[0].c_out;
+    if ((int)(B.convs.size() + 1) * S.width != S.channels) { set_error("Res2 widths do not tile %d channels", S.channels); return SPARKCODEC_EINVAL; }
+    SC_TRY(spk_conv(h, p + ".2.conv", p + ".2.bn", &B.c2));
+    SC_TRY(get(h, p + ".3.linear1.weight", &t));
+    B.se_dim = (int)t->shape[0];
+    SC_TRY(upload(h, t->data, &B.se_w1));
+    SC_TRY(get(h, p + ".3.linear1.bias", &t, {B.se_dim}));
+    SC_TRY(upload(h, t->data, &B.se_b1));
+    SC_TRY(get(h, p + ".3.linear2.weight", &t, {S.channels, B.se_dim}));
+    SC_TRY(upload(h, t->data, &B.se_w2));
+    SC_TRY(get(h, p + ".3.linear2.bias", &t, {S.channels}));
+    SC_TRY(upload(h, t->data, &B.se_b2));
+  }
+  SC_TRY(spk_conv(h, e + ".conv", "", &S.conv_cat));
+  if (S.conv_cat.c_in != 3 * S.channels || S.conv_cat.k != 1) { set_error("ECAPA cat conv shape"); return SPARKCODEC_EINVAL; }
+  // ---- perceiver resampler (perceiver_encoder.py:297-350) ----
+  S.dim = c.latent_dim; S.n_lat = c.token_num;
+  SC_TRY(get(h, ps + ".latents", &t, {S.n_lat, S.dim}));
+  SC_TRY(upload(h, t->data, &S.latents));
+  SC_TRY(get(h, ps + ".proj_context.weight", &t, {S.dim, S.conv_cat.c_out}));
+  SC_TRY(upload(h, t->data, &S.pc_w));
+  SC_TRY(get(h, ps + ".proj_context.bias", &t, {S.dim}));
+  SC_TRY(upload(h, t->data, &S.pc_b));
+  for (int i = 0; h->host.count(ps + ".layers." + std::to_string(i) + ".0.to_q.weight"); ++i) {
+    const std::string a = ps + ".layers." + std::to_string(i) + ".0", f = ps + ".layers." + std::to_string(i) + ".1";
+    S.layers.emplace_back();
+    SpkPercLayer& L = S.layers.back();
+    const int inner = S.heads * S.dim_head;
+    SC_TRY(get(h, a + ".to_q.weight", &t, {inner, S.dim}));
+    SC_TRY(upload(h, t->data, &L.wq));
+    SC_TRY(get(h, a + ".to_kv.weight", &t, {2 * inner, S.dim}));
+    SC_TRY(upload(h, t->data, &L.wkv));
+    SC_TRY(get(h, a + ".to_out.weight", &t, {S.dim, inner}));
+    SC_TRY(upload(h, t->data, &L.wo));
+    SC_TRY(get(h, f + ".0.weight", &t));
+    S.ff_inner = (int)t->shape[0] / 2;
+    SC_TRY(upload(h, t->data, &L.w_ff0));
+    SC_TRY(get(h, f + ".0.bias", &u, {2 * S.ff_inner}));
+    SC_TRY(upload(h, u->data, &L.b_ff0));
+    SC_TRY(get(h, f + ".2.weight", &t, {S.dim, S.ff_inner}));
+    SC_TRY(upload(h, t->data, &L.w_ff2));
+    SC_TRY(get(h, f + ".2.bias", &t, {S.dim}));
+    SC_TRY(upload(h, t->data, &L.b_ff2));
+  }
+  SC_TRY(get(h, ps + ".norm.gamma", &t, {S.dim}));
+  SC_TRY(upload(h, t->data, &S.norm_gamma));
+  SC_TRY(get(h, "speaker_encoder.quantizer.project_in.weight", &t, {c.fsq_num_levels, S.dim}));
+  SC_TRY(upload(h, t->data, &S.fsq_win));
+  SC_TRY(get(h, "speaker_encoder.quantizer.project_in.bias", &t, {c.fsq_num_levels}));
+  SC_TRY(upload(h, t->data, &S.fsq_bin));
+  S.present = true;
   return 0;
 }
 
@@ -456,6 +632,7 @@ static int do_finalize(sparkcodec_handle* h) {
     SC_TRY(upload(h, csq, &h->codes_sq));
     h->has_encoder = true;
   }
+  if (h->host.count("speaker_encoder.speaker_encoder.layer1.conv.weight")) SC_TRY(build_speaker(h));
   h->host.clear();
   h->finalized = true;
   return 0;
@@ -801,6 +978,131 @@ static int run_pass(Pass& P, const void* sem, int sem_dt, const void* glob, int 
   return 0;
 }
 
+// ---- speaker half of tokenize: workspace + schedule ---------------------------------------------------------
+struct SpkWorkspace {
+  float *frames, *spec, *mag, *mel, *a1, *y, *z, *u, *cat, *latent, *ctx, *kv, *lat, *lat2, *q, *att, *ffh, *ffg, *se_m, *se_h, *se_s;
+};
+static int spk_frames_of(const SpeakerModel& S, int n_samples) { return n_samples / S.hop + 1; }   // torch.stft(center=True)
+static void spk_carve(const sparkcodec_handle* h, Arena& a, size_t B, size_t n_samples, SpkWorkspace* w) {
+  const SpeakerModel& S = h->spk;
+  const size_t T = spk_frames_of(S, (int)n_samples), R = B * T, C = S.channels, inner = (size_t)S.heads * S.dim_head;
+  w->frames = a.f32(R * S.win);
+  w->spec = a.f32(R * 2 * S.bins);
+  w->mag = a.f32(R * S.bins);
+  w->mel = a.f32(R * S.n_mels);
+  w->a1 = a.f32(R * C);
+  w->y = a.f32(R * C);
+  w->z = a.f32(R * C);
+  w->u = a.f32(R * C);
+  w->cat = a.f32(R * 3 * C);
+  w->latent = a.f32(R * S.conv_cat.c_out);
+  w->ctx = a.f32(B * (S.n_lat + T) * S.dim);
+  w->kv = a.f32(B * (S.n_lat + T) * 2 * inner);
+  w->lat = a.f32(B * S.n_lat * S.dim);
+  w->lat2 = a.f32(B * S.n_lat * S.dim);
+  w->q = a.f32(B * S.n_lat * inner);
+  w->att = a.f32(B * S.n_lat * inner);
+  w->ffh = a.f32(B * S.n_lat * 2 * S.ff_inner);
+  w->ffg = a.f32(B * S.n_lat * S.ff_inner);
+  w->se_m = a.f32(B * C);
+  w->se_h = a.f32(B * 128 + B * 1024);
+  w->se_s = a.f32(B * C);
+}
+static size_t spk_workspace_needed(const sparkcodec_handle* h, size_t B, size_t n_samples) {
+  Arena a{nullptr, 0, ~(size_t)0};
+  SpkWorkspace w;
+  spk_carve(h, a, B, n_samples, &w);
+  return a.off + 1024;
+}
+
+static int spk_run_conv(const SpkConv& cv, const float* x, int ldx, const float* x2, int ldx2, int B, int rows, int dilation,
+                        bool relu, float* y, int ldy, cudaStream_t st) {
+  SpkGemm g;
+  g.x = x; g.ldx = ldx; g.x2 = x2; g.ldx2 = ldx2;
+  g.batch = B; g.rows = rows; g.K = cv.c_in;
+  g.ntaps = cv.k;
+  for (int j = 0; j < cv.k; ++j) g.shift[j] = (j - (cv.k - 1) / 2) * dilation;   // "same" padding = dilation * (k - 1) / 2
+  g.w = cv.w; g.ldw = cv.k * cv.c_in; g.bias = cv.b;
+  g.relu = relu ? 1 : 0; g.scale = cv.scale; g.shift_v = cv.shift;
+  g.y = y; g.ldy = ldy; g.N = cv.c_out;
+  return launch_spk_gemm(g, st);
+}
+static int spk_linear(const float* x, int ldx, int rows, int K, const float* w, const float* bias, const float* res, int ldres,
+                      int act_relu, int act, float* y, int ldy, int N, cudaStream_t st) {
+  SpkGemm g;
+  g.x = x; g.ldx = ldx; g.batch = 1; g.rows = rows; g.K = K;
+  g.w = w; g.ldw = K; g.bias = bias; g.relu = act_relu; g.act = act;
+  g.res = res; g.ldres = ldres; g.y = y; g.ldy = ldy; g.N = N;
+  return launch_spk_gemm(g, st);
+}
+
+// ref_wav (B, n) fp32 -> global tokens (B, token_num) int32.  Optional tap (test hook): name -> fp32 copy.
+static int run_speaker(sparkcodec_handle* h, const float* wav, int B, int n, SpkWorkspace& W, int* tokens, float* margin,
+                       TapReq* tap, cudaStream_t st) {
+  const SpeakerModel& S = h->spk;
+  const int T = spk_frames_of(S, n), R = B * T, C = S.channels, inner = S.heads * S.dim_head;
+  auto tap_out = [&](const char* name, const float* src, size_t rows, size_t ch) -> int {
+    if (!tap || !tap->name || strcmp(tap->name, name) != 0) return 0;
+    if ((size_t)B * rows * ch > tap->cap) { set_error("tap buffer too small for '%s'", name); return SPARKCODEC_ENOMEM; }
+    if (tap->shape) { tap->shape[0] = (int64_t)rows; tap->shape[1] = (int64_t)ch; }
+    tap->hit = true;
+    SC_CUDA(cudaMemcpyAsync(tap->out, src, (size_t)B * rows * ch * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+  };
+  NvtxRange range("sparkcodec.tokenize_speaker");
+  // ---- mel spectrogram (bicodec.py:191-211 MelSpectrogram, power 1, slaney): frames -> |DFT| -> filterbank ----
+  SC_TRY(launch_spk_frames(wav, B, n, T, S.hop, S.win, W.frames, st));
+  SC_TRY(spk_linear(W.frames, S.win, R, S.win, S.dft, nullptr, nullptr, 0, 0, 0, W.spec, 2 * S.bins, 2 * S.bins, st));
+  SC_TRY(launch_spk_magnitude(W.spec, (size_t)R, S.bins, W.mag, st));
+  SC_TRY(spk_linear(W.mag, S.bins, R, S.bins, S.fb, nullptr, nullptr, 0, 0, 0, W.mel, S.n_mels, S.n_mels, st));
+  SC_TRY(tap_out("mel", W.mel, T, S.n_mels));
+  // ---- ECAPA-TDNN trunk -> latent (ecapa_tdnn.py:196-208) ----
+  SC_TRY(spk_run_conv(S.layer1, W.mel, S.n_mels, nullptr, 0, B, T, 1, true, W.a1, C, st));
+  const float* x_in = W.a1;
+  int ld_in = C;
+  for (size_t bi = 0; bi < S.blocks.size(); ++bi) {
+    const SpkRes2Block& K = S.blocks[bi];
+    const int wd = S.width, nums = (int)K.convs.size();
+    SC_TRY(spk_run_conv(K.c0, x_in, ld_in, nullptr, 0, B, T, 1, true, W.y, C, st));
+    for (int i = 0; i < nums; ++i)   // sp = conv(sp_prev + spx[i]) -> relu -> bn, written to slice i (ecapa_tdnn.py:66-79)
+      SC_TRY(spk_run_conv(K.convs[i], W.y + (size_t)i * wd, C, i >= 1 ? W.z + (size_t)(i - 1) * wd : nullptr, C, B, T,
+                          K.dilation, true, W.z + (size_t)i * wd, C, st));
+    SC_TRY(launch_spk_copy_cols(W.y + (size_t)nums * wd, C, W.z + (size_t)nums * wd, C, (size_t)R, wd, st));
+    SC_TRY(spk_run_conv(K.c2, W.z, C, nullptr, 0, B, T, 1, true, W.u, C, st));
+    // SE_Connect (ecapa_tdnn.py:119-132) and the block's residual: out = x + u * sigmoid(W2 relu(W1 mean_t(u)))
+    SC_TRY(launch_spk_mean_rows(W.u, B, T, C, C, W.se_m, st));
+    SC_TRY(spk_linear(W.se_m, C, B, C, K.se_w1, K.se_b1, nullptr, 0, 1, 0, W.se_h, K.se_dim, K.se_dim, st));
+    SC_TRY(spk_linear(W.se_h, K.se_dim, B, K.se_dim, K.se_w2, K.se_b2, nullptr, 0, 0, 1, W.se_s, C, C, st));
+    float* out = W.cat + bi * (size_t)C;                       // torch.cat([out2, out3, out4], dim=1): slice bi of (B, T, 3C)
+    SC_TRY(launch_spk_se_apply(x_in, ld_in, W.u, C, W.se_s, B, T, C, out, 3 * C, st));
+    x_in = out;
+    ld_in = 3 * C;
+  }
+  SC_TRY(spk_run_conv(S.conv_cat, W.cat, 3 * C, nullptr, 0, B, T, 1, true, W.latent, S.conv_cat.c_out, st));
+  SC_TRY(tap_out("ecapa_latent", W.latent, T, S.conv_cat.c_out));
+  // ---- perceiver resampler (perceiver_encoder.py:335-347) ----
+  const int nk = S.n_lat + T, D = S.dim;
+  // proj_context straight into rows [n_lat, n_lat + T) of every utterance's context block
+  for (int b = 0; b < B; ++b)
+    SC_TRY(spk_linear(W.latent + (size_t)b * T * S.conv_cat.c_out, S.conv_cat.c_out, T, S.conv_cat.c_out, S.pc_w, S.pc_b,
+                      nullptr, 0, 0, 0, W.ctx + ((size_t)b * nk + S.n_lat) * D, D, D, st));
+  SC_TRY(launch_spk_place_rows(S.latents, 0, B, S.n_lat, D, W.lat, S.n_lat, 0, st));   // latents repeated per utterance
+  for (const SpkPercLayer& L : S.layers) {
+    SC_TRY(launch_spk_place_rows(W.lat, (size_t)S.n_lat * D, B, S.n_lat, D, W.ctx, nk, 0, st));   // context = cat(latents, x)
+    SC_TRY(spk_linear(W.lat, D, B * S.n_lat, D, L.wq, nullptr, nullptr, 0, 0, 0, W.q, inner, inner, st));
+    SC_TRY(spk_linear(W.ctx, D, B * nk, D, L.wkv, nullptr, nullptr, 0, 0, 0, W.kv, 2 * inner, 2 * inner, st));
+    SC_TRY(launch_spk_attention(W.q, W.kv, B, S.n_lat, nk, S.heads, S.dim_head, W.att, st));
+    SC_TRY(spk_linear(W.att, inner, B * S.n_lat, inner, L.wo, nullptr, W.lat, D, 0, 0, W.lat2, D, D, st));      // + latents
+    SC_TRY(spk_linear(W.lat2, D, B * S.n_lat, D, L.w_ff0, L.b_ff0, nullptr, 0, 0, 0, W.ffh, 2 * S.ff_inner, 2 * S.ff_inner, st));
+    SC_TRY(launch_spk_geglu(W.ffh, (size_t)B * S.n_lat, S.ff_inner, W.ffg, st));
+    SC_TRY(spk_linear(W.ffg, S.ff_inner, B * S.n_lat, S.ff_inner, L.w_ff2, L.b_ff2, W.lat2, D, 0, 0, W.lat, D, D, st));   // + latents
+  }
+  SC_TRY(launch_spk_rmsnorm(W.lat, S.norm_gamma, D, B * S.n_lat, W.lat2, st));
+  SC_TRY(tap_out("perceiver", W.lat2, S.n_lat, D));
+  // ---- FSQ quantise (residual_fsq.py:213-283 with one quantizer) ----
+  return launch_spk_fsq_quantize(W.lat2, D, B * S.n_lat, S.fsq_win, S.fsq_bin, h->fsq_levels, h->cfg.fsq_num_levels, tokens, margin, st);
+}
+
 static int check_common(sparkcodec_handle* h, int batch, int frames, int precision) {
   if (!h) { set_error("null handle"); return SPARKCODEC_EINVAL; }
   if (!h->finalized) { set_error("sparkcodec_finalize has not been called"); return SPARKCODEC_ESTATE; }
@@ -910,7 +1212,9 @@ int sparkcodec_set_tensor(sparkcodec_handle* h, const char* key, const float* da
   if (h->finalized) { set_error("weights are already finalized"); return SPARKCODEC_ESTATE; }
   const std::string k(key);
   static const char* used[] = {"quantizer.codebook.", "quantizer.out_project.", "speaker_encoder.quantizer.project_out.",
-                               "speaker_encoder.project.", "prenet.", "decoder.", "encoder.", "quantizer.in_project."};
+                               "speaker_encoder.project.", "prenet.", "decoder.", "encoder.", "quantizer.in_project.",
+                               "speaker_encoder.speaker_encoder.layer", "speaker_encoder.speaker_encoder.conv.",
+                               "speaker_encoder.perceiver_sampler.", "speaker_encoder.quantizer.project_in."};
   bool keep = false;
   for (const char* p : used) keep |= k.rfind(p, 0) == 0;
   if (!keep) return 0;   // encode-side / training-only tensor
@@ -1035,6 +1339,75 @@ int sparkcodec_tokenize_semantic(sparkcodec_handle* h, const float* feat, int ba
                         margin_out ? margin_out + (size_t)b0 * frames : nullptr));
   }
   return 0;
+}
+
+int sparkcodec_set_mel_params(sparkcodec_handle* h, int sample_rate, int n_fft, int win_length, int hop_length, int n_mels,
+                              float f_min, float f_max) {
+  if (!h) { set_error("null handle"); return SPARKCODEC_EINVAL; }
+  if (h->finalized) { set_error("weights are already finalized"); return SPARKCODEC_ESTATE; }
+  if (sample_rate < 1 || n_fft < 2 || win_length < 1 || win_length > n_fft || hop_length < 1 || n_mels < 1 || f_min < 0) {
+    set_error("bad mel parameters");
+    return SPARKCODEC_EINVAL;
+  }
+  SpeakerModel& S = h->spk;
+  S.sample_rate = sample_rate; S.n_fft = n_fft; S.win = win_length; S.hop = hop_length; S.n_mels = n_mels;
+  S.fmin = f_min; S.fmax = f_max;
+  return 0;
+}
+
+static int speaker_ready(sparkcodec_handle* h, int batch, int n_samples) {
+  if (!h) { set_error("null handle"); return SPARKCODEC_EINVAL; }
+  if (!h->finalized) { set_error("sparkcodec_finalize has not been called"); return SPARKCODEC_ESTATE; }
+  if (!h->spk.present) {
+    set_error("the checkpoint had no speaker_encoder.speaker_encoder.* / perceiver_sampler.* tensors: speaker tokenize is unavailable");
+    return SPARKCODEC_ESTATE;
+  }
+  if (batch < 0 || n_samples < 0) { set_error("negative batch / samples"); return SPARKCODEC_EINVAL; }
+  if (batch > 0 && n_samples <= h->spk.win / 2) {
+    set_error("reference clip of %d samples is shorter than the STFT padding (%d)", n_samples, h->spk.win / 2 + 1);
+    return SPARKCODEC_EINVAL;
+  }
+  return 0;
+}
+
+int sparkcodec_speaker_workspace_bytes(sparkcodec_handle* h, int batch, int n_samples, size_t* bytes) {
+  if (!bytes) { set_error("null argument"); return SPARKCODEC_EINVAL; }
+  SC_TRY(speaker_ready(h, batch, n_samples));
+  *bytes = spk_workspace_needed(h, (size_t)std::max(batch, 1), (size_t)std::max(n_samples, 1));
+  return 0;
+}
+
+static int tokenize_speaker_impl(sparkcodec_handle* h, const float* ref_wav, int batch, int n_samples, void* workspace,
+                                 size_t workspace_bytes, int32_t* tokens_out, float* margin_out, TapReq* tap, void* stream) {
+  SC_TRY(speaker_ready(h, batch, n_samples));
+  if (batch == 0) return 0;
+  if (!ref_wav || !tokens_out) { set_error("null tensor pointer"); return SPARKCODEC_EINVAL; }
+  if (!workspace || spk_workspace_needed(h, batch, n_samples) > workspace_bytes) {
+    set_error("speaker workspace of %zu bytes is too small (%zu needed)", workspace_bytes, spk_workspace_needed(h, batch, n_samples));
+    return SPARKCODEC_ENOMEM;
+  }
+  SC_ON_DEVICE(h->device);
+  g_launch_counter = &h->launches;
+  Arena a{static_cast<char*>(workspace), 0, workspace_bytes};
+  SpkWorkspace W;
+  spk_carve(h, a, batch, n_samples, &W);
+  SC_TRY(run_speaker(h, ref_wav, batch, n_samples, W, tokens_out, margin_out, tap, static_cast<cudaStream_t>(stream)));
+  if (tap && tap->name && !tap->hit) { set_error("unknown tap '%s'", tap->name); return SPARKCODEC_EINVAL; }
+  return 0;
+}
+
+int sparkcodec_tokenize_speaker(sparkcodec_handle* h, const float* ref_wav, int batch, int n_samples, void* workspace,
+                                size_t workspace_bytes, int32_t* tokens_out, float* margin_out, void* stream) {
+  return tokenize_speaker_impl(h, ref_wav, batch, n_samples, workspace, workspace_bytes, tokens_out, margin_out, nullptr, stream);
+}
+
+int sparkcodec_tokenize_speaker_tap(sparkcodec_handle* h, const float* ref_wav, int batch, int n_samples, void* workspace,
+                                    size_t workspace_bytes, int32_t* tokens_out, const char* tap, float* tap_out,
+                                    size_t tap_capacity, int64_t* tap_shape, void* stream) {
+  if (!tap || !tap_out) { set_error("null argument"); return SPARKCODEC_EINVAL; }
+  TapReq t;
+  t.name = tap; t.out = tap_out; t.cap = tap_capacity; t.shape = tap_shape;
+  return tokenize_speaker_impl(h, ref_wav, batch, n_samples, workspace, workspace_bytes, tokens_out, nullptr, &t, stream);
 }
 
 int sparkcodec_halo_frames(sparkcodec_handle* h, int* prenet_halo, int* wavegen_halo) {

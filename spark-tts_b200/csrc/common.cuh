@@ -151,6 +151,36 @@ int launch_dwconv_ln(const float* x, int batch, int rows, int c, const float* dw
 int launch_head(const float* x, int batch, int rows, int c, const float* alpha, const float* inv_alpha,
                 const float* w, float bias, float* wav, int crop_begin, int crop_rows, cudaStream_t s);
 
+// ---- speaker half of tokenize (speaker_kernels.cu): plain fp32 FFMA kernels, channels-last activations ----
+struct SpkGemm {
+  const float* x = nullptr; int ldx = 0;       // input rows (batch * rows, K) with row stride ldx
+  const float* x2 = nullptr; int ldx2 = 0;     // optional second input added element-wise on load
+  int batch = 1, rows = 0, K = 0;
+  int ntaps = 1; int shift[8] = {0};           // conv taps: row shifts (rows outside [0, rows) read as zero)
+  const float* w = nullptr; int ldw = 0;       // W[n][j * K + c]
+  const float* bias = nullptr;
+  int relu = 0;                                // ReLU after the bias ...
+  const float* scale = nullptr; const float* shift_v = nullptr;   // ... then the folded BatchNorm affine (optional)
+  int act = 0;                                 // 1: sigmoid
+  const float* res = nullptr; int ldres = 0;   // optional residual added last
+  float* y = nullptr; int ldy = 0; int N = 0;
+};
+int launch_spk_frames(const float* wav, int batch, int n, int frames, int hop, int win, float* out, cudaStream_t s);
+int launch_spk_magnitude(const float* spec, size_t rows, int bins, float* out, cudaStream_t s);
+int launch_spk_gemm(const SpkGemm& g, cudaStream_t s);
+int launch_spk_mean_rows(const float* x, int batch, int rows, int C, int ldx, float* out, cudaStream_t s);
+int launch_spk_se_apply(const float* x, int ldx, const float* u, int ldu, const float* sc, int batch, int rows, int C,
+                        float* out, int ldo, cudaStream_t s);
+int launch_spk_copy_cols(const float* src, int lds, float* dst, int ldd, size_t rows, int cols, cudaStream_t s);
+int launch_spk_place_rows(const float* src, size_t src_batch_stride, int batch, int src_rows, int C, float* dst,
+                          int dst_rows, int row_off, cudaStream_t s);
+int launch_spk_attention(const float* q, const float* kv, int batch, int nq, int nk, int heads, int dim_head, float* out,
+                         cudaStream_t s);
+int launch_spk_geglu(const float* h, size_t rows, int inner, float* out, cudaStream_t s);
+int launch_spk_rmsnorm(const float* x, const float* gamma, int dim, int rows, float* out, cudaStream_t s);
+int launch_spk_fsq_quantize(const float* x, int dim, int rows, const float* w_in, const float* b_in, const int* levels,
+                            int n_levels, int* idx_out, float* margin_out, cudaStream_t s);
+
 // ---- small host helpers ------------------------------------------------------------------------
 inline uint16_t f32_to_bf16_rn(float f) {
   uint32_t u;

@@ -1,4 +1,4 @@
-// Fused ResidualUnit of the WaveGenerator for the narrow stages (C = 96 / 192 channels), one kernel:
+// Fused ResidualUnit of the WaveGenerator (C = 96 / 192 / 384 channels), one kernel:
 //
 //   mid   = snake_mid( conv_k7_dil( op_in ) + b7 )          op_in = snake_in(x) as bf16 hi/lo planes
 //   x     = x + conv_1x1( mid ) + b1                         fp32 residual stream, updated in place
@@ -7,24 +7,27 @@
 // (reference: ResidualUnit.forward, sparktts/modules/blocks/layers.py:51-67; the Snake of the NEXT unit /
 // up-sampler is applied here because it is element-wise on this unit's output.)
 //
-// Un-fused, the k7 conv writes `mid` to HBM and the 1x1 conv reads it back; at C <= 192 the 1x1 conv is
-// purely HBM-bound (16 B per output element).  Here `mid` never leaves the SM:
+// Un-fused, the k7 conv writes `mid` to HBM and the 1x1 conv reads it back; the 1x1 conv is then purely HBM-bound
+// (16 B per output element).  Here `mid` never leaves the SM:
 //
-//   TMEM acc1 (k7 result) --mid warps: tcgen05.ld, +b7, Snake, bf16 hi/lo split, tcgen05.st IN PLACE--> the 32 fp32
+//   TMEM acc1 (k7 result) --mid team: tcgen05.ld, +b7, Snake, bf16 hi/lo split, tcgen05.st IN PLACE--> the 32 fp32
 //        columns of a chunk become 16 columns of packed bf16 hi + 16 columns of packed bf16 lo
 //        --tcgen05.mma with the A operand in TENSOR MEMORY (B = W1 chunk from smem, split-K over chunks)--> acc2
-//        --final warps: + residual slab (TMA) + b1, store x, Snake, store operand planes.
+//        --final team: + residual slab (TMA) + b1 -> x slab, Snake -> operand planes, all stored with TMA.
 // Keeping `mid` in TMEM leaves the whole shared memory to the operand rings: the weight ring has to cover the
 // ~2k-cycle refill round trip (MMA done -> commit -> producer -> TMA from L2 -> full), see DESIGN.md.
 //
-// Roles (352 threads, one persistent CTA per SM):
-//   warp 0 / one lane : TMA producer: activation halo tiles (one per K group, shared by the 7 taps through
-//                       row-offset descriptors), W7 tap tiles and W1 tiles through one weight ring
-//   warp 1 / one lane : tcgen05.mma issuer (k7 conv of tile i, then the 1x1 conv of tile i - SKEW)
-//   warps 2..9        : epilogue: mid stage of tile i, final stage of tile i - SKEW
-//   warp 10 / one lane: residual TMA producer (fp32 128 x 32 slabs, SWIZZLE_128B)
-// C = 96 keeps two acc1 and two acc2 buffers in TMEM and skews the 1x1 conv by one tile (SKEW = 1) so the
-// tensor pipe never waits for the mid stage; C = 192 (acc1 + acc2 = 384 columns) runs un-skewed.
+// Roles (640 threads, one persistent CTA per SM, clusters of two CTAs):
+//   warps 0..7   : mid team   (acc1 -> mid operand, two chunks in flight)
+//   warps 8..15  : final team (acc2 + residual -> x, operand planes)
+//   warp 16 / 17 / 18, one lane each: TMA producers (residual slabs, activation halo tiles, W7 / W1 weight ring)
+//   warp 19 / one lane: tcgen05.mma issuer (highest warp id: the scheduler favours it over the polling teams)
+// TMEM plans (512 columns):
+//   C =  96: acc1 x2 + acc2 x2 (96 columns each); the 1x1 conv of tile i-1 is issued after the k7 conv of tile i (SKEW 1)
+//   C = 192: acc1 x2 (384) + ONE 96-column acc2: the 1x1 conv runs as two N halves between the halves of the next k7 conv
+//   C = 384: ONE acc1 (384, the k7 conv is issued as two N = 192 MMAs per step) + two 64-column acc2 buffers: the 1x1
+//            conv runs as six N chunks that ping-pong between them (the final team drains chunk n while chunk n+1 is
+//            accumulated); no skew -- the tensor pipe idles only while the first mid chunks are converted.
 #include <algorithm>
 #include <cstdlib>
 #include <vector>
@@ -69,35 +72,47 @@ constexpr int kRuTraceEvents = 32, kRuTraceTiles = 16;
 
 template <int C, int NTERMS, int PG>   // PG = CTAs sharing one MMA (1, or 2 = cta_group::2 pair)
 struct RuCfg {
+  static constexpr bool WIDE = C > 256;                            // C = 384: one acc1, k7 conv as two N halves
   static constexpr int kPlanes = NTERMS == 3 ? 2 : 1;
   static constexpr int kChunks = C / 32;                           // K chunks of 32 channels
-  static constexpr int G = NTERMS == 3 ? 1 : (C == 96 ? 3 : 2);   // K chunks per ring stage
+  static constexpr int G = (NTERMS == 3 || WIDE) ? 1 : (C == 96 ? 3 : 2);   // K chunks per ring stage (k7 conv)
   static constexpr int kGroups = kChunks / G;
   static constexpr int kAStage = G * kPlanes * kRuAChunkBytes;
+  static constexpr int KN = WIDE ? 2 : 1;                          // N halves of the k7 conv (UMMA N <= 256)
+  static constexpr int N7 = C / KN;                                // N of one k7 MMA
   static constexpr int kWChunk = (C / PG) * 64;                    // C / PG rows x 64 B (one plane): a CTA pair splits the N rows
   static constexpr int kWStage = G * kPlanes * kWChunk;
-  // TMEM plan.  acc1 (k7 result, then the converted mid operand) is double buffered at both widths, and the 1x1 conv
-  // of tile i - 1 is issued AFTER (part of) the k7 conv of tile i (SKEW = 1), so the tensor pipe never waits for the
+  // TMEM plan.  C <= 192: acc1 (k7 result, then the converted mid operand) is double buffered and the 1x1 conv of
+  // tile i - 1 is issued AFTER (part of) the k7 conv of tile i (SKEW = 1), so the tensor pipe never waits for the
   // mid stage.  C = 96: two 96-column acc2 buffers (4 x 96 = 384 columns).  C = 192: 2 x 192 columns of acc1 leave
-  // 128, so the 1x1 conv runs as TWO N halves through ONE 96-column accumulator (SPLIT); the halves are issued
-  // between the two halves of the next tile's k7 conv, which gives the final team time to drain the first one.
+  // 128, so the 1x1 conv runs as TWO N halves through ONE 96-column accumulator; the halves are issued between the
+  // two halves of the next tile's k7 conv, which gives the final team time to drain the first one.  C = 384: acc1
+  // alone takes 384 columns (single buffer, SKEW = 0); the 1x1 conv runs as SIX 64-column N chunks through TWO
+  // accumulators, so the final team drains chunk n while the tensor cores accumulate chunk n + 1.
   static constexpr bool SPLIT = C > 96;
-  static constexpr int NB1 = 2;
-  static constexpr int NH = SPLIT ? 2 : 1;                         // N halves of the 1x1 conv
+  static constexpr int NB1 = WIDE ? 1 : 2;
+  static constexpr int NH = WIDE ? 6 : (SPLIT ? 2 : 1);            // N chunks of the 1x1 conv
   static constexpr int N2 = C / NH;                                // accumulator width of the 1x1 conv
-  static constexpr int NB2 = SPLIT ? 1 : 2;
-  static constexpr int SKEW = 1;
-  static constexpr int kW1Stage = G * kPlanes * (N2 / PG) * 64;    // bytes of a W1 stage in this CTA (chunk stride stays kWChunk)
+  static constexpr int NB2 = WIDE ? 2 : (SPLIT ? 1 : 2);
+  static constexpr int SKEW = WIDE ? 0 : 1;
+  // W1 ring stages.  C <= 192: one stage per K group, chunk stride = the W7 chunk stride.  C = 384: a chunk is only
+  // N2 / PG = 32 or 64 rows, so a stage carries G1 = 6 K chunks (compact) -- 12 stages per tile instead of 72.
+  static constexpr int G1 = WIDE ? 6 : G;
+  static constexpr int kGroups1 = kChunks / G1;
+  static constexpr int kW1Chunk = WIDE ? (N2 / PG) * 64 : kWChunk;                 // chunk stride (one plane) inside a W1 stage
+  static constexpr int kW1Stage = G1 * kPlanes * (N2 / PG) * 64;                    // bytes of a W1 stage in this CTA
   // ring depths (227 KB budget)
   static constexpr int SA = (NTERMS == 3) ? 2 : (C <= 96 ? 2 : 3);
   // Output side of the final stage.  Every 32-column chunk ends with TMA stores (x slab + operand planes) issued by
   // one thread; the team may run kOutSlots - 2 chunks ahead of the stores' shared-memory reads.  C = 96 has
   // shared memory to spare, so it gets three staging slots and a fourth residual slab (worth 1-2 %: its limit is
   // the tensor pipe itself, whose N = 96 MMAs take 56 instead of 48 cycles reading operands from shared memory,
-  // plus ~20 % weight-ring waits).  C = 192 keeps the shared memory for the weight ring.
+  // plus ~20 % weight-ring waits).  C = 192 keeps the shared memory for the weight ring.  C = 384: BOTH epilogue
+  // teams run the final stage on alternate 32-column chunks (the 1x1 phase is not overlapped with a k7 conv there,
+  // so the drain rate is what the tensor pipe waits for): one staging slot and two residual slabs per team.
   static constexpr int kOutSlots = C <= 96 ? 3 : 2;
-  static constexpr int SR = C <= 96 ? 4 : 3;
-  static constexpr int kParBytes = 3 * C * 4;
+  static constexpr int SR = (C <= 96 || WIDE) ? 4 : 3;   // WIDE: two slabs per epilogue team (slot parity = team)
+  static constexpr int kParBytes = (WIDE ? 6 : 3) * C * 4;   // WIDE also keeps bias1 / alpha_out / inv_out in shared memory
   static constexpr int kStageOut = kOutSlots * kPlanes * kRuPlaneTile;   // staging of the operand-plane TMA stores
   static constexpr int kFixed = SA * kAStage + SR * kRuSlabBytes + kStageOut + kParBytes + 1024 /* barriers */ +
                                 1024 /* alignment */;
@@ -109,10 +124,13 @@ struct RuCfg {
                                     kNumBars * 8 + 16 + 1024 /* alignment */;
   static_assert(kNumBars * 8 + 16 <= 1024, "barrier block larger than budgeted");
   static_assert(SW >= 3, "weight ring too shallow");
-  static_assert(kChunks % G == 0, "K groups must tile the channels");
+  static_assert(kChunks % G == 0 && kChunks % G1 == 0, "K groups must tile the channels");
+  static_assert(kW1Stage <= kWStage, "a W1 stage must fit a ring slot");
   static_assert(NB1 * C + NB2 * N2 <= 512, "accumulators must fit TMEM");
+  static_assert(N7 <= 256 && N7 % 16 == 0 && N2 % 16 == 0, "UMMA N range");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
-  static_assert(kWChunk % 1024 == 0, "weight chunks must stay 1024 B aligned");
+  static_assert(kWChunk % 1024 == 0 && kW1Chunk % 1024 == 0 && ((N7 / PG) * 64) % 1024 == 0,
+                "weight chunks must stay 1024 B aligned");
 };
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -120,7 +138,8 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat162 v) { return *reinterpret_cast<uint32_t*>(&v); }
 // event trace of CTA 0 (debug builds of the schedule; dbg is null in normal runs)
 __device__ __forceinline__ void ru_trace(const RuParams& p, int tile_it, int ev) {
-  if (p.dbg && blockIdx.x == 0 && tile_it < kRuTraceTiles) p.dbg[tile_it * kRuTraceEvents + ev] = clock64();
+  if (p.dbg && blockIdx.x == 0 && tile_it < kRuTraceTiles && ev < kRuTraceEvents - 5)
+    p.dbg[tile_it * kRuTraceEvents + ev] = clock64();
 }
 
 // mbar_wait that adds the cycles spent waiting to `acc` when tracing (schedule debugging)
@@ -143,7 +162,10 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
   using Cfg = RuCfg<C, NTERMS, PG>;
   constexpr int SA = Cfg::SA, SW = Cfg::SW, SR = Cfg::SR, NB1 = Cfg::NB1, NB2 = Cfg::NB2;
   constexpr int G = Cfg::G, SKEW = Cfg::SKEW, NMID = Cfg::kNumMid, NH = Cfg::NH, N2 = Cfg::N2;
-  constexpr int KG1 = Cfg::SPLIT ? (Cfg::kGroups + 1) / 2 : Cfg::kGroups;   // k7 K groups issued before the first 1x1 half
+  constexpr int KN = Cfg::KN, N7 = Cfg::N7, G1 = Cfg::G1;
+  constexpr int RB7 = N7 / CL;                         // W7 rows one CTA fetches per N half and stage (= TMA box rows)
+  // k7 K groups issued before the first 1x1 half (skewed C = 192 schedule only)
+  constexpr int KG1 = (Cfg::SPLIT && SKEW == 1) ? (Cfg::kGroups + 1) / 2 : Cfg::kGroups;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;
@@ -196,6 +218,11 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
     s_par[i] = __ldg(p.bias7 + i);
     s_par[C + i] = __ldg(p.alpha_mid + i);
     s_par[2 * C + i] = __ldg(p.inv_mid + i);
+    if (Cfg::WIDE) {   // the final stage is on the tensor pipe's critical path there: no global loads inside a chunk
+      s_par[3 * C + i] = __ldg(p.bias1 + i);
+      s_par[4 * C + i] = p.out_hi ? __ldg(p.alpha_out + i) : 0.f;
+      s_par[5 * C + i] = p.out_hi ? __ldg(p.inv_out + i) : 0.f;
+    }
   }
   if (warp == kRuTmaWWarp && lane == 0) {
     prefetch_tmap(&tm_a_hi);
@@ -210,7 +237,8 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
     for (int s = 0; s < SW; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), PAIR ? 1 : CL); }
     for (int s = 0; s < NMID; ++s) mbar_init(mid_full(0, s), PG);   // one arrive per CTA (after a named barrier of the 4 warps that converted the chunk)
     for (int s = 0; s < NB1; ++s) mbar_init(acc1_full(s), 1);
-    for (int s = 0; s < NB2; ++s) { mbar_init(acc2_full(s), 1); mbar_init(acc2_empty(s), PG); }
+    // acc2 is handed back by one thread per final-stage team and CTA (WIDE: both teams drain every accumulator)
+    for (int s = 0; s < NB2; ++s) { mbar_init(acc2_full(s), 1); mbar_init(acc2_empty(s), PG * (Cfg::WIDE ? 2 : 1)); }
     for (int s = 0; s < SR; ++s) { mbar_init(res_full(s), 1); mbar_init(res_empty(s), 1); }
     fence_barrier_init();
   }
@@ -268,11 +296,17 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
     if (elect_one()) {
       uint32_t ws = 0, wph = 0;
       constexpr uint16_t mask = (uint16_t)((1u << CL) - 1u);
-      const uint32_t mc_off = (uint32_t)(cl_rank * (C / CL)) * 64u;
+      // W7 chunk of one stage: KN N halves of N7 rows.  Pair: this CTA holds rows [h N7 + rank RB7, +RB7) of half h at
+      // chunk offset h RB7 rows (the tensor cores read the other RB7 rows of the half from the peer).  Multicast:
+      // it fetches the same rows but writes them at their absolute row offset into BOTH CTAs' full-height chunks.
       auto load_w = [&](uint32_t dst, const CUtensorMap* map, uint32_t bar, int k0) {
-        if (PAIR) tma_load_2d_cg2(dst, map, lead(bar), k0, cl_rank * (C / CL));
-        else if (CL > 1) tma_load_2d_mc(dst + mc_off, map, bar, k0, cl_rank * (C / CL), mask);
-        else tma_load_2d(dst, map, bar, k0, 0);
+#pragma unroll
+        for (int h = 0; h < KN; ++h) {
+          const int row = h * N7 + cl_rank * RB7;
+          if (PAIR) tma_load_2d_cg2(dst + (uint32_t)(h * RB7) * 64u, map, lead(bar), k0, row);
+          else if (CL > 1) tma_load_2d_mc(dst + (uint32_t)row * 64u, map, bar, k0, row, mask);
+          else tma_load_2d(dst + (uint32_t)row * 64u, map, bar, k0, row);
+        }
       };
       const uint32_t mc1_off = (uint32_t)(cl_rank * (N2 / CL)) * 64u;
       auto load_w1 = [&](uint32_t dst, const CUtensorMap* map, uint32_t bar, int k0, int half) {
@@ -297,22 +331,27 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
         }
       };
       auto w1_half = [&](int half) {
-        for (int kg = 0; kg < Cfg::kGroups; ++kg) {
+        for (int kg = 0; kg < Cfg::kGroups1; ++kg) {
           mbar_wait(w_empty(ws), wph ^ 1u);
           if (leader) mbar_expect_tx(w_full(ws), PG * Cfg::kW1Stage);
 #pragma unroll
-          for (int g = 0; g < G; ++g) {
-            const uint32_t sw = w_base + ws * Cfg::kWStage + (uint32_t)(g * Cfg::kPlanes) * Cfg::kWChunk;
-            load_w1(sw, &tm_w1_hi, w_full(ws), (kg * G + g) * 32, half);
-            if (NTERMS == 3) load_w1(sw + Cfg::kWChunk, &tm_w1_lo, w_full(ws), (kg * G + g) * 32, half);
+          for (int g = 0; g < G1; ++g) {
+            const uint32_t sw = w_base + ws * Cfg::kWStage + (uint32_t)(g * Cfg::kPlanes) * Cfg::kW1Chunk;
+            load_w1(sw, &tm_w1_hi, w_full(ws), (kg * G1 + g) * 32, half);
+            if (NTERMS == 3) load_w1(sw + Cfg::kW1Chunk, &tm_w1_lo, w_full(ws), (kg * G1 + g) * 32, half);
           }
           if (++ws == SW) { ws = 0; wph ^= 1u; }
         }
       };
-      // same order as the MMA issuer: k7 groups [0, KG1) of tile it, 1x1 half 0 of tile it - 1, the remaining k7
-      // groups, 1x1 half 1 (SPLIT only)
+      // same order as the MMA issuer.  Skewed (C <= 192): k7 groups [0, KG1) of tile it, 1x1 half 0 of tile it - 1,
+      // the remaining k7 groups, 1x1 half 1 (C = 192 only).  Un-skewed (C = 384): k7 conv of tile it, then its NH
+      // 1x1 chunks.
       for (int it = 0; it < n_my + SKEW; ++it) {
         if (it < n_my) w7_groups(0, KG1);
+        if (SKEW == 0) {
+          for (int nh = 0; nh < NH; ++nh) w1_half(nh);
+          continue;
+        }
         if (it >= SKEW) w1_half(0);
         if (it < n_my) w7_groups(KG1, Cfg::kGroups);
         if (NH > 1 && it >= SKEW) w1_half(1);
@@ -322,7 +361,7 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
     // ================================ MMA issuer ================================
     // pair mode: the leader's thread issues the M = 256 MMAs for both CTAs
     if (leader && elect_one()) {
-      constexpr uint32_t idesc = PAIR ? make_idesc_cg2<C>() : make_idesc<C>();
+      constexpr uint32_t idesc = PAIR ? make_idesc_cg2<N7>() : make_idesc<N7>();   // one k7 MMA covers N7 columns
       auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t accumulate) {
         if (PAIR) umma_bf16_cg2(d, a, b, idesc, accumulate);
         else umma_bf16(d, a, b, idesc, accumulate);
@@ -360,16 +399,22 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
 #pragma unroll
             for (int g = 0; g < G; ++g) {
               const uint64_t a_hi = make_smem_desc<32>(sa + (uint32_t)(g * Cfg::kPlanes) * kRuAChunkBytes + a_off);
-              const uint64_t w_hi = make_smem_desc<32>(sw + (uint32_t)(g * Cfg::kPlanes) * Cfg::kWChunk);
+              const uint64_t a_lo = make_smem_desc<32>(sa + (uint32_t)(g * Cfg::kPlanes + 1) * kRuAChunkBytes + a_off);
 #pragma unroll
-              for (int k = 0; k < 2; ++k) mma(d1, a_hi + 2 * k, w_hi + 2 * k, (kg | j | g | k) != 0);
-              if (NTERMS == 3) {
-                const uint64_t a_lo = make_smem_desc<32>(sa + (uint32_t)(g * Cfg::kPlanes + 1) * kRuAChunkBytes + a_off);
-                const uint64_t w_lo = make_smem_desc<32>(sw + (uint32_t)(g * Cfg::kPlanes + 1) * Cfg::kWChunk);
+              for (int h = 0; h < KN; ++h) {   // N halves of the k7 conv: B rows [h N7, +N7) -> accumulator columns [h N7, +N7)
+                // rows of half h inside a chunk: pair h * N7 / 2 (this CTA's share), otherwise h * N7
+                const uint32_t hoff = (uint32_t)(h * (N7 / PG)) * 64u;
+                const uint32_t dh = d1 + (uint32_t)(h * N7);
+                const uint64_t w_hi = make_smem_desc<32>(sw + (uint32_t)(g * Cfg::kPlanes) * Cfg::kWChunk + hoff);
 #pragma unroll
-                for (int k = 0; k < 2; ++k) mma(d1, a_lo + 2 * k, w_hi + 2 * k, 1u);
+                for (int k = 0; k < 2; ++k) mma(dh, a_hi + 2 * k, w_hi + 2 * k, (kg | j | g | k) != 0);
+                if (NTERMS == 3) {
+                  const uint64_t w_lo = make_smem_desc<32>(sw + (uint32_t)(g * Cfg::kPlanes + 1) * Cfg::kWChunk + hoff);
 #pragma unroll
-                for (int k = 0; k < 2; ++k) mma(d1, a_hi + 2 * k, w_lo + 2 * k, 1u);
+                  for (int k = 0; k < 2; ++k) mma(dh, a_lo + 2 * k, w_hi + 2 * k, 1u);
+#pragma unroll
+                  for (int k = 0; k < 2; ++k) mma(dh, a_hi + 2 * k, w_lo + 2 * k, 1u);
+                }
               }
             }
             commit_w(w_empty(ws));
@@ -395,25 +440,25 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
         if (half == 0) ru_trace(p, jt, 2);
         const uint32_t mid_tmem = tmem_base + (uint32_t)(jt % NB1) * C;   // acc1 buffer of tile jt, converted in place
         const uint32_t mid_par = (uint32_t)(jt / NB1) & 1u;
-        for (int kg = 0; kg < Cfg::kGroups; ++kg) {
+        for (int kg = 0; kg < Cfg::kGroups1; ++kg) {
           mbar_wait_t(w_full(ws), wph, timed, ww1);
           const uint32_t sw = w_base + ws * Cfg::kWStage;
 #pragma unroll
-          for (int g = 0; g < G; ++g) {
-            const int kc = kg * G + g;
+          for (int g = 0; g < G1; ++g) {
+            const int kc = kg * G1 + g;
             if (half == 0) {
               mbar_wait_t(mid_full(jt % NB1, kc), mid_par, timed, wm);
-              ru_trace(p, jt, 3 + kc);
+              if (kc < 6) ru_trace(p, jt, 3 + kc);
             }
             tc_fence_after();
             // A operand in tensor memory: lane = row, 16 K values = 8 columns of packed bf16 pairs
             const uint32_t a_hi = mid_tmem + (uint32_t)kc * 32u;
-            const uint64_t w_hi = make_smem_desc<32>(sw + (uint32_t)(g * Cfg::kPlanes) * Cfg::kWChunk);
+            const uint64_t w_hi = make_smem_desc<32>(sw + (uint32_t)(g * Cfg::kPlanes) * Cfg::kW1Chunk);
 #pragma unroll
             for (int k = 0; k < 2; ++k) mma_ts(d2, a_hi + 8 * k, w_hi + 2 * k, (kg | g | k) != 0);
             if (NTERMS == 3) {
               const uint32_t a_lo = a_hi + 16u;
-              const uint64_t w_lo = make_smem_desc<32>(sw + (uint32_t)(g * Cfg::kPlanes + 1) * Cfg::kWChunk);
+              const uint64_t w_lo = make_smem_desc<32>(sw + (uint32_t)(g * Cfg::kPlanes + 1) * Cfg::kW1Chunk);
 #pragma unroll
               for (int k = 0; k < 2; ++k) mma_ts(d2, a_lo + 8 * k, w_hi + 2 * k, 1u);
 #pragma unroll
@@ -434,6 +479,10 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
       };
       for (int it = 0; it < n_my + SKEW; ++it) {
         if (it < n_my) k7_groups(it, 0, KG1);
+        if (SKEW == 0) {   // C = 384: the tile's own 1x1 chunks follow its k7 conv (single acc1 buffer)
+          for (int nh = 0; nh < NH; ++nh) one_by_one(it, nh);
+          continue;
+        }
         if (it >= SKEW) one_by_one(it - SKEW, 0);
         if (it < n_my && KG1 < Cfg::kGroups) k7_groups(it, KG1, Cfg::kGroups);
         if (NH > 1 && it >= SKEW) one_by_one(it - SKEW, 1);
@@ -517,7 +566,7 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
         // arrives (a cluster-scope release arrive by every thread costs thousands of cycles in pair mode)
         asm volatile("bar.sync %0, 128;" ::"r"(2 + sub) : "memory");
         if (group == 0 && lane == 0) arrive_lead(mid_full(buf, ci));
-        if (group == 0 && lane == 0) ru_trace(p, it, 11 + ci);
+        if (group == 0 && lane == 0 && ci < 6) ru_trace(p, it, 11 + ci);
       }
     };
 
@@ -636,20 +685,134 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
         }
         if (++rs == SR) { rs = 0; rph ^= 1u; }
         if (++out_slot == (uint32_t)Cfg::kOutSlots) out_slot = 0;
-        if (warp == kRuFinWarp0 && lane == 0) ru_trace(p, jt, 21 + c / 32);
+        if (warp == kRuFinWarp0 && lane == 0 && c < 192) ru_trace(p, jt, 21 + c / 32);
       }
       }
     };
 
+    // ---- C = 384: final stage of ONE 32-column chunk `ci` of tile `jt`, run by team `tm` (chunks alternate between the
+    // two teams, so two chunks drain at once: here the 1x1 phase is not hidden behind a k7 conv -- single acc1 buffer --
+    // and the tensor pipe waits for whatever the drain does not keep up with).  Same data path as final_stage; one
+    // staging slot and two residual slabs (slots of the team's parity) per team.
+    const int tm = warp >> 3;                            // 0 / 1
+    const bool wstorer = (warp & 7) == 0 && lane == 0;   // one TMA-store thread per team
+    int wprev_rs = -1;
+    auto wide_final_chunk = [&](int jt, int ci) {
+      const int tile = tile_of(jt);
+      const int b = tile_b(tile), l0 = tile_l0(tile);
+      const bool has_out = p.out_hi != nullptr;
+      const int nh = ci >> 1, cc = (ci & 1) * 32, c = ci * 32;
+      const uint32_t u = (uint32_t)jt * NH + (uint32_t)nh;
+      const uint32_t q = (uint32_t)jt * Cfg::kChunks + (uint32_t)ci;     // running chunk number -> residual ring slot
+      const uint32_t rs_ = q % SR, rph_ = (q / SR) & 1u;
+      mbar_wait(acc2_full(u % NB2), (u / NB2) & 1u);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(group * 32) << 16) + (uint32_t)(NB1 * C) + (u % NB2) * N2;
+      uint32_t r[16];
+      tmem_ld_x16(t_row + cc + 16 * half, r);
+      tmem_ld_wait();
+      tc_fence_before();
+      asm volatile("bar.sync %0, %1;" ::"r"(6 + tm), "n"(kRuTeamThreads) : "memory");   // the team has drained its 32 columns
+      if (wstorer) arrive_lead(acc2_empty(u % NB2));
+      const uint32_t slab = res_base + rs_ * kRuSlabBytes;
+      const uint32_t st_hi = out_base + (uint32_t)tm * (uint32_t)(Cfg::kPlanes * kRuPlaneTile);
+      const uint32_t st_lo = st_hi + kRuPlaneTile;
+      mbar_wait(res_full(rs_), rph_);
+      uint8_t* const slab_row = smem_raw + (slab - smem_u32(smem_raw)) + (size_t)row_in_tile * 128;
+      uint8_t* const hi_row = smem_raw + (st_hi - smem_u32(smem_raw)) + (size_t)row_in_tile * 64;
+      uint8_t* const lo_row = smem_raw + (st_lo - smem_u32(smem_raw)) + (size_t)row_in_tile * 64;
+      const uint32_t swz64 = (uint32_t)(row_in_tile >> 1) & 3u;
+      const int n0 = c + 16 * half;
+      float4 v[4], b4[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[j] = *reinterpret_cast<const float4*>(slab_row + ((((uint32_t)(4 * half + j)) ^ ((uint32_t)row_in_tile & 7u)) << 4));
+        b4[j] = *reinterpret_cast<const float4*>(s_par + 3 * C + n0 + 4 * j);
+      }
+      // this chunk's slab is not the one the team's previous store is still reading: the new x goes in right away
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[j].x = (__uint_as_float(r[4 * j + 0]) + v[j].x) + b4[j].x;
+        v[j].y = (__uint_as_float(r[4 * j + 1]) + v[j].y) + b4[j].y;
+        v[j].z = (__uint_as_float(r[4 * j + 2]) + v[j].z) + b4[j].z;
+        v[j].w = (__uint_as_float(r[4 * j + 3]) + v[j].w) + b4[j].w;
+        *reinterpret_cast<float4*>(slab_row + ((((uint32_t)(4 * half + j)) ^ ((uint32_t)row_in_tile & 7u)) << 4)) = v[j];
+      }
+      // Snake + bf16 split into registers FIRST: the team's one staging slot may still be read by its previous TMA
+      // stores, and that read latency hides behind this arithmetic
+      uint4 hp[2], lp[2];
+      if (has_out) {
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          uint32_t* hpp = reinterpret_cast<uint32_t*>(&hp[jj]);
+          uint32_t* lpp = reinterpret_cast<uint32_t*>(&lp[jj]);
+          float4 a4[2], i4[2];
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            a4[h2] = *reinterpret_cast<const float4*>(s_par + 4 * C + n0 + 4 * (2 * jj + h2));
+            i4[h2] = *reinterpret_cast<const float4*>(s_par + 5 * C + n0 + 4 * (2 * jj + h2));
+          }
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const int j = 2 * jj + h2;
+            const float s0 = snake_sel<NTERMS == 3>(v[j].x, a4[h2].x, i4[h2].x), s1 = snake_sel<NTERMS == 3>(v[j].y, a4[h2].y, i4[h2].y);
+            const float s2 = snake_sel<NTERMS == 3>(v[j].z, a4[h2].z, i4[h2].z), s3 = snake_sel<NTERMS == 3>(v[j].w, a4[h2].w, i4[h2].w);
+            const __nv_bfloat162 h0 = __floats2bfloat162_rn(s0, s1), h1 = __floats2bfloat162_rn(s2, s3);
+            hpp[2 * h2] = pack_bf16(h0);
+            hpp[2 * h2 + 1] = pack_bf16(h1);
+            if (NTERMS == 3) {
+              const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+              lpp[2 * h2] = pack_bf16(__floats2bfloat162_rn(s0 - f0.x, s1 - f0.y));
+              lpp[2 * h2 + 1] = pack_bf16(__floats2bfloat162_rn(s2 - f1.x, s3 - f1.y));
+            }
+          }
+        }
+      }
+      // the team's previous stores have finished READING its staging slot and its previous residual slab
+      if (wstorer) {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (wprev_rs >= 0) mbar_arrive(res_empty(wprev_rs));
+      }
+      asm volatile("bar.sync %0, %1;" ::"r"(10 + tm), "n"(kRuTeamThreads) : "memory");   // staging slot free for everyone
+      if (has_out) {
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const uint32_t off = (((uint32_t)(2 * half + jj)) ^ swz64) << 4;   // SWIZZLE_64B box layout
+          *reinterpret_cast<uint4*>(hi_row + off) = hp[jj];
+          if (NTERMS == 3) *reinterpret_cast<uint4*>(lo_row + off) = lp[jj];
+        }
+      }
+      fence_proxy_async();   // generic-proxy writes -> visible to the TMA unit's async-proxy reads
+      asm volatile("bar.sync %0, %1;" ::"r"(8 + tm), "n"(kRuTeamThreads) : "memory");
+      if (wstorer) {
+        tma_store_3d(&tm_res, slab, c, l0, b);
+        if (has_out) {
+          tma_store_3d(&tm_o_hi, st_hi, c, l0, b);
+          if (NTERMS == 3) tma_store_3d(&tm_o_lo, st_lo, c, l0, b);
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        wprev_rs = (int)rs_;
+      }
+    };
+
     const int sub = (warp - kRuMidWarp0) >> 2;   // 0..1 mid team, 2..3 final team
-    // the teams work on different tiles at the same time: mid of tile i, final of tile i - 1
-    static_assert(SKEW == 1, "the epilogue teams assume the skewed schedule");
-    if (!fin_team) {
-      for (int it = 0; it < n_my; ++it) mid_stage(it, sub, 2);
+    if (Cfg::WIDE) {
+      // C = 384 (un-skewed, single acc1): all 16 warps convert the mid chunks of tile it (4 chunks in flight), then
+      // both teams drain the 1x1 accumulators on alternate chunks
+      for (int it = 0; it < n_my; ++it) {
+        mid_stage(it, sub, 4);
+        for (int ci = tm; ci < Cfg::kChunks; ci += 2) wide_final_chunk(it, ci);
+      }
+      if (wstorer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output stores have landed
     } else {
-      for (int jt = 0; jt < n_my; ++jt) final_stage(jt);
+      // the teams work on different tiles at the same time: mid of tile i, final of tile i - 1
+      if (!fin_team) {
+        for (int it = 0; it < n_my; ++it) mid_stage(it, sub, 2);
+      } else {
+        for (int jt = 0; jt < n_my; ++jt) final_stage(jt);
+      }
+      if (storer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output stores have landed
     }
-    if (storer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output stores have landed
   }
 
   tc_fence_before();
@@ -691,7 +854,7 @@ int launch_ru(const GemmWeights& c7, const GemmWeights& c1, const OpBuf& a, int 
   for (int i = 0; i < 2; ++i) {
     const uint64_t wd[2] = {(uint64_t)gw[i]->kt * C, (uint64_t)C};
     const uint64_t ws[1] = {(uint64_t)gw[i]->kt * C * 2};
-    const uint32_t wb[2] = {32u, (uint32_t)((i == 0 ? C : Cfg::N2) / CL)};
+    const uint32_t wb[2] = {32u, (uint32_t)((i == 0 ? Cfg::N7 : Cfg::N2) / CL)};
     SC_TRY(encode_tmap(&tw[2 * i], gw[i]->w_hi, 2, wd, ws, wb, 64, true, false));
     SC_TRY(encode_tmap(&tw[2 * i + 1], NTERMS == 3 ? gw[i]->w_lo : gw[i]->w_hi, 2, wd, ws, wb, 64, true, false));
   }
@@ -752,13 +915,15 @@ int launch_ru(const GemmWeights& c7, const GemmWeights& c1, const OpBuf& a, int 
 }  // namespace
 
 // k7 conv (single phase, 7 taps at multiples of one dilation <= 9) followed by a 1x1 conv, both C -> C with
-// C in {96, 192}: the shapes of the last two WaveGenerator stages.
+// C in {96, 192, 384}: the shapes of the last three WaveGenerator stages (C = 768 would need 768 accumulator
+// columns of tensor memory; that stage keeps its two kernels).
 bool resunit_fusable(const GemmWeights& c7, const GemmWeights& c1, int* dil) {
   const int C = c7.c_in;
-  if (C != 96 && C != 192) return false;
+  static const int no_wide = [] { const char* e = getenv("SPARKCODEC_RU_WIDE"); return e && atoi(e) == 0; }();
+  if (C != 96 && C != 192 && !(C == 384 && !no_wide)) return false;
   if (c7.n_total != C || c1.c_in != C || c1.n_total != C) return false;
   if (c7.taps.n_phase != 1 || c7.taps.ntaps[0] != 7 || c1.taps.n_phase != 1 || c1.taps.ntaps[0] != 1) return false;
-  if (c1.taps.shift[0][0] != 0 || c7.block_n != C || c1.block_n != C) return false;
+  if (c1.taps.shift[0][0] != 0) return false;
   const int d = c7.taps.shift[0][4] - c7.taps.shift[0][3];
   if (d < 1 || kBlockM + 6 * d > kRuHaloRowsMax) return false;
   for (int j = 0; j < 7; ++j)
@@ -806,6 +971,11 @@ int launch_resunit_fused(const GemmWeights& c7, const GemmWeights& c1, const OpB
                      : launch_ru<CC, NT, 1, false>(c7, c1, a, batch, L, p, num_sms, stream)
   if (c7.c_in == 96) {
     if (f32) { RU_DISPATCH(96, 3); } else { RU_DISPATCH(96, 1); }
+  }
+  if (c7.c_in == 384) {
+    // fp32 mode: only the CTA pair fits (a full-height 48 KB weight stage would leave a 1-deep ring)
+    if (f32) return launch_ru<384, 3, 2, true>(c7, c1, a, batch, L, p, num_sms, stream);
+    RU_DISPATCH(384, 1);
   }
   if (f32) { RU_DISPATCH(192, 3); } else { RU_DISPATCH(192, 1); }
 #undef RU_DISPATCH

@@ -171,3 +171,86 @@ def synthetic_features(cfg: BiCodecConfig, batch: int, frames: int, seed: int = 
     if frames > 1:
         x[:, 1:] = 0.6 * x[:, 1:] + 0.4 * x[:, :-1]
     return x.contiguous()
+
+
+def synthetic_speaker_state_dict(cfg: BiCodecConfig, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Encode-side tensors of the speaker half of ``BiCodec.tokenize`` (bicodec.py:162-167): the ECAPA-TDNN trunk up to
+    its ``latent`` output (ecapa_tdnn.py:152-214; the pooling / x-vector head is computed and thrown away by
+    ``SpeakerEncoder.tokenize``, so it is not part of this dict), the perceiver resampler (perceiver_encoder.py:297-350)
+    and the FSQ ``project_in`` (residual_fsq.py:66-68).  Own generator, like ``synthetic_encoder_state_dict``.
+    BatchNorm layers carry non-trivial running statistics; every bias / affine is perturbed."""
+    g = torch.Generator().manual_seed(seed + 104729)
+    sd: Dict[str, torch.Tensor] = {}
+    ch, width, F_in = 512, 64, cfg.num_mels
+
+    def bn(p, c):
+        sd[p + ".weight"] = 1.0 + _n(g, (c,), 0.1)
+        sd[p + ".bias"] = _n(g, (c,), 0.1)
+        sd[p + ".running_mean"] = _n(g, (c,), 0.1) + 0.3
+        sd[p + ".running_var"] = _u(g, (c,), 0.5, 1.5)
+        sd[p + ".num_batches_tracked"] = torch.tensor(100, dtype=torch.int64)
+
+    def conv(p, cout, cin, k, gain=1.4):
+        sd[p + ".weight"] = _n(g, (cout, cin, k), gain / (cin * k) ** 0.5)
+        sd[p + ".bias"] = _n(g, (cout,), 0.1)
+
+    e = "speaker_encoder.speaker_encoder"
+    conv(e + ".layer1.conv", ch, F_in, 5, gain=8.0)          # mel magnitudes of a 0.1-rms signal are ~0.1
+    bn(e + ".layer1.bn", ch)
+    for name in ("layer2", "layer3", "layer4"):
+        p = f"{e}.{name}.se_res2block"
+        conv(p + ".0.conv", ch, ch, 1)
+        bn(p + ".0.bn", ch)
+        for i in range(7):
+            conv(f"{p}.1.convs.{i}", width, width, 3)
+            bn(f"{p}.1.bns.{i}", width)
+        conv(p + ".2.conv", ch, ch, 1)
+        bn(p + ".2.bn", ch)
+        sd[p + ".3.linear1.weight"] = _n(g, (128, ch), 1.0 / ch ** 0.5)
+        sd[p + ".3.linear1.bias"] = _n(g, (128,), 0.1)
+        sd[p + ".3.linear2.weight"] = _n(g, (ch, 128), 1.0 / 128 ** 0.5)
+        sd[p + ".3.linear2.bias"] = _n(g, (ch,), 0.1)
+    conv(e + ".conv", 3 * ch, 3 * ch, 1)
+
+    s = "speaker_encoder.perceiver_sampler"
+    L, dim, inner = cfg.token_num, cfg.latent_dim, 512
+    sd[s + ".latents"] = _n(g, (L, dim), 0.5)
+    sd[s + ".proj_context.weight"] = _n(g, (dim, 3 * ch), 1.0 / (3 * ch) ** 0.5)
+    sd[s + ".proj_context.bias"] = _n(g, (dim,), 0.1)
+    ff_inner = int(dim * 4 * 2 / 3)
+    for i in range(2):
+        a = f"{s}.layers.{i}.0"
+        sd[a + ".to_q.weight"] = _n(g, (inner, dim), 2.0 / dim ** 0.5)
+        sd[a + ".to_kv.weight"] = _n(g, (2 * inner, dim), 2.0 / dim ** 0.5)
+        sd[a + ".to_out.weight"] = _n(g, (dim, inner), 1.0 / inner ** 0.5)
+        f = f"{s}.layers.{i}.1"
+        sd[f + ".0.weight"] = _n(g, (2 * ff_inner, dim), 1.0 / dim ** 0.5)
+        sd[f + ".0.bias"] = _n(g, (2 * ff_inner,), 0.1)
+        sd[f + ".2.weight"] = _n(g, (dim, ff_inner), 1.0 / ff_inner ** 0.5)
+        sd[f + ".2.bias"] = _n(g, (dim,), 0.1)
+    sd[s + ".norm.gamma"] = 1.0 + _n(g, (dim,), 0.1)
+    nl = len(cfg.fsq_levels)
+    sd["speaker_encoder.quantizer.project_in.weight"] = _n(g, (nl, dim), 1.2 / dim ** 0.5)
+    sd["speaker_encoder.quantizer.project_in.bias"] = _n(g, (nl,), 0.1)
+    return sd
+
+
+def synthetic_ref_wav(cfg: BiCodecConfig, batch: int, seconds: float = 6.0, seed: int = 777) -> torch.Tensor:
+    """(B, n) fp32 stand-in for the reference clip ``BiCodec.tokenize`` receives: a few drifting harmonics plus noise
+    per utterance (so that the mel frames differ along time and between utterances), rms ~ 0.1, n = the
+    ``get_ref_clip`` length (a multiple of latent_hop_length)."""
+    import math
+    g = torch.Generator().manual_seed(seed)
+    n = int(cfg.sample_rate * seconds) // cfg.latent_hop_length * cfg.latent_hop_length
+    t = torch.arange(n, dtype=torch.float32) / cfg.sample_rate
+    out = torch.zeros((batch, n))
+    for b in range(batch):
+        f0 = 90.0 + 160.0 * float(torch.rand((), generator=g))
+        vib = 1.0 + 0.03 * torch.sin(2 * math.pi * (3.0 + 2.0 * float(torch.rand((), generator=g))) * t)
+        phase = 2 * math.pi * torch.cumsum(f0 * vib, 0) / cfg.sample_rate
+        for k in range(1, 9):
+            out[b] += (0.6 ** k) * float(torch.rand((), generator=g) + 0.3) * torch.sin(k * phase)
+        env = 0.55 + 0.45 * torch.sin(2 * math.pi * (0.7 + float(torch.rand((), generator=g))) * t)
+        out[b] = out[b] * env + 0.05 * torch.randn(n, generator=g)
+        out[b] *= 0.1 / out[b].pow(2).mean().sqrt()
+    return out.contiguous()

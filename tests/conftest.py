@@ -42,3 +42,16 @@ def state_dict_with_encoder(cfg, state_dict):
     """The synthetic checkpoint plus the encode-side tensors of the semantic tokenize row."""
     from spark_tts_b200.synthetic import synthetic_encoder_state_dict
     return {**state_dict, **synthetic_encoder_state_dict(cfg, seed=0)}
+
+
+def speaker_golden_cases():
+    import glob
+    d = os.path.join(ROOT, "tests", "golden")
+    return sorted(glob.glob(os.path.join(d, "speaker_*.npz")))
+
+
+@pytest.fixture(scope="session")
+def state_dict_with_speaker(cfg, state_dict):
+    """The synthetic checkpoint plus every encode-side tensor (feature encoder + ECAPA / perceiver / FSQ project_in)."""
+    from spark_tts_b200.synthetic import synthetic_encoder_state_dict, synthetic_speaker_state_dict
+    return {**state_dict, **synthetic_encoder_state_dict(cfg, seed=0), **synthetic_speaker_state_dict(cfg, seed=0)}

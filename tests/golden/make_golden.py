@@ -20,10 +20,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 
 from oracle import bicodec_oracle as O                                          # noqa: E402
-from oracle.reference_loader import ReferenceDetokenizer, ReferenceSemanticTokenizer   # noqa: E402
+from oracle.reference_loader import (ReferenceDetokenizer, ReferenceSemanticTokenizer,   # noqa: E402
+                                     ReferenceSpeakerTokenizer)
 from spark_tts_b200.config import BiCodecConfig                     # noqa: E402
 from spark_tts_b200.synthetic import (synthetic_encoder_state_dict, synthetic_features,   # noqa: E402
-                                      synthetic_state_dict, synthetic_tokens)
+                                      synthetic_ref_wav, synthetic_speaker_state_dict, synthetic_state_dict,
+                                      synthetic_tokens)
 
 # name, batch, frames, token seed, semantic dtype, global dtype
 CASES = [
@@ -34,6 +36,8 @@ CASES = [
 ]
 WEIGHT_SEED = 0
 # semantic tokenize (encode side): name, batch, frames, feature seed
+# speaker tokenize (encode side): name, batch, clip seconds, waveform seed
+SPEAKER_CASES = [("a_b2_6s", 2, 6.0, 301), ("b_b1_1s", 1, 0.96, 302), ("c_b3_2s", 3, 2.0, 303)]
 TOKENIZE_CASES = [("a_b2_t60", 2, 60, 201), ("b_b1_t7", 1, 7, 202), ("c_b3_t1", 3, 1, 203), ("d_b1_t300", 1, 300, 204)]
 
 
@@ -77,6 +81,21 @@ def main():
                             feat_checksum=np.float64(feat.double().sum().item()),
                             semantic_tokens=idx.numpy(), margin=margin.numpy())
         print("tokenize", name, tuple(idx.shape), "min margin", float(margin.min()))
+    # speaker half of BiCodec.tokenize (bicodec.py:162-167) through the reference's mel transform + SpeakerEncoder;
+    # the clips are regenerated from the seed (synthetic_ref_wav), only the answers are stored
+    sd_spk = {**sd, **synthetic_speaker_state_dict(cfg, seed=WEIGHT_SEED)}
+    spk = ReferenceSpeakerTokenizer(cfg).load_checkpoint(sd_spk)
+    for name, B, seconds, seed in SPEAKER_CASES:
+        wav = synthetic_ref_wav(cfg, B, seconds, seed)
+        tokens = spk.tokenize(wav)
+        o_tokens, margin = O.tokenize_speaker(sd_spk, cfg, wav)
+        mel = spk.mel_transformer(wav.unsqueeze(1)).squeeze(1)
+        np.savez_compressed(os.path.join(out_dir, f"speaker_{name}.npz"), weight_seed=np.int64(WEIGHT_SEED),
+                            wav_seed=np.int64(seed), batch=np.int64(B), seconds=np.float64(seconds),
+                            wav_checksum=np.float64(wav.double().sum().item()), global_tokens=tokens.numpy(),
+                            margin=margin.numpy(), mel_first4=mel[:, :, :4].numpy())
+        print("speaker", name, tuple(tokens.shape), "oracle equal", bool(torch.equal(tokens, o_tokens)),
+              "min margin", float(margin.min()))
 
 
 if __name__ == "__main__":

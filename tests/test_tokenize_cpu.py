@@ -5,9 +5,9 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import tokenize_golden_cases
+from conftest import speaker_golden_cases, tokenize_golden_cases
 from oracle import bicodec_oracle as O
-from spark_tts_b200.synthetic import synthetic_features
+from spark_tts_b200.synthetic import synthetic_features, synthetic_ref_wav
 
 
 @pytest.mark.parametrize("path", tokenize_golden_cases(), ids=lambda p: p.split("tokenize_")[-1][:-4])
@@ -35,3 +35,69 @@ def test_vq_tokenize_inverts_detokenize_codes(cfg, state_dict_with_encoder):
     cbn = torch.nn.functional.normalize(cb)
     dist = enc.pow(2).sum(1, keepdim=True) - 2 * enc @ cbn.t() + cbn.pow(2).sum(1, keepdim=True).t()
     assert torch.equal((-dist).max(1)[1], k)
+
+
+# ---------------------------------------------------------------- speaker half (bicodec.py:162-167)
+@pytest.mark.parametrize("path", speaker_golden_cases(), ids=lambda p: p.split("speaker_")[-1][:-4])
+def test_oracle_speaker_tokenize_matches_reference_golden(path, cfg, state_dict_with_speaker):
+    """The restatement (torch.stft mel + ECAPA latent + perceiver + FSQ) reproduces the global tokens the reference's
+    own torchaudio MelSpectrogram + SpeakerEncoder.tokenize produced, bit for bit."""
+    g = np.load(path)
+    wav = synthetic_ref_wav(cfg, int(g["batch"]), float(g["seconds"]), int(g["wav_seed"]))
+    assert abs(wav.double().sum().item() - float(g["wav_checksum"])) < 1e-6
+    mel = O.mel_spectrogram(wav, cfg)
+    assert np.array_equal(mel[:, :, :4].numpy(), g["mel_first4"])               # same bits as torchaudio's transform
+    tokens, margin = O.tokenize_speaker(state_dict_with_speaker, cfg, wav)
+    assert tokens.dtype == torch.int32 and tuple(tokens.shape) == (int(g["batch"]), 1, cfg.token_num)
+    assert np.array_equal(tokens.numpy(), g["global_tokens"])
+    assert np.allclose(margin.numpy(), g["margin"], atol=1e-6)
+    assert int(tokens.min()) >= 0 and int(tokens.max()) < 4 ** len(cfg.fsq_levels)
+
+
+def test_speaker_goldens_exist_and_tokens_are_diverse():
+    cases = speaker_golden_cases()
+    assert len(cases) >= 3
+    for p in cases:
+        t = np.load(p)["global_tokens"]
+        assert len(np.unique(t)) > t.size // 3            # not a collapsed quantizer
+
+
+def test_fsq_quantize_is_the_inverse_of_the_detokenize_decode(cfg, state_dict_with_speaker):
+    """The reference's stated FSQ invariant (residual_fsq.py:430-432) on the index arithmetic: decoding an index to its
+    level codes (the detokenize side) and re-encoding the codes gives the index back."""
+    levels = cfg.fsq_levels
+    idx = torch.arange(0, 4 ** len(levels), 7, dtype=torch.int32)
+    codes = O.fsq_codes(idx.unsqueeze(0), levels)[0]                      # (n, 6) in {-1, -.5, 0, .5}
+    lv = torch.tensor(levels, dtype=torch.int32)
+    basis = torch.cumprod(torch.tensor([1] + list(levels[:-1])), dim=0).to(torch.int32)
+    back = ((codes * (lv // 2) + (lv // 2)) * basis).sum(-1).to(torch.int32)
+    assert torch.equal(back, idx)
+
+
+def test_ref_clip_and_volume_normalize_follow_the_reference():
+    """BiCodecTokenizer.get_ref_clip (audio_tokenizer.py:57-71) and audio_volume_normalize (utils/audio.py:33-74)."""
+    from spark_tts_b200.audio_tokenizer import BiCodecTokenizer, audio_volume_normalize
+    from spark_tts_b200.config import BiCodecConfig
+
+    class _M:                                                               # no GPU needed for the host-side helpers
+        cfg = BiCodecConfig()
+
+        def to(self, d):
+            return self
+    tok = BiCodecTokenizer(device="cuda", model=_M())
+    rng = np.random.default_rng(0)
+    long = rng.standard_normal(200000).astype(np.float32) * 0.05
+    clip = tok.get_ref_clip(long)
+    assert clip.shape == (96000,) and np.array_equal(clip, long[:96000])
+    short = rng.standard_normal(1000).astype(np.float32)
+    clip = tok.get_ref_clip(short)
+    assert clip.shape == (96000,) and np.array_equal(clip[:1000], short) and np.array_equal(clip[1000:2000], short)
+    try:
+        from oracle.reference_loader import _import_reference, reference_available
+        if reference_available():
+            _import_reference()
+            from sparktts.utils.audio import audio_volume_normalize as ref_norm
+            for sig in (long, long * 30, long * 0.01, short[:8]):
+                assert np.allclose(audio_volume_normalize(sig.copy()), ref_norm(sig.copy()), atol=0, rtol=0)
+    except ImportError:
+        pass                                                                # (soundfile / soxr absent: helper not importable)
