@@ -81,7 +81,13 @@ struct RuCfg {
   static constexpr int KN = WIDE ? 2 : 1;                          // N halves of the k7 conv (UMMA N <= 256)
   static constexpr int N7 = C / KN;                                // N of one k7 MMA
   static constexpr int kWChunk = (C / PG) * 64;                    // C / PG rows x 64 B (one plane): a CTA pair splits the N rows
-  static constexpr int kWStage = G * kPlanes * kWChunk;
+  // Taps of the k7 conv per weight-ring stage.  C = 96 in fp32 mode: a (tap, K chunk) stage is only 6 N = 96 MMAs
+  // (336 tensor-pipe cycles), less than what the single issuing thread spends per stage on the barrier wait, the
+  // descriptor arithmetic and the commit -- the kernel was ISSUE bound at ~67 cycles per 56-cycle MMA.  Four taps
+  // per stage (groups of 4 + 3) amortise that 3.5x.
+  static constexpr int TJ = (C == 96 && NTERMS == 3 && PG == 2) ? 4 : 1;   // (pair mode: 3 KB per plane and tap)
+  static constexpr int kWTap = G * kPlanes * kWChunk;              // bytes of one tap inside a stage
+  static constexpr int kWStage = TJ * kWTap;
   // TMEM plan.  C <= 192: acc1 (k7 result, then the converted mid operand) is double buffered and the 1x1 conv of
   // tile i - 1 is issued AFTER (part of) the k7 conv of tile i (SKEW = 1), so the tensor pipe never waits for the
   // mid stage.  C = 96: two 96-column acc2 buffers (4 x 96 = 384 columns).  C = 192: 2 x 192 columns of acc1 leave
@@ -97,7 +103,9 @@ struct RuCfg {
   static constexpr int SKEW = WIDE ? 0 : 1;
   // W1 ring stages.  C <= 192: one stage per K group, chunk stride = the W7 chunk stride.  C = 384: a chunk is only
   // N2 / PG = 32 or 64 rows, so a stage carries G1 = 6 K chunks (compact) -- 12 stages per tile instead of 72.
-  static constexpr int G1 = WIDE ? 6 : G;
+  // (C = 96 with four-tap stages: the whole W1 -- 3 chunks, 18 KB -- is ONE stage; as three stages it occupied the entire
+  // 3-slot ring during the 1x1 phase and the next tile's first W7 stage could not be prefetched.)
+  static constexpr int G1 = WIDE ? 6 : (TJ > 1 ? kChunks : G);
   static constexpr int kGroups1 = kChunks / G1;
   static constexpr int kW1Chunk = WIDE ? (N2 / PG) * 64 : kWChunk;                 // chunk stride (one plane) inside a W1 stage
   static constexpr int kW1Stage = G1 * kPlanes * (N2 / PG) * 64;                    // bytes of a W1 stage in this CTA
@@ -110,9 +118,11 @@ struct RuCfg {
   // plus ~20 % weight-ring waits).  C = 192 keeps the shared memory for the weight ring.  C = 384: BOTH epilogue
   // teams run the final stage on alternate 32-column chunks (the 1x1 phase is not overlapped with a k7 conv there,
   // so the drain rate is what the tensor pipe waits for): one staging slot and two residual slabs per team.
-  static constexpr int kOutSlots = C <= 96 ? 3 : 2;
+  // (C = 96 with four-tap weight stages: two staging slots, so that FOUR residual slabs still fit -- the slab of a
+  // chunk comes from HBM and has to be requested two chunks ahead, a late slab cost the final team 1.6k cycles a tile.)
+  static constexpr int kOutSlots = (C <= 96 && TJ == 1) ? 3 : 2;
   static constexpr int SR = (C <= 96 || WIDE) ? 4 : 3;   // WIDE: two slabs per epilogue team (slot parity = team)
-  static constexpr int kParBytes = (WIDE ? 6 : 3) * C * 4;   // WIDE also keeps bias1 / alpha_out / inv_out in shared memory
+  static constexpr int kParBytes = 6 * C * 4;   // bias7 | alpha_mid | inv_mid | bias1 | alpha_out | inv_out
   static constexpr int kStageOut = kOutSlots * kPlanes * kRuPlaneTile;   // staging of the operand-plane TMA stores
   static constexpr int kFixed = SA * kAStage + SR * kRuSlabBytes + kStageOut + kParBytes + 1024 /* barriers */ +
                                 1024 /* alignment */;
@@ -162,7 +172,7 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
   using Cfg = RuCfg<C, NTERMS, PG>;
   constexpr int SA = Cfg::SA, SW = Cfg::SW, SR = Cfg::SR, NB1 = Cfg::NB1, NB2 = Cfg::NB2;
   constexpr int G = Cfg::G, SKEW = Cfg::SKEW, NMID = Cfg::kNumMid, NH = Cfg::NH, N2 = Cfg::N2;
-  constexpr int KN = Cfg::KN, N7 = Cfg::N7, G1 = Cfg::G1;
+  constexpr int KN = Cfg::KN, N7 = Cfg::N7, G1 = Cfg::G1, TJ = Cfg::TJ;
   constexpr int RB7 = N7 / CL;                         // W7 rows one CTA fetches per N half and stage (= TMA box rows)
   // k7 K groups issued before the first 1x1 half (skewed C = 192 schedule only)
   constexpr int KG1 = (Cfg::SPLIT && SKEW == 1) ? (Cfg::kGroups + 1) / 2 : Cfg::kGroups;
@@ -218,11 +228,10 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
     s_par[i] = __ldg(p.bias7 + i);
     s_par[C + i] = __ldg(p.alpha_mid + i);
     s_par[2 * C + i] = __ldg(p.inv_mid + i);
-    if (Cfg::WIDE) {   // the final stage is on the tensor pipe's critical path there: no global loads inside a chunk
-      s_par[3 * C + i] = __ldg(p.bias1 + i);
-      s_par[4 * C + i] = p.out_hi ? __ldg(p.alpha_out + i) : 0.f;
-      s_par[5 * C + i] = p.out_hi ? __ldg(p.inv_out + i) : 0.f;
-    }
+    // the final stage is latency bound (one chunk in flight per team): no global loads inside a chunk
+    s_par[3 * C + i] = __ldg(p.bias1 + i);
+    s_par[4 * C + i] = p.out_hi ? __ldg(p.alpha_out + i) : 0.f;
+    s_par[5 * C + i] = p.out_hi ? __ldg(p.inv_out + i) : 0.f;
   }
   if (warp == kRuTmaWWarp && lane == 0) {
     prefetch_tmap(&tm_a_hi);
@@ -317,14 +326,17 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
       };
       auto w7_groups = [&](int g0, int g1) {
         for (int kg = g0; kg < g1; ++kg) {
-          for (int j = 0; j < 7; ++j) {
+          for (int j0 = 0; j0 < 7; j0 += TJ) {            // one stage = up to TJ consecutive taps of this K group
+            const int nt = 7 - j0 < TJ ? 7 - j0 : TJ;
             mbar_wait(w_empty(ws), wph ^ 1u);
-            if (leader) mbar_expect_tx(w_full(ws), PG * Cfg::kWStage);
+            if (leader) mbar_expect_tx(w_full(ws), (uint32_t)(PG * nt) * Cfg::kWTap);
+            for (int t = 0; t < nt; ++t) {
 #pragma unroll
-            for (int g = 0; g < G; ++g) {
-              const uint32_t sw = w_base + ws * Cfg::kWStage + (uint32_t)(g * Cfg::kPlanes) * Cfg::kWChunk;
-              load_w(sw, &tm_w7_hi, w_full(ws), j * C + (kg * G + g) * 32);
-              if (NTERMS == 3) load_w(sw + Cfg::kWChunk, &tm_w7_lo, w_full(ws), j * C + (kg * G + g) * 32);
+              for (int g = 0; g < G; ++g) {
+                const uint32_t sw = w_base + ws * Cfg::kWStage + (uint32_t)t * Cfg::kWTap + (uint32_t)(g * Cfg::kPlanes) * Cfg::kWChunk;
+                load_w(sw, &tm_w7_hi, w_full(ws), (j0 + t) * C + (kg * G + g) * 32);
+                if (NTERMS == 3) load_w(sw + Cfg::kWChunk, &tm_w7_lo, w_full(ws), (j0 + t) * C + (kg * G + g) * 32);
+              }
             }
             if (++ws == SW) { ws = 0; wph ^= 1u; }
           }
@@ -392,9 +404,11 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
           if (kg == 0) ru_trace(p, it, 0);
           const uint32_t sa = a_base + as * Cfg::kAStage;
           for (int j = 0; j < 7; ++j) {
-            mbar_wait_t(w_full(ws), wph, timed, ww);
-            tc_fence_after();
-            const uint32_t sw = w_base + ws * Cfg::kWStage;
+            if (j % TJ == 0) {                                     // a ring stage carries TJ consecutive taps
+              mbar_wait_t(w_full(ws), wph, timed, ww);
+              tc_fence_after();
+            }
+            const uint32_t sw = w_base + ws * Cfg::kWStage + (uint32_t)(j % TJ) * Cfg::kWTap;
             const uint32_t a_off = (uint32_t)(j * p.dil) * 64u;   // tap j starts j*dil rows into the halo tile
 #pragma unroll
             for (int g = 0; g < G; ++g) {
@@ -417,8 +431,10 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
                 }
               }
             }
-            commit_w(w_empty(ws));
-            if (++ws == SW) { ws = 0; wph ^= 1u; }
+            if (j % TJ == TJ - 1 || j == 6) {
+              commit_w(w_empty(ws));
+              if (++ws == SW) { ws = 0; wph ^= 1u; }
+            }
           }
           commit(a_empty(as));
           if (++as == SA) { as = 0; aph ^= 1u; }
@@ -605,13 +621,17 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
         if (storer) {
           asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPend) : "memory");
           if (pend_rs[0] >= 0) mbar_arrive(res_empty(pend_rs[0]));
+          if (C == 96 && cc == 64) ru_trace(p, jt, 19);
         }
         tmem_ld_wait();
         tc_fence_before();
+        const bool tr = C == 96 && storer && cc == 64;   // schedule debugging: where the last chunk of a tile spends its time
+        if (tr) ru_trace(p, jt, 14);
         const uint32_t slab = res_base + rs * kRuSlabBytes;
         const uint32_t st_hi = out_base + out_slot * (uint32_t)(Cfg::kPlanes * kRuPlaneTile);
         const uint32_t st_lo = st_hi + kRuPlaneTile;
         mbar_wait(res_full(rs), rph);
+        if (tr) ru_trace(p, jt, 15);
         // the previous chunk's barrier ordered this thread after the storer's wait above (one chunk earlier)
         // Plain C++ shared-memory accesses (no asm volatile): the compiler is free to issue all loads of the chunk
         // first and to interleave the 16 Snake chains; the mbarrier waits / bar.sync around the chunk are the
@@ -625,7 +645,7 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           v[j] = *reinterpret_cast<const float4*>(slab_row + ((((uint32_t)(4 * half + j)) ^ ((uint32_t)row_in_tile & 7u)) << 4));
-          b4[j] = __ldg(reinterpret_cast<const float4*>(p.bias1 + n0 + 4 * j));
+          b4[j] = *reinterpret_cast<const float4*>(s_par + 3 * C + n0 + 4 * j);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -645,8 +665,8 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
             float4 a4[2], i4[2];
 #pragma unroll
             for (int h2 = 0; h2 < 2; ++h2) {
-              a4[h2] = __ldg(reinterpret_cast<const float4*>(p.alpha_out + n0 + 4 * (2 * jj + h2)));
-              i4[h2] = __ldg(reinterpret_cast<const float4*>(p.inv_out + n0 + 4 * (2 * jj + h2)));
+              a4[h2] = *reinterpret_cast<const float4*>(s_par + 4 * C + n0 + 4 * (2 * jj + h2));
+              i4[h2] = *reinterpret_cast<const float4*>(s_par + 5 * C + n0 + 4 * (2 * jj + h2));
             }
 #pragma unroll
             for (int h2 = 0; h2 < 2; ++h2) {
@@ -667,12 +687,17 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
             if (NTERMS == 3) *reinterpret_cast<uint4*>(lo_row + off) = lp;
           }
         }
+        if (tr) ru_trace(p, jt, 16);
         fence_proxy_async();   // generic-proxy writes -> visible to the TMA unit's async-proxy reads
+        if (tr) ru_trace(p, jt, 17);
         asm volatile("bar.sync 1, %0;" ::"n"(kRuTeamThreads) : "memory");
+        if (tr) ru_trace(p, jt, 18);
+        // every thread of the team has drained its share of the accumulator (tcgen05.wait::ld before the barrier):
+        // after the last chunk ONE thread hands the TMEM buffer back to the (leader's) MMA warp.  Not the storer: in
+        // pair mode this is a cluster-scope release arrive, which took ~2.5k cycles on a thread with shared-memory
+        // writes in flight and delayed its TMA stores and the team's next barrier.
+        if (cc + 32 >= N2 && warp == kRuFinWarp0 + 1 && lane == 0) arrive_lead(acc2_empty(u % NB2));
         if (storer) {
-          // every thread of the team has drained its share of the accumulator (tcgen05.wait::ld before the barrier):
-          // after the last chunk ONE thread hands the TMEM buffer back to the (leader's) MMA warp
-          if (cc + 32 >= N2) arrive_lead(acc2_empty(u % NB2));
           tma_store_3d(&tm_res, slab, c, l0, b);
           if (has_out) {
             tma_store_3d(&tm_o_hi, st_hi, c, l0, b);

@@ -580,48 +580,59 @@ head_kernel(const float* __restrict__ x, int rows, const float* __restrict__ alp
 #pragma unroll
   for (int g = 0; g < kHeadRingGran - 1; ++g) issue(g);
 
-  float win[7][NCH];   // win[j] = snake(x[l + j - 3])
+  // Scatter form of the 7-tap conv: the Snake'd row ri (row 0 = sample l0 - 3) adds w[j] * s into the running sum of
+  // output sample ri - j, j = 0..6; sample ri - 6 is complete once row ri has been added.  The seven running sums
+  // live in acc[sample mod 7]; the loop body is unrolled over 28 rows (7 granules of 4 rows) so that every slot index
+  // is a compile-time constant: no sliding-window register moves (the first version spent 18 MOVs per row on them
+  // and was issue bound once the sustained clock dropped to ~1.25 GHz under the power cap).
+  float acc[7];
 #pragma unroll
-  for (int j = 0; j < 7; ++j)
-#pragma unroll
-    for (int k = 0; k < NCH; ++k) win[j][k] = 0.f;
+  for (int j = 0; j < 7; ++j) acc[j] = 0.f;
   const int l_end = min(l0 + kHeadRun, rows);
+  constexpr int N_GRAN7 = (N_GRAN + 6) / 7 * 7;
 #pragma unroll 1
-  for (int g = 0; g < N_GRAN; ++g) {
-    asm volatile("cp.async.wait_group %0;" ::"n"(kHeadRingGran - 2) : "memory");   // granule g has landed
-    __syncwarp();
-    const float* gp = ring + (g % kHeadRingGran) * (kHeadGranRows * C);
+  for (int g0 = 0; g0 < N_GRAN7; g0 += 7) {
 #pragma unroll
-    for (int u = 0; u < kHeadGranRows; ++u) {
-      const int ri = g * kHeadGranRows + u;                // row index inside the run (0 = l0 - 3)
+    for (int gg = 0; gg < 7; ++gg) {
+      const int g = g0 + gg;
+      if (g < N_GRAN) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(kHeadRingGran - 2) : "memory");   // granule g has landed
+        __syncwarp();
+        const float* gp = ring + (g % kHeadRingGran) * (kHeadGranRows * C);
 #pragma unroll
-      for (int j = 0; j < 6; ++j)
+        for (int u = 0; u < kHeadGranRows; ++u) {
+          constexpr int kPeriod = 7;
+          const int rr = gg * kHeadGranRows + u;            // compile-time row index inside the 28-row block
+          const int ri = g * kHeadGranRows + u;             // row index inside the run (0 = l0 - 3); ri = rr (mod 7)
+          float sv[NCH];
 #pragma unroll
-        for (int k = 0; k < NCH; ++k) win[j][k] = win[j + 1][k];
+          for (int k = 0; k < NCH; ++k) sv[k] = snake_f(gp[u * C + lane + 32 * k], a[k], ia[k]);
 #pragma unroll
-      for (int k = 0; k < NCH; ++k) win[6][k] = snake_f(gp[u * C + lane + 32 * k], a[k], ia[k]);
-      // window complete for output sample ri - 6
-      const int so = ri - 6;
-      if (so >= 0 && so < kHeadRun) {
-        float s = 0.f;
+          for (int j = 0; j < 7; ++j) {
+            const int slot = ((rr - j) % kPeriod + kPeriod) % kPeriod;
 #pragma unroll
-        for (int j = 0; j < 7; ++j)
+            for (int k = 0; k < NCH; ++k) acc[slot] = fmaf(wt[j][k], sv[k], acc[slot]);
+          }
+          const int done = ((rr - 6) % kPeriod + kPeriod) % kPeriod;   // output sample ri - 6 is complete
+          const int so = ri - 6;
+          if (so >= 0 && so < kHeadRun) {
+            sp[so & 31][lane] = acc[done];
+            if ((so & 31) == 31) {   // 32 samples done: transpose-reduce through shared memory, lane L gets sample L
+              __syncwarp();
+              float tot = 0.f;
 #pragma unroll
-          for (int k = 0; k < NCH; ++k) s = fmaf(wt[j][k], win[j][k], s);
-        sp[so & 31][lane] = s;
-        if ((so & 31) == 31) {   // 32 samples done: transpose-reduce through shared memory, lane L gets sample L
-          __syncwarp();
-          float tot = 0.f;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) tot += sp[lane][j];
-          __syncwarp();
-          const int l = l0 + so - 31 + lane;
-          if (l < l_end) wav[(size_t)b * rows + l] = tanhf(tot + bias);
+              for (int j = 0; j < 32; ++j) tot += sp[lane][j];
+              __syncwarp();
+              const int l = l0 + so - 31 + lane;
+              if (l < l_end) wav[(size_t)b * rows + l] = tanhf(tot + bias);
+            }
+          }
+          acc[done] = 0.f;
         }
+        __syncwarp();            // all lanes are done reading this granule's slot before it is refilled
+        issue(g + kHeadRingGran - 1);
       }
     }
-    __syncwarp();            // all lanes are done reading this granule's slot before it is refilled
-    issue(g + kHeadRingGran - 1);
   }
 }
 
