@@ -738,7 +738,7 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
       tmem_ld_wait();
       tc_fence_before();
       asm volatile("bar.sync %0, %1;" ::"r"(6 + tm), "n"(kRuTeamThreads) : "memory");   // the team has drained its 32 columns
-      if (wstorer) arrive_lead(acc2_empty(u % NB2));
+      if ((warp & 7) == 1 && lane == 0) arrive_lead(acc2_empty(u % NB2));   // (not the storer: a cluster-scope release arrive is slow)
       const uint32_t slab = res_base + rs_ * kRuSlabBytes;
       const uint32_t st_hi = out_base + (uint32_t)tm * (uint32_t)(Cfg::kPlanes * kRuPlaneTile);
       const uint32_t st_lo = st_hi + kRuPlaneTile;

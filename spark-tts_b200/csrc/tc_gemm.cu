@@ -8,11 +8,17 @@
 // box and TMA out-of-bounds zero fill IS the convolution's zero padding (3-D map C x L x batch:
 // rows never bleed across utterances).
 //
-// Structure (persistent, warp specialised, one CTA per SM):
-//   warp 0 / lane 0 : TMA producer  -> smem ring of {A_hi, A_lo, W_hi, W_lo} stages (mbarrier full/empty)
-//   warp 1 / lane 0 : tcgen05.mma issuer, accumulators in TMEM (2 stages of BLOCK_N columns)
-//   warps 2..5      : epilogue: tcgen05.ld -> bias / residual / Snake / GELU -> fp32 + bf16 hi/lo stores,
-//                     overlapped with the next tile's MMAs through the second TMEM stage.
+// Structure (persistent, warp specialised, one CTA per SM, 608 threads; optionally clusters of two CTAs that issue
+// cta_group::2 M = 256 MMAs -- "pair mode"):
+//   warp 0 / one lane  : TMA producer -> shared-memory rings (mbarrier full / empty).  Convs with several taps use the
+//                        HALO mainloop: one activation tile with the conv halo per K chunk (all taps read it through
+//                        row-offset descriptors) + a ring of per-(tap, K chunk) weight tiles; 1x1 convs / Linear layers
+//                        use one ring of {A, W} stages
+//   warp 1 / one lane  : tcgen05.mma issuer, accumulators in TMEM (2 stages of BLOCK_N columns)
+//   warps 2..9, 10..17 : two epilogue teams on alternate 32-column chunks of an accumulator: tcgen05.ld -> swizzled
+//                        transpose slab -> bias / residual / Snake / GELU -> coalesced fp32 + bf16 hi/lo stores,
+//                        overlapped with the next tile's MMAs through the second TMEM stage
+//   warp 18 / one lane : residual TMA producer (instantiations with a residual input)
 // Precision modes: NTERMS == 1 : A_hi*W_hi (bf16);  NTERMS == 3 : A_hi*W_hi + A_lo*W_hi + A_hi*W_lo
 // (error-compensated split, ~2^-16 relative per product, fp32 accumulate) = the "fp32" mode.
 #include <algorithm>

@@ -42,3 +42,24 @@ for prec in ("fp32", "bf16"):
         a[0] += 1; a[1] += r["ms"]; a[2] += r["flops"]; a[3] += r["bytes"]
     for name, (n, ms, fl, by) in agg.items():
         print(f"    {name:86s} x{n:<3d} {ms:7.3f} ms  {fl / ms / 1e9:8.1f} TF/s  {by / ms / 1e6:7.0f} GB/s")
+
+# ---- speaker half (sparkcodec_tokenize_speaker): reference clips on device -> global tokens on device
+from spark_tts_b200.synthetic import synthetic_ref_wav, synthetic_speaker_state_dict
+
+sd_spk = {**sd, **synthetic_speaker_state_dict(cfg, 0)}
+m = BiCodec.from_state_dict(cfg, sd_spk, device=dev)
+for Bs in (1, 16):
+    wav = synthetic_ref_wav(cfg, Bs, 6.0, 6).to(dev)
+    for _ in range(3):
+        m.tokenize_speaker(wav)
+    ts = []
+    for _ in range(10):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        m.tokenize_speaker(wav)
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    print(f"speaker tokenize fp32 B={Bs} x 6 s clip: median {ts[len(ts) // 2]:.3f} ms ({Bs / (ts[len(ts) // 2] * 1e-3):.0f} clips/s)")
