@@ -7,7 +7,8 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsparkcodec.so")
+# (SPARKCODEC_LIB: A/B timing of two builds of the same ABI on one box; the default is the in-tree library)
+LIB_PATH = os.environ.get("SPARKCODEC_LIB") or os.path.join(_HERE, "libsparkcodec.so")
 
 OK, EINVAL, EINDEX, ECUDA, ESTATE, ENOMEM, EMISSING = 0, -1, -2, -3, -4, -5, -6
 I32, I64 = 0, 1

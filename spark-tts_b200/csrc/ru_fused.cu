@@ -17,11 +17,14 @@
 // Keeping `mid` in TMEM leaves the whole shared memory to the operand rings: the weight ring has to cover the
 // ~2k-cycle refill round trip (MMA done -> commit -> producer -> TMA from L2 -> full), see DESIGN.md.
 //
-// Roles (640 threads, one persistent CTA per SM, clusters of two CTAs):
+// Roles (672 threads, one persistent CTA per SM, clusters of two CTAs):
 //   warps 0..7   : mid team   (acc1 -> mid operand, two chunks in flight)
 //   warps 8..15  : final team (acc2 + residual -> x, operand planes)
 //   warp 16 / 17 / 18, one lane each: TMA producers (residual slabs, activation halo tiles, W7 / W1 weight ring)
-//   warp 19 / one lane: tcgen05.mma issuer (highest warp id: the scheduler favours it over the polling teams)
+//   warp 19 / one lane: tcgen05.mma issuer (high warp id: the scheduler favours it over the polling teams)
+//   warp 20 / one lane: TMA stores of the final stage.  The teams only write a chunk into shared memory and arrive on
+//                       an mbarrier; this thread issues the stores and hands staging slots / residual slabs back once
+//                       the TMA unit has read them, so the store latency is off the teams' critical path
 // TMEM plans (512 columns):
 //   C =  96: acc1 x2 + acc2 x2 (96 columns each); the 1x1 conv of tile i-1 is issued after the k7 conv of tile i (SKEW 1)
 //   C = 192: acc1 x2 (384) + ONE 96-column acc2: the 1x1 conv runs as two N halves between the halves of the next k7 conv
@@ -43,7 +46,7 @@ constexpr int kRuAChunkBytes = 12 * 1024;           // 184 rows x 64 B, rounded 
 constexpr int kRuSlabBytes = kBlockM * 128;         // 128 rows x 32 fp32
 constexpr int kRuPlaneTile = kBlockM * 64;          // 128 rows x 32 bf16 (one operand plane of an output chunk)
 // warp roles: 0..7 mid team, 8..15 final team, 16 / 17 / 18 TMA producers (residual, activations, weights),
-// 19 MMA issuer.
+// 19 MMA issuer, 20 TMA-store issuer.
 // The warp scheduler favours the highest warp id among eligible warps, so the single-thread roles that
 // feed the tensor pipe sit ABOVE the 16 epilogue warps (which spend much of their time polling mbarriers).
 // A warp may only read the TMEM lane quarter warp_id % 4: both teams start at a multiple of 4, so
@@ -56,7 +59,8 @@ constexpr int kRuResWarp = kRuFinWarp0 + kRuTeamWarps;   // residual slabs
 constexpr int kRuTmaAWarp = kRuResWarp + 1;              // activation halo tiles
 constexpr int kRuTmaWWarp = kRuTmaAWarp + 1;             // W7 / W1 tiles
 constexpr int kRuMmaWarp = kRuTmaWWarp + 1;
-constexpr int kRuThreads = (kRuMmaWarp + 1) * 32;
+constexpr int kRuStoreWarp = kRuMmaWarp + 1;             // TMA stores of the final stage (x slabs + operand planes)
+constexpr int kRuThreads = (kRuStoreWarp + 1) * 32;
 
 struct RuParams {
   int batch, L, dil, halo_rows;
@@ -129,7 +133,7 @@ struct RuCfg {
   static constexpr int SWRaw = (227 * 1024 - kFixed) / kWStage;
   static constexpr int SW = SWRaw > 12 ? 12 : SWRaw;
   static constexpr int kNumMid = NB1 * kChunks;                    // one "chunk converted" barrier per (acc1 buffer, chunk)
-  static constexpr int kNumBars = 2 * SA + 2 * SW + kNumMid + NB1 + 2 * NB2 + 2 * SR;
+  static constexpr int kNumBars = 2 * SA + 2 * SW + kNumMid + NB1 + 2 * NB2 + 2 * SR + 2 * kOutSlots;
   static constexpr int kSmemBytes = SA * kAStage + SW * kWStage + SR * kRuSlabBytes + kStageOut + kParBytes +
                                     kNumBars * 8 + 16 + 1024 /* alignment */;
   static_assert(kNumBars * 8 + 16 <= 1024, "barrier block larger than budgeted");
@@ -194,6 +198,9 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
   auto acc2_empty = [&](int s) { return bar_base + 8u * (2 * SA + 2 * SW + NMID + NB1 + NB2 + s); };
   auto res_full = [&](int s) { return bar_base + 8u * (2 * SA + 2 * SW + NMID + NB1 + 2 * NB2 + s); };
   auto res_empty = [&](int s) { return bar_base + 8u * (2 * SA + 2 * SW + NMID + NB1 + 2 * NB2 + SR + s); };
+  // staging slot written by the team -> store warp / read by the TMA unit -> team
+  auto out_full = [&](int s) { return bar_base + 8u * (2 * SA + 2 * SW + NMID + NB1 + 2 * NB2 + 2 * SR + s); };
+  auto out_empty = [&](int s) { return bar_base + 8u * (2 * SA + 2 * SW + NMID + NB1 + 2 * NB2 + 2 * SR + Cfg::kOutSlots + s); };
   const uint32_t tmem_slot = bar_base + 8u * Cfg::kNumBars;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   float* s_par = reinterpret_cast<float*>(smem_raw + (par_base - smem_u32(smem_raw)));   // [bias7 | alpha_mid | inv_mid]
@@ -249,6 +256,7 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
     // acc2 is handed back by one thread per final-stage team and CTA (WIDE: both teams drain every accumulator)
     for (int s = 0; s < NB2; ++s) { mbar_init(acc2_full(s), 1); mbar_init(acc2_empty(s), PG * (Cfg::WIDE ? 2 : 1)); }
     for (int s = 0; s < SR; ++s) { mbar_init(res_full(s), 1); mbar_init(res_empty(s), 1); }
+    for (int s = 0; s < Cfg::kOutSlots; ++s) { mbar_init(out_full(s), 1); mbar_init(out_empty(s), 1); }
     fence_barrier_init();
   }
   if (warp == kRuMmaWarp) {
@@ -525,6 +533,43 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
         }
       }
     }
+  } else if (warp == kRuStoreWarp) {
+    // ================================ TMA-store issuer ================================
+    // Walks the final stage's chunks in the teams' order.  Per chunk: wait until all 256 threads of the team have
+    // written the slab + staging slot (out_full), issue the stores as one bulk group, then -- once the TMA unit has
+    // READ everything but that newest group -- hand the previous chunk's staging slot and residual slab back.
+    if (elect_one()) {
+      const bool has_out = p.out_hi != nullptr;
+      int prev_slot = -1, prev_rs = -1;
+      for (int jt = 0; jt < n_my; ++jt) {
+        const int tile = tile_of(jt);
+        const int b = tile_b(tile), l0 = tile_l0(tile);
+        for (int ci = 0; ci < Cfg::kChunks; ++ci) {
+          const uint32_t q = (uint32_t)jt * Cfg::kChunks + (uint32_t)ci;
+          // staging slot and its use count: WIDE = one slot per team (chunks alternate between the teams)
+          const int slot = Cfg::WIDE ? (ci & 1) : (int)(q % Cfg::kOutSlots);
+          const uint32_t n_use = Cfg::WIDE ? (uint32_t)jt * (Cfg::kChunks / 2) + (uint32_t)(ci >> 1) : q / Cfg::kOutSlots;
+          const int rs_ = (int)(q % SR);
+          mbar_wait(out_full(slot), n_use & 1u);
+          const uint32_t slab = res_base + (uint32_t)rs_ * kRuSlabBytes;
+          const uint32_t st_hi = out_base + (uint32_t)slot * (uint32_t)(Cfg::kPlanes * kRuPlaneTile);
+          tma_store_3d(&tm_res, slab, ci * 32, l0, b);
+          if (has_out) {
+            tma_store_3d(&tm_o_hi, st_hi, ci * 32, l0, b);
+            if (NTERMS == 3) tma_store_3d(&tm_o_lo, st_hi + kRuPlaneTile, ci * 32, l0, b);
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // every group but the newest has been read
+          if (prev_slot >= 0) {
+            mbar_arrive(out_empty(prev_slot));
+            mbar_arrive(res_empty(prev_rs));
+          }
+          prev_slot = slot;
+          prev_rs = rs_;
+        }
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output stores have landed
+    }
   } else {
     // ================================ epilogue teams ================================
     const bool fin_team = warp >= kRuFinWarp0;
@@ -586,163 +631,42 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
       }
     };
 
-    // ---- final stage of tile `jt` (final team only): acc2 + residual slab + b1 -> x, Snake -> operand planes.
+    // ---- final stage: acc2 + residual slab + b1 -> x, Snake -> operand planes.
     // A thread owns 16 columns of ITS row (TMEM lane): it adds them into its row of the residual slab IN PLACE
     // (the slab then holds the new x tile in the TMA box layout), Snakes them straight from registers and
-    // parks the bf16 hi/lo pairs in a staging tile (SWIZZLE_64B box layout).  One elected thread then stores
-    // the x slab and the staging tiles with TMA: no transposed re-read, no per-thread global stores or
-    // address arithmetic, rows beyond the utterance (and dummy tiles) are clipped by the TMA unit.
-    const int ew = (warp - kRuFinWarp0) & 7;    // 0..7 within the final team
+    // parks the bf16 hi/lo pairs in a staging tile (SWIZZLE_64B box layout), then arrives on the slot's `out_full`
+    // mbarrier.  The STORE WARP issues the TMA stores of the slab and the staging tiles (no transposed re-read, no
+    // per-thread global stores or address arithmetic, rows beyond the utterance and dummy tiles are clipped by the
+    // TMA unit) and hands the staging slot (`out_empty`) and the slab (`res_empty`) back once the TMA unit has read
+    // them.  Before the store warp existed one thread of the team did this, and every chunk paid its wait for the
+    // previous stores (~0.8 k cycles) plus the issue of three TMA stores (~0.5 k) at the team's barrier.
+    const int ew = warp & 7;                    // 0..7 within a team
     const int half = ew >> 2;                   // which 16 of a chunk's 32 columns this warp drains from TMEM
-    const bool storer = warp == kRuFinWarp0 && lane == 0;
-    constexpr int kPend = Cfg::kOutSlots - 2;   // store groups that may still be reading shared memory at a chunk start
-    uint32_t rs = 0, rph = 0, out_slot = 0;
-    int pend_rs[kPend + 1];                     // residual slots whose x stores may still be reading them (oldest first)
-#pragma unroll
-    for (int i = 0; i <= kPend; ++i) pend_rs[i] = -1;
-    auto final_stage = [&](int jt) {
-      const int tile = tile_of(jt);
-      const int b = tile_b(tile), l0 = tile_l0(tile);
+    // One 32-column chunk.  q = running chunk number of this CTA (residual ring position), slot / n_use = staging slot
+    // and how often it has been used before (mbarrier parities), t_col = TMEM column of the chunk, hand_back = this
+    // team is done with accumulator `acc_idx` after the chunk, bar_id = the team's named barrier.
+    auto final_chunk = [&](int jt, int c, uint32_t q, int slot, uint32_t n_use, uint32_t t_col, bool hand_back,
+                           uint32_t acc_idx, int bar_id, bool tr) {
       const bool has_out = p.out_hi != nullptr;
-#pragma unroll 1
-      for (int nh = 0; nh < NH; ++nh) {            // N halves of the 1x1 conv (one accumulator each)
-      const uint32_t u = (uint32_t)jt * NH + (uint32_t)nh;
-      mbar_wait(acc2_full(u % NB2), (u / NB2) & 1u);
-      tc_fence_after();
-      if (warp == kRuFinWarp0 && lane == 0 && nh == 0) ru_trace(p, jt, 20);
-      const uint32_t t_row = tmem_base + ((uint32_t)(group * 32) << 16) + (uint32_t)(NB1 * C) + (u % NB2) * N2;
-#pragma unroll 1
-      for (int cc = 0; cc < N2; cc += 32) {
-        const int c = nh * N2 + cc;                // output column of the chunk
-        uint32_t r[16];
-        tmem_ld_x16(t_row + cc + 16 * half, r);
-        // all but the newest kPend store groups have finished READING shared memory: the oldest pending residual
-        // slot can be refilled, and (after this chunk's barrier) the staging slot of the NEXT chunk is free again
-        if (storer) {
-          asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPend) : "memory");
-          if (pend_rs[0] >= 0) mbar_arrive(res_empty(pend_rs[0]));
-          if (C == 96 && cc == 64) ru_trace(p, jt, 19);
-        }
-        tmem_ld_wait();
-        tc_fence_before();
-        const bool tr = C == 96 && storer && cc == 64;   // schedule debugging: where the last chunk of a tile spends its time
-        if (tr) ru_trace(p, jt, 14);
-        const uint32_t slab = res_base + rs * kRuSlabBytes;
-        const uint32_t st_hi = out_base + out_slot * (uint32_t)(Cfg::kPlanes * kRuPlaneTile);
-        const uint32_t st_lo = st_hi + kRuPlaneTile;
-        mbar_wait(res_full(rs), rph);
-        if (tr) ru_trace(p, jt, 15);
-        // the previous chunk's barrier ordered this thread after the storer's wait above (one chunk earlier)
-        // Plain C++ shared-memory accesses (no asm volatile): the compiler is free to issue all loads of the chunk
-        // first and to interleave the 16 Snake chains; the mbarrier waits / bar.sync around the chunk are the
-        // compiler barriers.
-        uint8_t* const slab_row = smem_raw + (slab - smem_u32(smem_raw)) + (size_t)row_in_tile * 128;
-        uint8_t* const hi_row = smem_raw + (st_hi - smem_u32(smem_raw)) + (size_t)row_in_tile * 64;
-        uint8_t* const lo_row = smem_raw + (st_lo - smem_u32(smem_raw)) + (size_t)row_in_tile * 64;
-        const uint32_t swz64 = (uint32_t)(row_in_tile >> 1) & 3u;
-        const int n0 = c + 16 * half;
-        float4 v[4], b4[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          v[j] = *reinterpret_cast<const float4*>(slab_row + ((((uint32_t)(4 * half + j)) ^ ((uint32_t)row_in_tile & 7u)) << 4));
-          b4[j] = *reinterpret_cast<const float4*>(s_par + 3 * C + n0 + 4 * j);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          // same association as the stand-alone 1x1 kernel: (acc + residual) + bias
-          v[j].x = (__uint_as_float(r[4 * j + 0]) + v[j].x) + b4[j].x;
-          v[j].y = (__uint_as_float(r[4 * j + 1]) + v[j].y) + b4[j].y;
-          v[j].z = (__uint_as_float(r[4 * j + 2]) + v[j].z) + b4[j].z;
-          v[j].w = (__uint_as_float(r[4 * j + 3]) + v[j].w) + b4[j].w;
-          *reinterpret_cast<float4*>(slab_row + ((((uint32_t)(4 * half + j)) ^ ((uint32_t)row_in_tile & 7u)) << 4)) = v[j];
-        }
-        if (has_out) {
-#pragma unroll
-          for (int jj = 0; jj < 2; ++jj) {          // 8 columns = one 16 B piece of each operand plane
-            uint4 hp, lp;
-            uint32_t* hpp = reinterpret_cast<uint32_t*>(&hp);
-            uint32_t* lpp = reinterpret_cast<uint32_t*>(&lp);
-            float4 a4[2], i4[2];
-#pragma unroll
-            for (int h2 = 0; h2 < 2; ++h2) {
-              a4[h2] = *reinterpret_cast<const float4*>(s_par + 4 * C + n0 + 4 * (2 * jj + h2));
-              i4[h2] = *reinterpret_cast<const float4*>(s_par + 5 * C + n0 + 4 * (2 * jj + h2));
-            }
-#pragma unroll
-            for (int h2 = 0; h2 < 2; ++h2) {
-              const int j = 2 * jj + h2;
-              const float s0 = snake_sel<NTERMS == 3>(v[j].x, a4[h2].x, i4[h2].x), s1 = snake_sel<NTERMS == 3>(v[j].y, a4[h2].y, i4[h2].y);
-              const float s2 = snake_sel<NTERMS == 3>(v[j].z, a4[h2].z, i4[h2].z), s3 = snake_sel<NTERMS == 3>(v[j].w, a4[h2].w, i4[h2].w);
-              const __nv_bfloat162 h0 = __floats2bfloat162_rn(s0, s1), h1 = __floats2bfloat162_rn(s2, s3);
-              hpp[2 * h2] = pack_bf16(h0);
-              hpp[2 * h2 + 1] = pack_bf16(h1);
-              if (NTERMS == 3) {
-                const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
-                lpp[2 * h2] = pack_bf16(__floats2bfloat162_rn(s0 - f0.x, s1 - f0.y));
-                lpp[2 * h2 + 1] = pack_bf16(__floats2bfloat162_rn(s2 - f1.x, s3 - f1.y));
-              }
-            }
-            const uint32_t off = (((uint32_t)(2 * half + jj)) ^ swz64) << 4;   // SWIZZLE_64B box layout
-            *reinterpret_cast<uint4*>(hi_row + off) = hp;
-            if (NTERMS == 3) *reinterpret_cast<uint4*>(lo_row + off) = lp;
-          }
-        }
-        if (tr) ru_trace(p, jt, 16);
-        fence_proxy_async();   // generic-proxy writes -> visible to the TMA unit's async-proxy reads
-        if (tr) ru_trace(p, jt, 17);
-        asm volatile("bar.sync 1, %0;" ::"n"(kRuTeamThreads) : "memory");
-        if (tr) ru_trace(p, jt, 18);
-        // every thread of the team has drained its share of the accumulator (tcgen05.wait::ld before the barrier):
-        // after the last chunk ONE thread hands the TMEM buffer back to the (leader's) MMA warp.  Not the storer: in
-        // pair mode this is a cluster-scope release arrive, which took ~2.5k cycles on a thread with shared-memory
-        // writes in flight and delayed its TMA stores and the team's next barrier.
-        if (cc + 32 >= N2 && warp == kRuFinWarp0 + 1 && lane == 0) arrive_lead(acc2_empty(u % NB2));
-        if (storer) {
-          tma_store_3d(&tm_res, slab, c, l0, b);
-          if (has_out) {
-            tma_store_3d(&tm_o_hi, st_hi, c, l0, b);
-            if (NTERMS == 3) tma_store_3d(&tm_o_lo, st_lo, c, l0, b);
-          }
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-#pragma unroll
-          for (int i = 0; i < kPend; ++i) pend_rs[i] = pend_rs[i + 1];
-          pend_rs[kPend] = (int)rs;
-        }
-        if (++rs == SR) { rs = 0; rph ^= 1u; }
-        if (++out_slot == (uint32_t)Cfg::kOutSlots) out_slot = 0;
-        if (warp == kRuFinWarp0 && lane == 0 && c < 192) ru_trace(p, jt, 21 + c / 32);
-      }
-      }
-    };
-
-    // ---- C = 384: final stage of ONE 32-column chunk `ci` of tile `jt`, run by team `tm` (chunks alternate between the
-    // two teams, so two chunks drain at once: here the 1x1 phase is not hidden behind a k7 conv -- single acc1 buffer --
-    // and the tensor pipe waits for whatever the drain does not keep up with).  Same data path as final_stage; one
-    // staging slot and two residual slabs (slots of the team's parity) per team.
-    const int tm = warp >> 3;                            // 0 / 1
-    const bool wstorer = (warp & 7) == 0 && lane == 0;   // one TMA-store thread per team
-    int wprev_rs = -1;
-    auto wide_final_chunk = [&](int jt, int ci) {
-      const int tile = tile_of(jt);
-      const int b = tile_b(tile), l0 = tile_l0(tile);
-      const bool has_out = p.out_hi != nullptr;
-      const int nh = ci >> 1, cc = (ci & 1) * 32, c = ci * 32;
-      const uint32_t u = (uint32_t)jt * NH + (uint32_t)nh;
-      const uint32_t q = (uint32_t)jt * Cfg::kChunks + (uint32_t)ci;     // running chunk number -> residual ring slot
       const uint32_t rs_ = q % SR, rph_ = (q / SR) & 1u;
-      mbar_wait(acc2_full(u % NB2), (u / NB2) & 1u);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(group * 32) << 16) + (uint32_t)(NB1 * C) + (u % NB2) * N2;
       uint32_t r[16];
-      tmem_ld_x16(t_row + cc + 16 * half, r);
+      tmem_ld_x16(tmem_base + ((uint32_t)(group * 32) << 16) + t_col + 16 * half, r);
       tmem_ld_wait();
       tc_fence_before();
-      asm volatile("bar.sync %0, %1;" ::"r"(6 + tm), "n"(kRuTeamThreads) : "memory");   // the team has drained its 32 columns
-      if ((warp & 7) == 1 && lane == 0) arrive_lead(acc2_empty(u % NB2));   // (not the storer: a cluster-scope release arrive is slow)
+      if (hand_back) {
+        // every thread of the team has drained its share of the accumulator: ONE thread hands the TMEM buffer back to
+        // the (leader's) MMA warp -- in pair mode a cluster-scope release arrive
+        asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(kRuTeamThreads) : "memory");
+        if (ew == 1 && lane == 0) arrive_lead(acc2_empty(acc_idx));
+      }
+      if (tr) ru_trace(p, jt, 14);
       const uint32_t slab = res_base + rs_ * kRuSlabBytes;
-      const uint32_t st_hi = out_base + (uint32_t)tm * (uint32_t)(Cfg::kPlanes * kRuPlaneTile);
+      const uint32_t st_hi = out_base + (uint32_t)slot * (uint32_t)(Cfg::kPlanes * kRuPlaneTile);
       const uint32_t st_lo = st_hi + kRuPlaneTile;
       mbar_wait(res_full(rs_), rph_);
+      if (tr) ru_trace(p, jt, 15);
+      // Plain C++ shared-memory accesses (no asm volatile): the compiler is free to issue all loads of the chunk
+      // first and to interleave the 16 Snake chains; the mbarrier waits around the chunk are the compiler barriers.
       uint8_t* const slab_row = smem_raw + (slab - smem_u32(smem_raw)) + (size_t)row_in_tile * 128;
       uint8_t* const hi_row = smem_raw + (st_hi - smem_u32(smem_raw)) + (size_t)row_in_tile * 64;
       uint8_t* const lo_row = smem_raw + (st_lo - smem_u32(smem_raw)) + (size_t)row_in_tile * 64;
@@ -754,21 +678,20 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
         v[j] = *reinterpret_cast<const float4*>(slab_row + ((((uint32_t)(4 * half + j)) ^ ((uint32_t)row_in_tile & 7u)) << 4));
         b4[j] = *reinterpret_cast<const float4*>(s_par + 3 * C + n0 + 4 * j);
       }
-      // this chunk's slab is not the one the team's previous store is still reading: the new x goes in right away
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
+        // same association as the stand-alone 1x1 kernel: (acc + residual) + bias
         v[j].x = (__uint_as_float(r[4 * j + 0]) + v[j].x) + b4[j].x;
         v[j].y = (__uint_as_float(r[4 * j + 1]) + v[j].y) + b4[j].y;
         v[j].z = (__uint_as_float(r[4 * j + 2]) + v[j].z) + b4[j].z;
         v[j].w = (__uint_as_float(r[4 * j + 3]) + v[j].w) + b4[j].w;
         *reinterpret_cast<float4*>(slab_row + ((((uint32_t)(4 * half + j)) ^ ((uint32_t)row_in_tile & 7u)) << 4)) = v[j];
       }
-      // Snake + bf16 split into registers FIRST: the team's one staging slot may still be read by its previous TMA
-      // stores, and that read latency hides behind this arithmetic
+      // Snake + bf16 split into registers first; the staging slot is only needed for the stores below
       uint4 hp[2], lp[2];
       if (has_out) {
 #pragma unroll
-        for (int jj = 0; jj < 2; ++jj) {
+        for (int jj = 0; jj < 2; ++jj) {          // 8 columns = one 16 B piece of each operand plane
           uint32_t* hpp = reinterpret_cast<uint32_t*>(&hp[jj]);
           uint32_t* lpp = reinterpret_cast<uint32_t*>(&lp[jj]);
           float4 a4[2], i4[2];
@@ -792,14 +715,8 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
             }
           }
         }
-      }
-      // the team's previous stores have finished READING its staging slot and its previous residual slab
-      if (wstorer) {
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        if (wprev_rs >= 0) mbar_arrive(res_empty(wprev_rs));
-      }
-      asm volatile("bar.sync %0, %1;" ::"r"(10 + tm), "n"(kRuTeamThreads) : "memory");   // staging slot free for everyone
-      if (has_out) {
+        // the TMA unit has finished reading the slot's previous contents
+        mbar_wait(out_empty(slot), (n_use & 1u) ^ 1u);
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj) {
           const uint32_t off = (((uint32_t)(2 * half + jj)) ^ swz64) << 4;   // SWIZZLE_64B box layout
@@ -807,36 +724,52 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
           if (NTERMS == 3) *reinterpret_cast<uint4*>(lo_row + off) = lp[jj];
         }
       }
+      if (tr) ru_trace(p, jt, 16);
       fence_proxy_async();   // generic-proxy writes -> visible to the TMA unit's async-proxy reads
-      asm volatile("bar.sync %0, %1;" ::"r"(8 + tm), "n"(kRuTeamThreads) : "memory");
-      if (wstorer) {
-        tma_store_3d(&tm_res, slab, c, l0, b);
-        if (has_out) {
-          tma_store_3d(&tm_o_hi, st_hi, c, l0, b);
-          if (NTERMS == 3) tma_store_3d(&tm_o_lo, st_lo, c, l0, b);
-        }
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        wprev_rs = (int)rs_;
-      }
+      // team barrier + ONE arrive (256 arrives on one mbarrier word serialise in shared memory: measured + 3-5 % at C = 96)
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(kRuTeamThreads) : "memory");
+      if (ew == 0 && lane == 0) mbar_arrive(out_full(slot));
+      if (tr) ru_trace(p, jt, 17);
     };
 
     const int sub = (warp - kRuMidWarp0) >> 2;   // 0..1 mid team, 2..3 final team
+    const int tm = warp >> 3;                    // team 0 / 1
     if (Cfg::WIDE) {
       // C = 384 (un-skewed, single acc1): all 16 warps convert the mid chunks of tile it (4 chunks in flight), then
-      // both teams drain the 1x1 accumulators on alternate chunks
+      // BOTH teams drain the 1x1 accumulators on alternate 32-column chunks -- the 1x1 phase is not hidden behind a
+      // k7 conv here, so the tensor pipe waits for whatever the drain does not keep up with.  Staging slot = team,
+      // residual slabs of the team's parity.
       for (int it = 0; it < n_my; ++it) {
         mid_stage(it, sub, 4);
-        for (int ci = tm; ci < Cfg::kChunks; ci += 2) wide_final_chunk(it, ci);
+        for (int ci = tm; ci < Cfg::kChunks; ci += 2) {
+          const uint32_t u = (uint32_t)it * NH + (uint32_t)(ci >> 1);
+          mbar_wait(acc2_full(u % NB2), (u / NB2) & 1u);
+          tc_fence_after();
+          final_chunk(it, ci * 32, (uint32_t)it * Cfg::kChunks + (uint32_t)ci, tm, (uint32_t)it * (Cfg::kChunks / 2) + (uint32_t)(ci >> 1),
+                      (uint32_t)(NB1 * C) + (u % NB2) * N2 + (uint32_t)(ci & 1) * 32u, true, u % NB2, 6 + tm, false);
+        }
       }
-      if (wstorer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output stores have landed
-    } else {
+    } else if (!fin_team) {
       // the teams work on different tiles at the same time: mid of tile i, final of tile i - 1
-      if (!fin_team) {
-        for (int it = 0; it < n_my; ++it) mid_stage(it, sub, 2);
-      } else {
-        for (int jt = 0; jt < n_my; ++jt) final_stage(jt);
+      for (int it = 0; it < n_my; ++it) mid_stage(it, sub, 2);
+    } else {
+      for (int jt = 0; jt < n_my; ++jt) {
+#pragma unroll 1
+        for (int nh = 0; nh < NH; ++nh) {            // N halves of the 1x1 conv (one accumulator each)
+          const uint32_t u = (uint32_t)jt * NH + (uint32_t)nh;
+          mbar_wait(acc2_full(u % NB2), (u / NB2) & 1u);
+          tc_fence_after();
+          if (warp == kRuFinWarp0 && lane == 0 && nh == 0) ru_trace(p, jt, 20);
+#pragma unroll 1
+          for (int cc = 0; cc < N2; cc += 32) {
+            const int c = nh * N2 + cc;
+            const uint32_t q = (uint32_t)jt * Cfg::kChunks + (uint32_t)(c / 32);
+            final_chunk(jt, c, q, (int)(q % Cfg::kOutSlots), q / Cfg::kOutSlots, (uint32_t)(NB1 * C) + (u % NB2) * N2 + (uint32_t)cc,
+                        cc + 32 >= N2, u % NB2, 1, C == 96 && cc == 64 && warp == kRuFinWarp0 && lane == 0);
+            if (warp == kRuFinWarp0 && lane == 0 && c < 192) ru_trace(p, jt, 21 + c / 32);
+          }
+        }
       }
-      if (storer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output stores have landed
     }
   }
 
@@ -984,12 +917,14 @@ int launch_resunit_fused(const GemmWeights& c7, const GemmWeights& c1, const OpB
   p.out_hi = out.hi;
   p.out_lo = f32 ? out.lo : nullptr;
   // SPARKCODEC_CLUSTER: 1 = single CTAs, 2 = multicast clusters, 3 = CTA pairs; default: pairs in fp32 mode (tensor
-  // pipe bound: 3 MMAs per MAC), multicast in bf16 mode (epilogue bound) -- profiles/r1_pair_mode_ab.txt
+  // pipe bound: 3 MMAs per MAC), multicast in bf16 mode at C <= 192 (epilogue bound) -- profiles/r1_pair_mode_ab.txt
   static const int forced = [] {
     const char* e = getenv("SPARKCODEC_CLUSTER");
     return e ? atoi(e) : 0;
   }();
-  const int mode = forced ? forced : (f32 ? 3 : 2);
+  // (C = 384 in bf16 mode: pairs too -- 24 KB full-height weight stages leave a 3-4 deep ring that covers ~1.5 k cycles
+  // of single-term MMAs, less than the refill round trip; A/B 2.70-2.81 ms against 2.94-2.98 ms per unit)
+  const int mode = forced ? forced : ((f32 || c7.c_in == 384) ? 3 : 2);
 #define RU_DISPATCH(CC, NT)                                                                              \
   return mode >= 3 ? launch_ru<CC, NT, 2, true>(c7, c1, a, batch, L, p, num_sms, stream)                 \
          : mode == 2 ? launch_ru<CC, NT, 2, false>(c7, c1, a, batch, L, p, num_sms, stream)              \
