@@ -210,9 +210,12 @@ def main():
         return
 
     # ------------------------------------------------------------------ our arm
-    from spark_tts_b200 import BiCodec, BiCodecTokenizer, sharding
+    from spark_tts_b200 import BiCodec, BiCodecTokenizer, sharding, _lib
     from spark_tts_b200.streaming import StreamingDetokenizer
 
+    fp32_terms = int(_lib.load().sparkcodec_fp32_terms())
+    FP32_DTYPE = {2: "f32 (fp16 main product + two e5m2 cross products on tcgen05, fp32 accumulate)",
+                  3: "f32 (bf16x3 split products on tcgen05, fp32 accumulate)"}
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     if world > 1:
         import torch.distributed as dist
@@ -289,7 +292,7 @@ def main():
         gemm_ms = sum(r["ms"] for r in gemm)
         gemm_flops = sum(r["flops"] for r in gemm)
         top_name, top = max(agg.items(), key=lambda kv: kv[1]["ms"])
-        work = 3.0 if precision == "fp32" else 1.0
+        work = float(fp32_terms) if precision == "fp32" else 1.0   # bf16-MMA equivalents of tensor time per MAC
         ach = top["flops"] / (top["ms"] * 1e-3) / 1e12
         traffic, traffic_src = _ncu_traffic(top_name, precision, B, T)
         roof = {
@@ -304,8 +307,9 @@ def main():
                          "tensor_pipe_frac": gemm_flops * work / (gemm_ms * 1e-3) / 1e12 / peaks["tf_sustained"],
                          "share_of_step": gemm_ms / total_ms},
             "note": "achieved = algorithmic 2*MAC of the convolution / CUDA-event duration (per-launch events of a "
-                    "separate profiled pass, mean of 3); the fp32 mode issues 3 bf16 MMAs per algorithmic MAC "
-                    "(tensor_work_factor)"}
+                    "separate profiled pass, mean of 3); the fp32 mode spends tensor_work_factor bf16-MMA "
+                    "equivalents of tensor time per algorithmic MAC (2: one fp16 product + two e5m2 products at twice "
+                    "the rate; 3: three bf16 products)"}
         fused = [r for r in rows if r["name"].startswith("resunit_fused")]
         if fused:
             f_ms, f_fl = sum(r["ms"] for r in fused), sum(r["flops"] for r in fused)
@@ -374,7 +378,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "audio-s/s",
             "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (bf16x3 split products on tcgen05, fp32 accumulate)" if args.precision == "fp32" else "bf16",
+            "dtype": (FP32_DTYPE[fp32_terms] if args.precision == "fp32" else "bf16"),
             "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": launches}
 
     # ---- roofline of the dominant kernel: per-launch CUDA events in a separate, untimed pass ----

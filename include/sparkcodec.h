@@ -43,7 +43,9 @@ enum {
 enum { SPARKCODEC_I32 = 0, SPARKCODEC_I64 = 1 };
 
 /* arithmetic of the dense contractions (activations and I/O are fp32 either way):
- *   FP32 : error-compensated bf16x3 split products on tcgen05, fp32 accumulate
+ *   FP32 : error-compensated split products on tcgen05, fp32 accumulate: an fp16 x fp16 main term plus both cross
+ *          terms as e5m2 x e5m2 products at twice the rate (default), or three bf16 products
+ *          (env SPARKCODEC_FP32_TERMS=3; sparkcodec_fp32_terms() reports which)
  *          (parity bound vs the reference fp32: max-abs 1e-3, SNR >= 60 dB)
  *   BF16 : single bf16 product, fp32 accumulate (looser stated bound)            */
 enum { SPARKCODEC_PREC_FP32 = 0, SPARKCODEC_PREC_BF16 = 1 };
@@ -247,6 +249,10 @@ SPARKCODEC_API int sparkcodec_profile_read(sparkcodec_handle* h, char* buf, size
 /* Number of this library's kernel launches issued since the handle was created (bench.py's
  * `gpu_launches`). */
 SPARKCODEC_API int sparkcodec_launch_count(sparkcodec_handle* h, int64_t* count);
+
+/* Tensor-core products per multiply-accumulate of the FP32 precision mode in this process: 2 (fp16 main term + two
+ * e5m2 cross terms = 2 bf16-MMA equivalents of tensor time) or 3 (bf16 x 3).  bench.py's `tensor_work_factor`. */
+SPARKCODEC_API int sparkcodec_fp32_terms(void);
 
 #ifdef __cplusplus
 }

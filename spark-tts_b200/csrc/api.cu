@@ -187,6 +187,11 @@ static int upload_gemm(sparkcodec_handle* h, const PackedGemm& pk, GemmWeights* 
   SC_TRY(upload(h, pk.w_lo, &lo));
   g->w_hi = reinterpret_cast<__nv_bfloat16*>(hi);
   g->w_lo = reinterpret_cast<__nv_bfloat16*>(lo);
+  if (pk.w_h16.empty()) { set_error("dense layer with K = %d x %d: not a multiple of 32", pk.kt, pk.c_in); return SPARKCODEC_EINVAL; }
+  SC_TRY(upload(h, pk.w_h16, &hi));
+  SC_TRY(upload(h, pk.w_p8, &lo));
+  g->w_h16 = reinterpret_cast<__nv_bfloat16*>(hi);
+  g->w_p8 = reinterpret_cast<__nv_bfloat16*>(lo);
   SC_TRY(upload(h, pk.bias, &g->bias));
   return make_weight_tmaps(*g);
 }
@@ -708,6 +713,12 @@ struct TapReq {
   bool hit = false;
 };
 
+static OpBuf mode_op(OpBuf o, int prec) {
+  if (prec != SPARKCODEC_PREC_FP32) o.lo = nullptr;
+  o.fmt = op_fmt_for(prec);
+  return o;
+}
+
 struct Pass {
   sparkcodec_handle* h;
   int B, T, prec;
@@ -772,16 +783,10 @@ struct Pass {
   int tap_op(const char* name, const OpBuf& src, size_t rows, size_t ch) {
     if (!want(name)) return 0;
     SC_TRY(tap_check(rows, ch));
-    OpBuf s = src;
-    if (prec != SPARKCODEC_PREC_FP32) s.lo = nullptr;
+    const OpBuf s = mode_op(src, prec);
     return launch_merge(s, tap->out + tap->b0 * rows * ch, (size_t)B * rows * ch, st);
   }
 };
-
-static OpBuf mode_op(OpBuf o, int prec) {
-  if (prec != SPARKCODEC_PREC_FP32) o.lo = nullptr;
-  return o;
-}
 
 // One VocosBackbone (vocos.py:324-335) over operand planes `in` (B, T, c_in): embed conv k7 -> norm -> ConvNeXt
 // blocks -> final LayerNorm, written as operand planes (out_op) or fp32 (out_f32).  Shared by the prenet and
@@ -1514,6 +1519,8 @@ int sparkcodec_launch_count(sparkcodec_handle* h, int64_t* count) {
   return 0;
 }
 
+int sparkcodec_fp32_terms(void) { return fp32_terms(); }
+
 int sparkcodec_pack_conv(int kind, const float* w_host, const int64_t* wshape, int param, uint16_t* w_hi,
                          uint16_t* w_lo, size_t w_capacity, int32_t* shifts, int32_t* ntaps, int32_t* kt,
                          int32_t* n_phase, int32_t* n_total) {
@@ -1559,6 +1566,7 @@ int sparkcodec_op_conv(int device, int kind, const float* w_host, const int64_t*
   auto cleanup = [&]() { cudaStreamSynchronize(st); for (void* p : tmp.allocs) cudaFree(p); };
   GemmWeights g;
   OpBuf a, o;
+  a.fmt = o.fmt = op_fmt_for(precision);
   SnakeParams sp;
   void* p;
   const size_t n_in = (size_t)batch * L * c_in, n_out = (size_t)batch * L * pk.n_total;

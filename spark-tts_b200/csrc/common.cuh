@@ -42,13 +42,30 @@ extern thread_local int64_t* g_launch_counter;   // points at the active handle'
   } while (0)
 
 // ---- activations -------------------------------------------------------------------------------
-// All activations are channels-last (batch, rows, channels).  A dense-contraction operand is stored
-// as two bf16 planes hi = bf16(x), lo = bf16(x - hi) (the "OP" format); the fp32-precision mode
-// multiplies hi*Whi + lo*Whi + hi*Wlo on the tensor cores, the bf16 mode only hi*Whi.
+// All activations are channels-last (batch, rows, channels).  A dense-contraction operand is stored as two
+// 2-byte-per-element planes (the "OP" format), in one of two formats:
+//   OPFMT_BF16  : hi = bf16(x), lo = bf16(x - hi).  bf16 mode multiplies hi*Whi only (lo == null); the three-term
+//                 fp32 mode hi*Whi + lo*Whi + hi*Wlo (kind::f16 MMAs, ~2^-16 relative per product).
+//   OPFMT_F16F8 : hi = fp16(x) (11 significant bits); the second plane holds, per group of 32 channels, 64 bytes
+//                 [ e5m2((x - hi) * 2^kLoShift) x 32 | e5m2(hi * 2^-kHiShift) x 32 ].  The two-term fp32 mode multiplies
+//                 hi*Whi with kind::f16 MMAs and adds BOTH cross terms lo*Whi + hi*Wlo with kind::f8f6f4 MMAs (K = 32,
+//                 twice the rate) against a weight plane laid out [ e5m2(Whi * 2^-kLoShift) | e5m2(Wlo * 2^kHiShift) ]:
+//                 the cross terms are 2^-12 of the product, so their 3-bit significands cost ~2^-15 relative -- 74 dB
+//                 waveform SNR in the oracle simulation (tools/sim_split_precision.py) against a 60 dB bar, for two
+//                 thirds of the three-term tensor time.  Plane sizes, TMA boxes and K stepping are identical in both formats.
+enum OpFmt { OPFMT_BF16 = 0, OPFMT_F16F8 = 1 };
+constexpr int kLoShift = 4;   // activations: lo * 2^4 ; weights: hi * 2^-4   (e5m2 normal range 2^-14 .. 2^15)
+constexpr int kHiShift = 8;   // activations: hi * 2^-8; weights: lo * 2^8
 struct OpBuf {
-  __nv_bfloat16* hi = nullptr;
+  __nv_bfloat16* hi = nullptr;   // bf16 or fp16 bits
   __nv_bfloat16* lo = nullptr;   // null in bf16 mode
+  int fmt = OPFMT_BF16;
 };
+// MMA terms of the fp32 precision mode: 2 (default, OPFMT_F16F8) or 3 (OPFMT_BF16); env SPARKCODEC_FP32_TERMS
+int fp32_terms();
+inline int op_fmt_for(int precision) {
+  return (precision == SPARKCODEC_PREC_FP32 && fp32_terms() == 2) ? OPFMT_F16F8 : OPFMT_BF16;
+}
 
 constexpr int kMaxPhases = 8;   // polyphase branches of a transposed conv (= stride)
 constexpr int kMaxTaps = 7;     // taps per branch (k=7 convs; <=3 for the transposed convs)
@@ -66,11 +83,17 @@ struct TapTable {
 struct GemmWeights {
   int c_in = 0, n_total = 0, kt = 0;       // W is (n_total, kt*c_in) K-major
   TapTable taps;
-  __nv_bfloat16* w_hi = nullptr;
+  __nv_bfloat16* w_hi = nullptr;           // OPFMT_BF16 planes
   __nv_bfloat16* w_lo = nullptr;
+  __nv_bfloat16* w_h16 = nullptr;          // OPFMT_F16F8 planes: fp16(W) and the packed e5m2 plane [Whi | Wlo]
+  __nv_bfloat16* w_p8 = nullptr;
   float* bias = nullptr;                   // (n_total) (phase-replicated for transposed convs)
   int block_n = 0;                         // N tile of the tcgen05 kernel (divides cols_per_phase)
   CUtensorMap tmap_hi[2], tmap_lo[2];      // (K, N) boxes (bk, block_n) for bk = 64 ([0]) and 32 ([1])
+  CUtensorMap tmap_h16[2], tmap_p8[2];
+  // planes a kernel with NTERMS terms reads
+  const __nv_bfloat16* hi_for(int nterms) const { return nterms == 2 ? w_h16 : w_hi; }
+  const __nv_bfloat16* lo_for(int nterms) const { return nterms == 2 ? w_p8 : w_lo; }
   bool has_bk64 = false;                   // c_in % 64 == 0
 };
 

@@ -2,6 +2,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "op_split.cuh"
 
 namespace sparkcodec {
 
@@ -25,6 +26,7 @@ struct ConvGemmParams {
   float* out_f32;
   __nv_bfloat16* out_hi;
   __nv_bfloat16* out_lo;
+  int out_fmt;           // OPFMT_* of out_hi / out_lo
 };
 
 int fill_params(const GemmWeights& w, int batch, int L, const Epilogue& ep, int precision, ConvGemmParams* p);
@@ -115,20 +117,7 @@ __device__ __forceinline__ void epilogue_store4(const ConvGemmParams& p, float4 
     } else if (p.act == ACT_GELU) {
       acc.x = gelu_erf(acc.x); acc.y = gelu_erf(acc.y); acc.z = gelu_erf(acc.z); acc.w = gelu_erf(acc.w);
     }
-    const __nv_bfloat162 h0 = __floats2bfloat162_rn(acc.x, acc.y), h1 = __floats2bfloat162_rn(acc.z, acc.w);
-    uint2 hp;
-    hp.x = *reinterpret_cast<const uint32_t*>(&h0);
-    hp.y = *reinterpret_cast<const uint32_t*>(&h1);
-    *reinterpret_cast<uint2*>(p.out_hi + row_off + n) = hp;
-    if (p.out_lo) {
-      const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
-      const __nv_bfloat162 l0 = __floats2bfloat162_rn(acc.x - f0.x, acc.y - f0.y);
-      const __nv_bfloat162 l1 = __floats2bfloat162_rn(acc.z - f1.x, acc.w - f1.y);
-      uint2 lp;
-      lp.x = *reinterpret_cast<const uint32_t*>(&l0);
-      lp.y = *reinterpret_cast<const uint32_t*>(&l1);
-      *reinterpret_cast<uint2*>(p.out_lo + row_off + n) = lp;
-    }
+    store_planes4(p.out_hi, p.out_lo, p.out_fmt, row_off, n, acc.x, acc.y, acc.z, acc.w);
   }
 }
 

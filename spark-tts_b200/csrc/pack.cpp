@@ -2,6 +2,9 @@
 // through sparkcodec_pack_conv (tests/test_pack_cpu.py).
 #include "pack.h"
 
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
+
 #include <climits>
 #include <cmath>
 #include <cstring>
@@ -29,6 +32,28 @@ static void split_planes(PackedGemm& p) {
     uint16_t hi = f32_to_bf16_rn(f);
     p.w_hi[i] = hi;
     p.w_lo[i] = f32_to_bf16_rn(f - bf16_to_f32(hi));
+  }
+  // two-term fp32 mode (OPFMT_F16F8)
+  const size_t K = (size_t)p.kt * p.c_in;
+  p.w_h16.clear();
+  p.w_p8.clear();
+  if (K == 0 || K % 32 != 0) return;
+  p.w_h16.resize(n);
+  p.w_p8.resize(n);
+  uint8_t* p8 = reinterpret_cast<uint8_t*>(p.w_p8.data());
+  const float s_hi = std::ldexp(1.0f, -kLoShift), s_lo = std::ldexp(1.0f, kHiShift);
+  for (size_t i = 0; i < n; ++i) {
+    const float f = p.w_f32[i];
+    float c = f;                                           // finite saturation, like the device-side conversion
+    if (c > 65504.f) c = 65504.f;
+    if (c < -65504.f) c = -65504.f;
+    const __half h = __float2half_rn(c);
+    const float hf = __half2float(h);
+    p.w_h16[i] = __half_as_ushort(h);
+    const size_t row = i / K, k = i % K;
+    uint8_t* q = p8 + row * K * 2 + (k >> 5) * 64 + (k & 31);
+    q[0] = (uint8_t)__nv_cvt_float_to_fp8(hf * s_hi, __NV_SATFINITE, __NV_E5M2);
+    q[32] = (uint8_t)__nv_cvt_float_to_fp8((f - hf) * s_lo, __NV_SATFINITE, __NV_E5M2);
   }
 }
 

@@ -11,7 +11,11 @@ namespace sparkcodec {
 struct PackedGemm {
   int c_in = 0, n_total = 0, kt = 0;
   TapTable taps;
-  std::vector<uint16_t> w_hi, w_lo;   // (n_total, kt*c_in) bf16 bits
+  std::vector<uint16_t> w_hi, w_lo;   // (n_total, kt*c_in) bf16 bits (OPFMT_BF16: hi, lo)
+  // OPFMT_F16F8 (common.cuh): fp16(W) bits, and the packed e5m2 plane -- per row and group of 32 K values, 64 bytes
+  // [ e5m2(fp16(W) * 2^-kLoShift) x 32 | e5m2((W - fp16(W)) * 2^kHiShift) x 32 ] -- in the same (n_total, kt*c_in) x 2 B
+  // footprint.  Empty when kt*c_in is not a multiple of 32.
+  std::vector<uint16_t> w_h16, w_p8;
   std::vector<float> w_f32;           // same layout, fp32 (kept for the packing tests)
   std::vector<float> bias;            // (n_total)
 };

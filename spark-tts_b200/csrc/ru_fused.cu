@@ -17,14 +17,17 @@
 // Keeping `mid` in TMEM leaves the whole shared memory to the operand rings: the weight ring has to cover the
 // ~2k-cycle refill round trip (MMA done -> commit -> producer -> TMA from L2 -> full), see DESIGN.md.
 //
-// Roles (672 threads, one persistent CTA per SM, clusters of two CTAs):
+// Roles (640 threads = 20 warps, i.e. five per scheduler and 96 registers per thread -- a 21st warp costs every thread
+// 16 registers; one persistent CTA per SM, clusters of two CTAs):
 //   warps 0..7   : mid team   (acc1 -> mid operand, two chunks in flight)
 //   warps 8..15  : final team (acc2 + residual -> x, operand planes)
-//   warp 16 / 17 / 18, one lane each: TMA producers (residual slabs, activation halo tiles, W7 / W1 weight ring)
-//   warp 19 / one lane: tcgen05.mma issuer (high warp id: the scheduler favours it over the polling teams)
-//   warp 20 / one lane: TMA stores of the final stage.  The teams only write a chunk into shared memory and arrive on
-//                       an mbarrier; this thread issues the stores and hands staging slots / residual slabs back once
-//                       the TMA unit has read them, so the store latency is off the teams' critical path
+//   warp 16 / one lane: output side.  Residual slabs in (TMA loads) and the final stage's TMA stores out: the teams
+//                       only write a chunk into shared memory and arrive on an mbarrier; this thread issues the stores,
+//                       hands the staging slot back once the TMA unit has read it and refills the residual slab it just
+//                       stored from -- the store latency is off the teams' critical path and the slab ring needs no
+//                       "empty" barriers
+//   warp 17 / 18, one lane each: TMA producers (activation halo tiles, W7 / W1 weight ring)
+//   warp 19 / one lane: tcgen05.mma issuer (highest warp id: the scheduler favours it over the polling teams)
 // TMEM plans (512 columns):
 //   C =  96: acc1 x2 + acc2 x2 (96 columns each); the 1x1 conv of tile i-1 is issued after the k7 conv of tile i (SKEW 1)
 //   C = 192: acc1 x2 (384) + ONE 96-column acc2: the 1x1 conv runs as two N halves between the halves of the next k7 conv
@@ -45,8 +48,8 @@ constexpr int kRuHaloRowsMax = 184;                 // 128 + 6 * 9, multiple of 
 constexpr int kRuAChunkBytes = 12 * 1024;           // 184 rows x 64 B, rounded up to 1024
 constexpr int kRuSlabBytes = kBlockM * 128;         // 128 rows x 32 fp32
 constexpr int kRuPlaneTile = kBlockM * 64;          // 128 rows x 32 bf16 (one operand plane of an output chunk)
-// warp roles: 0..7 mid team, 8..15 final team, 16 / 17 / 18 TMA producers (residual, activations, weights),
-// 19 MMA issuer, 20 TMA-store issuer.
+// warp roles: 0..7 mid team, 8..15 final team, 16 residual loads + output stores, 17 / 18 TMA producers (activations,
+// weights), 19 MMA issuer.
 // The warp scheduler favours the highest warp id among eligible warps, so the single-thread roles that
 // feed the tensor pipe sit ABOVE the 16 epilogue warps (which spend much of their time polling mbarriers).
 // A warp may only read the TMEM lane quarter warp_id % 4: both teams start at a multiple of 4, so
@@ -55,12 +58,11 @@ constexpr int kRuTeamWarps = 8;
 constexpr int kRuTeamThreads = kRuTeamWarps * 32;
 constexpr int kRuMidWarp0 = 0;
 constexpr int kRuFinWarp0 = kRuMidWarp0 + kRuTeamWarps;
-constexpr int kRuResWarp = kRuFinWarp0 + kRuTeamWarps;   // residual slabs
+constexpr int kRuResWarp = kRuFinWarp0 + kRuTeamWarps;   // residual slabs in, x slabs + operand planes out
 constexpr int kRuTmaAWarp = kRuResWarp + 1;              // activation halo tiles
 constexpr int kRuTmaWWarp = kRuTmaAWarp + 1;             // W7 / W1 tiles
 constexpr int kRuMmaWarp = kRuTmaWWarp + 1;
-constexpr int kRuStoreWarp = kRuMmaWarp + 1;             // TMA stores of the final stage (x slabs + operand planes)
-constexpr int kRuThreads = (kRuStoreWarp + 1) * 32;
+constexpr int kRuThreads = (kRuMmaWarp + 1) * 32;
 
 struct RuParams {
   int batch, L, dil, halo_rows;
@@ -77,9 +79,9 @@ constexpr int kRuTraceEvents = 32, kRuTraceTiles = 16;
 template <int C, int NTERMS, int PG>   // PG = CTAs sharing one MMA (1, or 2 = cta_group::2 pair)
 struct RuCfg {
   static constexpr bool WIDE = C > 256;                            // C = 384: one acc1, k7 conv as two N halves
-  static constexpr int kPlanes = NTERMS == 3 ? 2 : 1;
+  static constexpr int kPlanes = NTERMS >= 2 ? 2 : 1;
   static constexpr int kChunks = C / 32;                           // K chunks of 32 channels
-  static constexpr int G = (NTERMS == 3 || WIDE) ? 1 : (C == 96 ? 3 : 2);   // K chunks per ring stage (k7 conv)
+  static constexpr int G = (NTERMS >= 2 || WIDE) ? 1 : (C == 96 ? 3 : 2);   // K chunks per ring stage (k7 conv)
   static constexpr int kGroups = kChunks / G;
   static constexpr int kAStage = G * kPlanes * kRuAChunkBytes;
   static constexpr int KN = WIDE ? 2 : 1;                          // N halves of the k7 conv (UMMA N <= 256)
@@ -89,7 +91,7 @@ struct RuCfg {
   // (336 tensor-pipe cycles), less than what the single issuing thread spends per stage on the barrier wait, the
   // descriptor arithmetic and the commit -- the kernel was ISSUE bound at ~67 cycles per 56-cycle MMA.  Four taps
   // per stage (groups of 4 + 3) amortise that 3.5x.
-  static constexpr int TJ = (C == 96 && NTERMS == 3 && PG == 2) ? 4 : 1;   // (pair mode: 3 KB per plane and tap)
+  static constexpr int TJ = (C == 96 && NTERMS >= 2 && PG == 2) ? 4 : 1;   // (pair mode: 3 KB per plane and tap)
   static constexpr int kWTap = G * kPlanes * kWChunk;              // bytes of one tap inside a stage
   static constexpr int kWStage = TJ * kWTap;
   // TMEM plan.  C <= 192: acc1 (k7 result, then the converted mid operand) is double buffered and the 1x1 conv of
@@ -114,7 +116,7 @@ struct RuCfg {
   static constexpr int kW1Chunk = WIDE ? (N2 / PG) * 64 : kWChunk;                 // chunk stride (one plane) inside a W1 stage
   static constexpr int kW1Stage = G1 * kPlanes * (N2 / PG) * 64;                    // bytes of a W1 stage in this CTA
   // ring depths (227 KB budget)
-  static constexpr int SA = (NTERMS == 3) ? 2 : (C <= 96 ? 2 : 3);
+  static constexpr int SA = (NTERMS >= 2) ? 2 : (C <= 96 ? 2 : 3);
   // Output side of the final stage.  Every 32-column chunk ends with TMA stores (x slab + operand planes) issued by
   // one thread; the team may run kOutSlots - 2 chunks ahead of the stores' shared-memory reads.  C = 96 has
   // shared memory to spare, so it gets three staging slots and a fourth residual slab (worth 1-2 %: its limit is
@@ -133,7 +135,7 @@ struct RuCfg {
   static constexpr int SWRaw = (227 * 1024 - kFixed) / kWStage;
   static constexpr int SW = SWRaw > 12 ? 12 : SWRaw;
   static constexpr int kNumMid = NB1 * kChunks;                    // one "chunk converted" barrier per (acc1 buffer, chunk)
-  static constexpr int kNumBars = 2 * SA + 2 * SW + kNumMid + NB1 + 2 * NB2 + 2 * SR + 2 * kOutSlots;
+  static constexpr int kNumBars = 2 * SA + 2 * SW + kNumMid + NB1 + 2 * NB2 + SR + 2 * kOutSlots;
   static constexpr int kSmemBytes = SA * kAStage + SW * kWStage + SR * kRuSlabBytes + kStageOut + kParBytes +
                                     kNumBars * 8 + 16 + 1024 /* alignment */;
   static_assert(kNumBars * 8 + 16 <= 1024, "barrier block larger than budgeted");
@@ -173,6 +175,7 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
                      const __grid_constant__ CUtensorMap tm_o_lo, const RuParams p) {
   static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of two");
   constexpr int PG = PAIR ? 2 : 1;
+  constexpr bool EXACT = NTERMS >= 2;   // both fp32 modes: range-reduced sine
   using Cfg = RuCfg<C, NTERMS, PG>;
   constexpr int SA = Cfg::SA, SW = Cfg::SW, SR = Cfg::SR, NB1 = Cfg::NB1, NB2 = Cfg::NB2;
   constexpr int G = Cfg::G, SKEW = Cfg::SKEW, NMID = Cfg::kNumMid, NH = Cfg::NH, N2 = Cfg::N2;
@@ -197,10 +200,9 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
   auto acc2_full = [&](int s) { return bar_base + 8u * (2 * SA + 2 * SW + NMID + NB1 + s); };
   auto acc2_empty = [&](int s) { return bar_base + 8u * (2 * SA + 2 * SW + NMID + NB1 + NB2 + s); };
   auto res_full = [&](int s) { return bar_base + 8u * (2 * SA + 2 * SW + NMID + NB1 + 2 * NB2 + s); };
-  auto res_empty = [&](int s) { return bar_base + 8u * (2 * SA + 2 * SW + NMID + NB1 + 2 * NB2 + SR + s); };
-  // staging slot written by the team -> store warp / read by the TMA unit -> team
-  auto out_full = [&](int s) { return bar_base + 8u * (2 * SA + 2 * SW + NMID + NB1 + 2 * NB2 + 2 * SR + s); };
-  auto out_empty = [&](int s) { return bar_base + 8u * (2 * SA + 2 * SW + NMID + NB1 + 2 * NB2 + 2 * SR + Cfg::kOutSlots + s); };
+  // staging slot written by the team -> output thread / read by the TMA unit -> team
+  auto out_full = [&](int s) { return bar_base + 8u * (2 * SA + 2 * SW + NMID + NB1 + 2 * NB2 + SR + s); };
+  auto out_empty = [&](int s) { return bar_base + 8u * (2 * SA + 2 * SW + NMID + NB1 + 2 * NB2 + SR + Cfg::kOutSlots + s); };
   const uint32_t tmem_slot = bar_base + 8u * Cfg::kNumBars;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   float* s_par = reinterpret_cast<float*>(smem_raw + (par_base - smem_u32(smem_raw)));   // [bias7 | alpha_mid | inv_mid]
@@ -244,7 +246,7 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
     prefetch_tmap(&tm_a_hi);
     prefetch_tmap(&tm_w7_hi);
     prefetch_tmap(&tm_w1_hi);
-    if (NTERMS == 3) {
+    if (NTERMS >= 2) {
       prefetch_tmap(&tm_a_lo);
       prefetch_tmap(&tm_w7_lo);
       prefetch_tmap(&tm_w1_lo);
@@ -255,7 +257,7 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
     for (int s = 0; s < NB1; ++s) mbar_init(acc1_full(s), 1);
     // acc2 is handed back by one thread per final-stage team and CTA (WIDE: both teams drain every accumulator)
     for (int s = 0; s < NB2; ++s) { mbar_init(acc2_full(s), 1); mbar_init(acc2_empty(s), PG * (Cfg::WIDE ? 2 : 1)); }
-    for (int s = 0; s < SR; ++s) { mbar_init(res_full(s), 1); mbar_init(res_empty(s), 1); }
+    for (int s = 0; s < SR; ++s) mbar_init(res_full(s), 1);
     for (int s = 0; s < Cfg::kOutSlots; ++s) { mbar_init(out_full(s), 1); mbar_init(out_empty(s), 1); }
     fence_barrier_init();
   }
@@ -283,7 +285,7 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
           const int nb = tile_b(nt), nrow0 = tile_l0(nt) - 3 * p.dil;
           for (int kc = 0; kc < Cfg::kChunks; ++kc) {
             tma_prefetch_3d(&tm_a_hi, kc * 32, nrow0, nb);
-            if (NTERMS == 3) tma_prefetch_3d(&tm_a_lo, kc * 32, nrow0, nb);
+            if (NTERMS >= 2) tma_prefetch_3d(&tm_a_lo, kc * 32, nrow0, nb);
           }
         }
         for (int kg = 0; kg < Cfg::kGroups; ++kg) {
@@ -294,10 +296,10 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
             const uint32_t sa = a_base + as * Cfg::kAStage + (uint32_t)(g * Cfg::kPlanes) * kRuAChunkBytes;
             if (PAIR) {
               tma_load_3d_cg2(sa, &tm_a_hi, lead(a_full(as)), (kg * G + g) * 32, row0, b);
-              if (NTERMS == 3) tma_load_3d_cg2(sa + kRuAChunkBytes, &tm_a_lo, lead(a_full(as)), (kg * G + g) * 32, row0, b);
+              if (NTERMS >= 2) tma_load_3d_cg2(sa + kRuAChunkBytes, &tm_a_lo, lead(a_full(as)), (kg * G + g) * 32, row0, b);
             } else {
               tma_load_3d(sa, &tm_a_hi, a_full(as), (kg * G + g) * 32, row0, b);
-              if (NTERMS == 3) tma_load_3d(sa + kRuAChunkBytes, &tm_a_lo, a_full(as), (kg * G + g) * 32, row0, b);
+              if (NTERMS >= 2) tma_load_3d(sa + kRuAChunkBytes, &tm_a_lo, a_full(as), (kg * G + g) * 32, row0, b);
             }
           }
           if (++as == SA) { as = 0; aph ^= 1u; }
@@ -343,7 +345,7 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
               for (int g = 0; g < G; ++g) {
                 const uint32_t sw = w_base + ws * Cfg::kWStage + (uint32_t)t * Cfg::kWTap + (uint32_t)(g * Cfg::kPlanes) * Cfg::kWChunk;
                 load_w(sw, &tm_w7_hi, w_full(ws), (j0 + t) * C + (kg * G + g) * 32);
-                if (NTERMS == 3) load_w(sw + Cfg::kWChunk, &tm_w7_lo, w_full(ws), (j0 + t) * C + (kg * G + g) * 32);
+                if (NTERMS >= 2) load_w(sw + Cfg::kWChunk, &tm_w7_lo, w_full(ws), (j0 + t) * C + (kg * G + g) * 32);
               }
             }
             if (++ws == SW) { ws = 0; wph ^= 1u; }
@@ -358,7 +360,7 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
           for (int g = 0; g < G1; ++g) {
             const uint32_t sw = w_base + ws * Cfg::kWStage + (uint32_t)(g * Cfg::kPlanes) * Cfg::kW1Chunk;
             load_w1(sw, &tm_w1_hi, w_full(ws), (kg * G1 + g) * 32, half);
-            if (NTERMS == 3) load_w1(sw + Cfg::kW1Chunk, &tm_w1_lo, w_full(ws), (kg * G1 + g) * 32, half);
+            if (NTERMS >= 2) load_w1(sw + Cfg::kW1Chunk, &tm_w1_lo, w_full(ws), (kg * G1 + g) * 32, half);
           }
           if (++ws == SW) { ws = 0; wph ^= 1u; }
         }
@@ -381,7 +383,14 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
     // ================================ MMA issuer ================================
     // pair mode: the leader's thread issues the M = 256 MMAs for both CTAs
     if (leader && elect_one()) {
-      constexpr uint32_t idesc = PAIR ? make_idesc_cg2<N7>() : make_idesc<N7>();   // one k7 MMA covers N7 columns
+      constexpr int HF = NTERMS == 2 ? 0 : 1;   // kind::f16 operand format: fp16 (two-term fp32 mode) or bf16
+      constexpr uint32_t idesc = PAIR ? make_idesc_cg2<N7, HF>() : make_idesc<N7, HF>();   // one k7 MMA covers N7 columns
+      // cross terms of the two-term mode as e5m2 products (kind::f8f6f4, K = 32 = the 32 B step of a kind::f16 K = 16)
+      constexpr uint32_t idesc8 = PAIR ? make_idesc_cg2<N7, 1>() : make_idesc<N7, 1>();
+      auto mma8 = [&](uint32_t d, uint64_t a, uint64_t b) {
+        if (PAIR) umma_f8_cg2(d, a, b, idesc8, 1u);
+        else umma_f8(d, a, b, idesc8, 1u);
+      };
       auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t accumulate) {
         if (PAIR) umma_bf16_cg2(d, a, b, idesc, accumulate);
         else umma_bf16(d, a, b, idesc, accumulate);
@@ -394,7 +403,12 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
         if (PAIR) umma_commit_cg2(bar);
         else umma_commit_cl<CL>(bar);
       };
-      constexpr uint32_t idesc2 = PAIR ? make_idesc_cg2<N2>() : make_idesc<N2>();   // the 1x1 conv is N2 wide
+      constexpr uint32_t idesc2 = PAIR ? make_idesc_cg2<N2, HF>() : make_idesc<N2, HF>();   // the 1x1 conv is N2 wide
+      constexpr uint32_t idesc82 = PAIR ? make_idesc_cg2<N2, 1>() : make_idesc<N2, 1>();
+      auto mma8_ts = [&](uint32_t d, uint32_t a_tmem, uint64_t b) {
+        if (PAIR) umma_f8_ts_cg2(d, a_tmem, b, idesc82, 1u);
+        else umma_f8_ts(d, a_tmem, b, idesc82, 1u);
+      };
       auto mma_ts = [&](uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t accumulate) {
         if (PAIR) umma_bf16_ts_cg2(d, a_tmem, b, idesc2, accumulate);
         else umma_bf16_ts(d, a_tmem, b, idesc2, accumulate);
@@ -430,12 +444,17 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
                 const uint64_t w_hi = make_smem_desc<32>(sw + (uint32_t)(g * Cfg::kPlanes) * Cfg::kWChunk + hoff);
 #pragma unroll
                 for (int k = 0; k < 2; ++k) mma(dh, a_hi + 2 * k, w_hi + 2 * k, (kg | j | g | k) != 0);
-                if (NTERMS == 3) {
+                if (NTERMS >= 2) {
                   const uint64_t w_lo = make_smem_desc<32>(sw + (uint32_t)(g * Cfg::kPlanes + 1) * Cfg::kWChunk + hoff);
+                  if (NTERMS == 2) {   // [A_lo8 | A_hi8] x [W_hi8 | W_lo8], 32 bytes each
 #pragma unroll
-                  for (int k = 0; k < 2; ++k) mma(dh, a_lo + 2 * k, w_hi + 2 * k, 1u);
+                    for (int k = 0; k < 2; ++k) mma8(dh, a_lo + 2 * k, w_lo + 2 * k);
+                  } else {
 #pragma unroll
-                  for (int k = 0; k < 2; ++k) mma(dh, a_hi + 2 * k, w_lo + 2 * k, 1u);
+                    for (int k = 0; k < 2; ++k) mma(dh, a_lo + 2 * k, w_hi + 2 * k, 1u);
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) mma(dh, a_hi + 2 * k, w_lo + 2 * k, 1u);
+                  }
                 }
               }
             }
@@ -480,13 +499,18 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
             const uint64_t w_hi = make_smem_desc<32>(sw + (uint32_t)(g * Cfg::kPlanes) * Cfg::kW1Chunk);
 #pragma unroll
             for (int k = 0; k < 2; ++k) mma_ts(d2, a_hi + 8 * k, w_hi + 2 * k, (kg | g | k) != 0);
-            if (NTERMS == 3) {
+            if (NTERMS >= 2) {
               const uint32_t a_lo = a_hi + 16u;
               const uint64_t w_lo = make_smem_desc<32>(sw + (uint32_t)(g * Cfg::kPlanes + 1) * Cfg::kW1Chunk);
+              if (NTERMS == 2) {   // columns +16..23: 32 e5m2 lo values, +24..31: 32 e5m2 hi values (four per column)
 #pragma unroll
-              for (int k = 0; k < 2; ++k) mma_ts(d2, a_lo + 8 * k, w_hi + 2 * k, 1u);
+                for (int k = 0; k < 2; ++k) mma8_ts(d2, a_lo + 8 * k, w_lo + 2 * k);
+              } else {
 #pragma unroll
-              for (int k = 0; k < 2; ++k) mma_ts(d2, a_hi + 8 * k, w_lo + 2 * k, 1u);
+                for (int k = 0; k < 2; ++k) mma_ts(d2, a_lo + 8 * k, w_hi + 2 * k, 1u);
+#pragma unroll
+                for (int k = 0; k < 2; ++k) mma_ts(d2, a_hi + 8 * k, w_lo + 2 * k, 1u);
+              }
             }
           }
           commit_w(w_empty(ws));
@@ -513,60 +537,42 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
       }
     }
   } else if (warp == kRuResWarp) {
-    // ================================ residual TMA producer ================================
+    // ================================ output thread: residual slabs in, TMA stores out ================================
+    // Walks the final stage's chunks in the teams' order (q = running chunk number of this CTA; chunk q uses residual
+    // slab q % SR).  Per chunk: wait until all 256 threads of the team have written the slab + staging slot (out_full),
+    // issue the stores as one bulk group, wait until the TMA unit has READ them, hand the staging slot back
+    // (out_empty) and refill the slab with the residual tile of chunk q + SR.  The slab ring therefore needs no
+    // "empty" barriers: the thread that frees a slab is the one that refills it.
     if (elect_one()) {
       prefetch_tmap(&tm_res);
-      uint32_t rs = 0, rph = 0;
-      for (int jt = 0; jt < n_my; ++jt) {
-        const int tile = tile_of(jt);
-        const int b = tile_b(tile);
-        const int l0 = tile_l0(tile);
-        if (p.l2_prefetch && jt + 1 < n_my) {   // pull the next tile's residual rows into L2 while this tile is processed
-          const int nt = tile_of(jt + 1);
-          for (int c = 0; c < C; c += 32) tma_prefetch_3d(&tm_res, c, tile_l0(nt), tile_b(nt));
-        }
-        for (int c = 0; c < C; c += 32) {
-          mbar_wait(res_empty(rs), rph ^ 1u);
-          mbar_expect_tx(res_full(rs), kRuSlabBytes);
-          tma_load_3d(res_base + rs * kRuSlabBytes, &tm_res, res_full(rs), c, l0, b);
-          if (++rs == SR) { rs = 0; rph ^= 1u; }
-        }
-      }
-    }
-  } else if (warp == kRuStoreWarp) {
-    // ================================ TMA-store issuer ================================
-    // Walks the final stage's chunks in the teams' order.  Per chunk: wait until all 256 threads of the team have
-    // written the slab + staging slot (out_full), issue the stores as one bulk group, then -- once the TMA unit has
-    // READ everything but that newest group -- hand the previous chunk's staging slot and residual slab back.
-    if (elect_one()) {
       const bool has_out = p.out_hi != nullptr;
-      int prev_slot = -1, prev_rs = -1;
-      for (int jt = 0; jt < n_my; ++jt) {
+      const uint32_t total = (uint32_t)n_my * Cfg::kChunks;
+      auto load_res = [&](uint32_t q) {
+        const int tile = tile_of((int)(q / Cfg::kChunks));
+        const uint32_t rs = q % SR;
+        mbar_expect_tx(res_full(rs), kRuSlabBytes);
+        tma_load_3d(res_base + rs * kRuSlabBytes, &tm_res, res_full(rs), (int)(q % Cfg::kChunks) * 32, tile_l0(tile), tile_b(tile));
+      };
+      for (uint32_t q = 0; q < (uint32_t)SR && q < total; ++q) load_res(q);
+      for (uint32_t q = 0; q < total; ++q) {
+        const int jt = (int)(q / Cfg::kChunks), ci = (int)(q % Cfg::kChunks);
         const int tile = tile_of(jt);
         const int b = tile_b(tile), l0 = tile_l0(tile);
-        for (int ci = 0; ci < Cfg::kChunks; ++ci) {
-          const uint32_t q = (uint32_t)jt * Cfg::kChunks + (uint32_t)ci;
-          // staging slot and its use count: WIDE = one slot per team (chunks alternate between the teams)
-          const int slot = Cfg::WIDE ? (ci & 1) : (int)(q % Cfg::kOutSlots);
-          const uint32_t n_use = Cfg::WIDE ? (uint32_t)jt * (Cfg::kChunks / 2) + (uint32_t)(ci >> 1) : q / Cfg::kOutSlots;
-          const int rs_ = (int)(q % SR);
-          mbar_wait(out_full(slot), n_use & 1u);
-          const uint32_t slab = res_base + (uint32_t)rs_ * kRuSlabBytes;
-          const uint32_t st_hi = out_base + (uint32_t)slot * (uint32_t)(Cfg::kPlanes * kRuPlaneTile);
-          tma_store_3d(&tm_res, slab, ci * 32, l0, b);
-          if (has_out) {
-            tma_store_3d(&tm_o_hi, st_hi, ci * 32, l0, b);
-            if (NTERMS == 3) tma_store_3d(&tm_o_lo, st_hi + kRuPlaneTile, ci * 32, l0, b);
-          }
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // every group but the newest has been read
-          if (prev_slot >= 0) {
-            mbar_arrive(out_empty(prev_slot));
-            mbar_arrive(res_empty(prev_rs));
-          }
-          prev_slot = slot;
-          prev_rs = rs_;
+        // staging slot and its use count: WIDE = one slot per team (chunks alternate between the teams)
+        const int slot = Cfg::WIDE ? (ci & 1) : (int)(q % Cfg::kOutSlots);
+        const uint32_t n_use = Cfg::WIDE ? (uint32_t)jt * (Cfg::kChunks / 2) + (uint32_t)(ci >> 1) : q / Cfg::kOutSlots;
+        mbar_wait(out_full(slot), n_use & 1u);
+        const uint32_t slab = res_base + (q % SR) * kRuSlabBytes;
+        const uint32_t st_hi = out_base + (uint32_t)slot * (uint32_t)(Cfg::kPlanes * kRuPlaneTile);
+        tma_store_3d(&tm_res, slab, ci * 32, l0, b);
+        if (has_out) {
+          tma_store_3d(&tm_o_hi, st_hi, ci * 32, l0, b);
+          if (NTERMS >= 2) tma_store_3d(&tm_o_lo, st_hi + kRuPlaneTile, ci * 32, l0, b);
         }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the TMA unit has read the slab and the slot
+        mbar_arrive(out_empty(slot));
+        if (q + SR < total) load_res(q + SR);
       }
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output stores have landed
     }
@@ -598,28 +604,41 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {     // 16 columns -> 8 packed hi columns + 8 packed lo columns
           uint32_t hi[8], lo[8];
+          uint32_t l8[4], h8[4];   // two-term mode: four e5m2 values per column
 #pragma unroll
           for (int qq = 0; qq < 4; ++qq) {
             const int q = 4 * hf + qq;
             const float4 b4 = *reinterpret_cast<const float4*>(s_par + c + 4 * q);
             const float4 a4 = *reinterpret_cast<const float4*>(s_par + C + c + 4 * q);
             const float4 i4 = *reinterpret_cast<const float4*>(s_par + 2 * C + c + 4 * q);
-            const float v0 = snake_sel<NTERMS == 3>(__uint_as_float(r[4 * q + 0]) + b4.x, a4.x, i4.x);
-            const float v1 = snake_sel<NTERMS == 3>(__uint_as_float(r[4 * q + 1]) + b4.y, a4.y, i4.y);
-            const float v2 = snake_sel<NTERMS == 3>(__uint_as_float(r[4 * q + 2]) + b4.z, a4.z, i4.z);
-            const float v3 = snake_sel<NTERMS == 3>(__uint_as_float(r[4 * q + 3]) + b4.w, a4.w, i4.w);
-            const __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1), h1 = __floats2bfloat162_rn(v2, v3);
-            hi[2 * qq] = pack_bf16(h0);
-            hi[2 * qq + 1] = pack_bf16(h1);
-            if (NTERMS == 3) {
-              const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
-              lo[2 * qq] = pack_bf16(__floats2bfloat162_rn(v0 - f0.x, v1 - f0.y));
-              lo[2 * qq + 1] = pack_bf16(__floats2bfloat162_rn(v2 - f1.x, v3 - f1.y));
+            const float v0 = snake_sel<EXACT>(__uint_as_float(r[4 * q + 0]) + b4.x, a4.x, i4.x);
+            const float v1 = snake_sel<EXACT>(__uint_as_float(r[4 * q + 1]) + b4.y, a4.y, i4.y);
+            const float v2 = snake_sel<EXACT>(__uint_as_float(r[4 * q + 2]) + b4.z, a4.z, i4.z);
+            const float v3 = snake_sel<EXACT>(__uint_as_float(r[4 * q + 3]) + b4.w, a4.w, i4.w);
+            if (NTERMS == 2) {
+              const Split4F8 sp = split4_f16f8(v0, v1, v2, v3);
+              hi[2 * qq] = sp.hi[0];
+              hi[2 * qq + 1] = sp.hi[1];
+              l8[qq] = sp.lo8;
+              h8[qq] = sp.hi8;
+            } else {
+              const __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1), h1 = __floats2bfloat162_rn(v2, v3);
+              hi[2 * qq] = pack_bf16(h0);
+              hi[2 * qq + 1] = pack_bf16(h1);
+              if (NTERMS == 3) {
+                const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+                lo[2 * qq] = pack_bf16(__floats2bfloat162_rn(v0 - f0.x, v1 - f0.y));
+                lo[2 * qq + 1] = pack_bf16(__floats2bfloat162_rn(v2 - f1.x, v3 - f1.y));
+              }
             }
           }
           // every accumulator column of the chunk is already in registers, so the in-place stores are safe
           tmem_st_x8(t_row + c + 8 * hf, hi);
           if (NTERMS == 3) tmem_st_x8(t_row + c + 16 + 8 * hf, lo);
+          if (NTERMS == 2) {   // 32 fp32 columns -> 16 of fp16 pairs + 8 of lo8 quads + 8 of hi8 quads
+            tmem_st_x4(t_row + c + 16 + 4 * hf, l8);
+            tmem_st_x4(t_row + c + 24 + 4 * hf, h8);
+          }
         }
         tmem_st_wait();
         tc_fence_before();
@@ -635,11 +654,11 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
     // A thread owns 16 columns of ITS row (TMEM lane): it adds them into its row of the residual slab IN PLACE
     // (the slab then holds the new x tile in the TMA box layout), Snakes them straight from registers and
     // parks the bf16 hi/lo pairs in a staging tile (SWIZZLE_64B box layout), then arrives on the slot's `out_full`
-    // mbarrier.  The STORE WARP issues the TMA stores of the slab and the staging tiles (no transposed re-read, no
-    // per-thread global stores or address arithmetic, rows beyond the utterance and dummy tiles are clipped by the
-    // TMA unit) and hands the staging slot (`out_empty`) and the slab (`res_empty`) back once the TMA unit has read
-    // them.  Before the store warp existed one thread of the team did this, and every chunk paid its wait for the
-    // previous stores (~0.8 k cycles) plus the issue of three TMA stores (~0.5 k) at the team's barrier.
+    // mbarrier.  The OUTPUT THREAD (warp 16) issues the TMA stores of the slab and the staging tiles (no transposed
+    // re-read, no per-thread global stores or address arithmetic, rows beyond the utterance and dummy tiles are clipped
+    // by the TMA unit), hands the staging slot back (`out_empty`) once the TMA unit has read it and refills the slab.
+    // When one thread of the team did this, every chunk paid its wait for the previous stores (~0.8 k cycles) plus the
+    // issue of three TMA stores (~0.5 k) at the team's barrier.
     const int ew = warp & 7;                    // 0..7 within a team
     const int half = ew >> 2;                   // which 16 of a chunk's 32 columns this warp drains from TMEM
     // One 32-column chunk.  q = running chunk number of this CTA (residual ring position), slot / n_use = staging slot
@@ -703,15 +722,24 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
 #pragma unroll
           for (int h2 = 0; h2 < 2; ++h2) {
             const int j = 2 * jj + h2;
-            const float s0 = snake_sel<NTERMS == 3>(v[j].x, a4[h2].x, i4[h2].x), s1 = snake_sel<NTERMS == 3>(v[j].y, a4[h2].y, i4[h2].y);
-            const float s2 = snake_sel<NTERMS == 3>(v[j].z, a4[h2].z, i4[h2].z), s3 = snake_sel<NTERMS == 3>(v[j].w, a4[h2].w, i4[h2].w);
-            const __nv_bfloat162 h0 = __floats2bfloat162_rn(s0, s1), h1 = __floats2bfloat162_rn(s2, s3);
-            hpp[2 * h2] = pack_bf16(h0);
-            hpp[2 * h2 + 1] = pack_bf16(h1);
-            if (NTERMS == 3) {
-              const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
-              lpp[2 * h2] = pack_bf16(__floats2bfloat162_rn(s0 - f0.x, s1 - f0.y));
-              lpp[2 * h2 + 1] = pack_bf16(__floats2bfloat162_rn(s2 - f1.x, s3 - f1.y));
+            const float s0 = snake_sel<EXACT>(v[j].x, a4[h2].x, i4[h2].x), s1 = snake_sel<EXACT>(v[j].y, a4[h2].y, i4[h2].y);
+            const float s2 = snake_sel<EXACT>(v[j].z, a4[h2].z, i4[h2].z), s3 = snake_sel<EXACT>(v[j].w, a4[h2].w, i4[h2].w);
+            if (NTERMS == 2) {
+              // lp[0] = the 16 lo8 bytes of this thread's 16 columns, lp[1] = the 16 hi8 bytes (word = quad j)
+              const Split4F8 sp = split4_f16f8(s0, s1, s2, s3);
+              hpp[2 * h2] = sp.hi[0];
+              hpp[2 * h2 + 1] = sp.hi[1];
+              reinterpret_cast<uint32_t*>(&lp[0])[j] = sp.lo8;
+              reinterpret_cast<uint32_t*>(&lp[1])[j] = sp.hi8;
+            } else {
+              const __nv_bfloat162 h0 = __floats2bfloat162_rn(s0, s1), h1 = __floats2bfloat162_rn(s2, s3);
+              hpp[2 * h2] = pack_bf16(h0);
+              hpp[2 * h2 + 1] = pack_bf16(h1);
+              if (NTERMS == 3) {
+                const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+                lpp[2 * h2] = pack_bf16(__floats2bfloat162_rn(s0 - f0.x, s1 - f0.y));
+                lpp[2 * h2 + 1] = pack_bf16(__floats2bfloat162_rn(s2 - f1.x, s3 - f1.y));
+              }
             }
           }
         }
@@ -722,6 +750,8 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
           const uint32_t off = (((uint32_t)(2 * half + jj)) ^ swz64) << 4;   // SWIZZLE_64B box layout
           *reinterpret_cast<uint4*>(hi_row + off) = hp[jj];
           if (NTERMS == 3) *reinterpret_cast<uint4*>(lo_row + off) = lp[jj];
+          // two-term mode: the 64 B row of the packed plane is [lo8 x 32 | hi8 x 32]; jj = 0 lo8, jj = 1 hi8
+          if (NTERMS == 2) *reinterpret_cast<uint4*>(lo_row + ((((uint32_t)(2 * jj + half)) ^ swz64) << 4)) = lp[jj];
         }
       }
       if (tr) ru_trace(p, jt, 16);
@@ -792,7 +822,7 @@ int launch_ru(const GemmWeights& c7, const GemmWeights& c1, const OpBuf& a, int 
   const uint64_t strides[2] = {(uint64_t)C * 2, (uint64_t)L * C * 2};
   const uint32_t box[3] = {32u, (uint32_t)p.halo_rows, 1u};
   SC_TRY(encode_tmap(&ta_hi, a.hi, 3, dims, strides, box, 64, false, false));
-  if (NTERMS == 3) SC_TRY(encode_tmap(&ta_lo, a.lo, 3, dims, strides, box, 64, false, false));
+  if (NTERMS >= 2) SC_TRY(encode_tmap(&ta_lo, a.lo, 3, dims, strides, box, 64, false, false));
   else ta_lo = ta_hi;
   const uint64_t rstr[2] = {(uint64_t)C * 4, (uint64_t)L * C * 4};
   const uint32_t rbox[3] = {32u, (uint32_t)kBlockM, 1u};
@@ -813,8 +843,8 @@ int launch_ru(const GemmWeights& c7, const GemmWeights& c1, const OpBuf& a, int 
     const uint64_t wd[2] = {(uint64_t)gw[i]->kt * C, (uint64_t)C};
     const uint64_t ws[1] = {(uint64_t)gw[i]->kt * C * 2};
     const uint32_t wb[2] = {32u, (uint32_t)((i == 0 ? Cfg::N7 : Cfg::N2) / CL)};
-    SC_TRY(encode_tmap(&tw[2 * i], gw[i]->w_hi, 2, wd, ws, wb, 64, true, false));
-    SC_TRY(encode_tmap(&tw[2 * i + 1], NTERMS == 3 ? gw[i]->w_lo : gw[i]->w_hi, 2, wd, ws, wb, 64, true, false));
+    SC_TRY(encode_tmap(&tw[2 * i], gw[i]->hi_for(NTERMS), 2, wd, ws, wb, 64, true, false));
+    SC_TRY(encode_tmap(&tw[2 * i + 1], NTERMS >= 2 ? gw[i]->lo_for(NTERMS) : gw[i]->w_hi, 2, wd, ws, wb, 64, true, false));
   }
   auto kern = resunit_fused_kernel<C, NTERMS, CL, PAIR>;
   static PerDevice cache;   // per instantiation and device: clusters that fit (0 = not initialised yet)
@@ -903,6 +933,11 @@ int launch_resunit_fused(const GemmWeights& c7, const GemmWeights& c1, const OpB
     set_error("resunit_fused: fp32 mode needs both operand planes");
     return SPARKCODEC_EINVAL;
   }
+  if (a.fmt != op_fmt_for(precision) || (out.hi && out.fmt != a.fmt)) {
+    set_error("resunit_fused: operand planes are not in the format of this precision mode");
+    return SPARKCODEC_EINVAL;
+  }
+  const int terms = f32 ? fp32_terms() : 1;
   RuParams p;
   p.batch = batch; p.L = L; p.dil = dil;
   p.halo_rows = (kBlockM + 6 * dil + 7) / 8 * 8;
@@ -930,14 +965,15 @@ int launch_resunit_fused(const GemmWeights& c7, const GemmWeights& c1, const OpB
          : mode == 2 ? launch_ru<CC, NT, 2, false>(c7, c1, a, batch, L, p, num_sms, stream)              \
                      : launch_ru<CC, NT, 1, false>(c7, c1, a, batch, L, p, num_sms, stream)
   if (c7.c_in == 96) {
-    if (f32) { RU_DISPATCH(96, 3); } else { RU_DISPATCH(96, 1); }
+    if (terms == 3) { RU_DISPATCH(96, 3); } else if (terms == 2) { RU_DISPATCH(96, 2); } else { RU_DISPATCH(96, 1); }
   }
   if (c7.c_in == 384) {
-    // fp32 mode: only the CTA pair fits (a full-height 48 KB weight stage would leave a 1-deep ring)
-    if (f32) return launch_ru<384, 3, 2, true>(c7, c1, a, batch, L, p, num_sms, stream);
+    // fp32 modes: only the CTA pair fits (a full-height 48 KB weight stage would leave a 1-deep ring)
+    if (terms == 3) return launch_ru<384, 3, 2, true>(c7, c1, a, batch, L, p, num_sms, stream);
+    if (terms == 2) return launch_ru<384, 2, 2, true>(c7, c1, a, batch, L, p, num_sms, stream);
     RU_DISPATCH(384, 1);
   }
-  if (f32) { RU_DISPATCH(192, 3); } else { RU_DISPATCH(192, 1); }
+  if (terms == 3) { RU_DISPATCH(192, 3); } else if (terms == 2) { RU_DISPATCH(192, 2); } else { RU_DISPATCH(192, 1); }
 #undef RU_DISPATCH
 }
 

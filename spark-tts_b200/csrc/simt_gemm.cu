@@ -1,5 +1,6 @@
-// CUDA-core verification kernel for the dense contractions: same operands (bf16 hi/lo planes), same
-// tap tables and the same fused epilogue as tc_gemm.cu, but plain FFMA on (hi + lo) values.
+// CUDA-core verification kernel for the dense contractions: same operands (operand planes in either format), same
+// tap tables and the same fused epilogue as tc_gemm.cu, but plain FFMA: on (hi + lo) values for OPFMT_BF16, and on the
+// three products the tensor cores form (hi*Whi + lo8*Whi8 + hi8*Wlo8) for OPFMT_F16F8.
 // It exists to bisect the tcgen05 path in tests (sparkcodec_set_impl / sparkcodec_op_conv impl=1);
 // the product path never selects it.
 #include "gemm_params.cuh"
@@ -12,9 +13,12 @@ constexpr int TM = 64, TN = 32, TK = 16;
 __global__ void __launch_bounds__(256)
 conv_gemm_simt_kernel(const ConvGemmParams p, const __nv_bfloat16* __restrict__ a_hi,
                       const __nv_bfloat16* __restrict__ a_lo, const __nv_bfloat16* __restrict__ w_hi,
-                      const __nv_bfloat16* __restrict__ w_lo, int kt, int m_tiles_per_utt) {
+                      const __nv_bfloat16* __restrict__ w_lo, int kt, int m_tiles_per_utt, int fmt) {
   __shared__ __align__(16) float sA[TM][TK];
   __shared__ __align__(16) float sW[TN][TK];
+  // OPFMT_F16F8: the e5m2 parts (still carrying their power-of-two scales, which cancel in the products)
+  __shared__ __align__(16) float sAl[TM][TK], sAh[TM][TK], sWh[TN][TK], sWl[TN][TK];
+  const bool f8 = fmt == OPFMT_F16F8;
   const int tid = threadIdx.x;
   const int b = blockIdx.x / m_tiles_per_utt;
   const int l0 = (blockIdx.x % m_tiles_per_utt) * TM;
@@ -36,25 +40,41 @@ conv_gemm_simt_kernel(const ConvGemmParams p, const __nv_bfloat16* __restrict__ 
     for (int k0 = 0; k0 < p.c_in; k0 += TK) {
       {
         const int l = l0 + ar + shift;
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        float v[4] = {0.f, 0.f, 0.f, 0.f}, vl[4] = {0.f, 0.f, 0.f, 0.f}, vh[4] = {0.f, 0.f, 0.f, 0.f};
         if (l >= 0 && l < p.L) {
           const size_t off = ((size_t)b * p.L + l) * p.c_in + k0 + ac;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            v[i] = __bfloat162float(a_hi[off + i]);
-            if (a_lo) v[i] += __bfloat162float(a_lo[off + i]);
+            if (f8) {
+              v[i] = __half2float(reinterpret_cast<const __half*>(a_hi)[off + i]);
+              const uint8_t* q = reinterpret_cast<const uint8_t*>(a_lo) + p8_off(off - (k0 + ac), k0 + ac + i);
+              vl[i] = e5m2_to_float(q[0]);
+              vh[i] = e5m2_to_float(q[32]);
+            } else {
+              v[i] = __bfloat162float(a_hi[off + i]);
+              if (a_lo) v[i] += __bfloat162float(a_lo[off + i]);
+            }
           }
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) sA[ar][ac + i] = v[i];
+        for (int i = 0; i < 4; ++i) { sA[ar][ac + i] = v[i]; sAl[ar][ac + i] = vl[i]; sAh[ar][ac + i] = vh[i]; }
       }
       if (tid < 128) {
         const size_t off = (size_t)(n0 + wr) * ldw + (size_t)j * p.c_in + k0 + wc;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          float v = __bfloat162float(w_hi[off + i]);
-          if (w_lo) v += __bfloat162float(w_lo[off + i]);
-          sW[wr][wc + i] = v;
+          float v, vh = 0.f, vl = 0.f;
+          if (f8) {
+            v = __half2float(reinterpret_cast<const __half*>(w_hi)[off + i]);
+            const int kk = j * p.c_in + k0 + wc + i;
+            const uint8_t* q = reinterpret_cast<const uint8_t*>(w_lo) + p8_off((size_t)(n0 + wr) * ldw, kk);
+            vh = e5m2_to_float(q[0]);
+            vl = e5m2_to_float(q[32]);
+          } else {
+            v = __bfloat162float(w_hi[off + i]);
+            if (w_lo) v += __bfloat162float(w_lo[off + i]);
+          }
+          sW[wr][wc + i] = v; sWh[wr][wc + i] = vh; sWl[wr][wc + i] = vl;
         }
       }
       __syncthreads();
@@ -63,6 +83,11 @@ conv_gemm_simt_kernel(const ConvGemmParams p, const __nv_bfloat16* __restrict__ 
         const float a = sA[r][k];
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = fmaf(a, sW[cg + i][k], acc[i]);
+        if (f8) {
+          const float al = sAl[r][k], ah = sAh[r][k];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] = fmaf(al, sWh[cg + i][k], fmaf(ah, sWl[cg + i][k], acc[i]));
+        }
       }
       __syncthreads();
     }
@@ -84,8 +109,13 @@ int launch_conv_gemm_simt(const GemmWeights& w, const OpBuf& a, int batch, int L
   const bool f32 = precision == SPARKCODEC_PREC_FP32;
   const int mt = (L + TM - 1) / TM;
   dim3 grid(batch * mt, w.n_total / TN);
-  conv_gemm_simt_kernel<<<grid, 256, 0, stream>>>(p, a.hi, f32 ? a.lo : nullptr, w.w_hi, f32 ? w.w_lo : nullptr,
-                                                 w.kt, mt);
+  const int terms = f32 ? fp32_terms() : 1;
+  if (a.fmt != op_fmt_for(precision)) {
+    set_error("simt gemm: operand planes are not in the format of this precision mode");
+    return SPARKCODEC_EINVAL;
+  }
+  conv_gemm_simt_kernel<<<grid, 256, 0, stream>>>(p, a.hi, f32 ? a.lo : nullptr, w.hi_for(terms),
+                                                 f32 ? w.lo_for(terms) : nullptr, w.kt, mt, a.fmt);
   SC_LAUNCH_CHECK();
   return 0;
 }

@@ -14,21 +14,10 @@
 namespace sparkcodec {
 namespace {
 
+// four consecutive channels at flat element index idx (idx % 4 == 0; every channel count here is a multiple of 32, so
+// the 32-channel groups of OPFMT_F16F8 are also groups of the flat index)
 __device__ __forceinline__ void store_op4(const OpBuf& o, size_t idx, float4 v) {
-  __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
-  uint2 hp;
-  hp.x = *reinterpret_cast<uint32_t*>(&h0);
-  hp.y = *reinterpret_cast<uint32_t*>(&h1);
-  *reinterpret_cast<uint2*>(o.hi + idx) = hp;
-  if (o.lo) {
-    float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
-    __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y);
-    __nv_bfloat162 l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
-    uint2 lp;
-    lp.x = *reinterpret_cast<uint32_t*>(&l0);
-    lp.y = *reinterpret_cast<uint32_t*>(&l1);
-    *reinterpret_cast<uint2*>(o.lo + idx) = lp;
-  }
+  store_planes4(o.hi, o.lo, o.fmt, idx & ~(size_t)31, (int)(idx & 31), v.x, v.y, v.z, v.w);
 }
 
 // ------------------------------------------------------------------------------- split / merge
@@ -47,8 +36,14 @@ __global__ void split_rows_kernel(const float* __restrict__ x, size_t src_batch_
 }
 __global__ void merge_kernel(OpBuf in, float* __restrict__ out, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    float v = __bfloat162float(in.hi[i]);
-    if (in.lo) v += __bfloat162float(in.lo[i]);
+    float v;
+    if (in.fmt == OPFMT_F16F8) {
+      v = __half2float(reinterpret_cast<const __half*>(in.hi)[i]);
+      v += e5m2_to_float(reinterpret_cast<const uint8_t*>(in.lo)[(i >> 5) * 64 + (i & 31)]) * (1.0f / (float)(1 << kLoShift));
+    } else {
+      v = __bfloat162float(in.hi[i]);
+      if (in.lo) v += __bfloat162float(in.lo[i]);
+    }
     out[i] = v;
   }
 }

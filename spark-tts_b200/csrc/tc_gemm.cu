@@ -19,8 +19,10 @@
 //                        transpose slab -> bias / residual / Snake / GELU -> coalesced fp32 + bf16 hi/lo stores,
 //                        overlapped with the next tile's MMAs through the second TMEM stage
 //   warp 18 / one lane : residual TMA producer (instantiations with a residual input)
-// Precision modes: NTERMS == 1 : A_hi*W_hi (bf16);  NTERMS == 3 : A_hi*W_hi + A_lo*W_hi + A_hi*W_lo
-// (error-compensated split, ~2^-16 relative per product, fp32 accumulate) = the "fp32" mode.
+// Precision modes: NTERMS == 1 : A_hi*W_hi (bf16);  NTERMS == 3 : A_hi*W_hi + A_lo*W_hi + A_hi*W_lo in bf16
+// (error-compensated split, ~2^-16 relative per product, fp32 accumulate);  NTERMS == 2 (the default "fp32" mode):
+// A_hi*W_hi in fp16 (kind::f16) + both cross terms as e5m2 products (kind::f8f6f4, K = 32 per MMA) read from the packed
+// second plane -- see OPFMT_F16F8 in common.cuh.  Same bytes per stage as NTERMS == 3, two thirds of its tensor time.
 #include <algorithm>
 #include <cstdlib>
 
@@ -48,7 +50,7 @@ constexpr int align_up(int v, int a) { return (v + a - 1) / a * a; }
 //             the per-(tap, K-chunk) W tiles.  Cuts the L2->smem operand traffic by 26-45 %.
 template <int BLOCK_N, int BK, int NTERMS, bool RES, bool HALO, int CG>
 struct TileCfg {
-  static constexpr int kPlanes = (NTERMS == 3) ? 2 : 1;
+  static constexpr int kPlanes = (NTERMS >= 2) ? 2 : 1;
   static constexpr int kABytes = kBlockM * BK * 2;
   static constexpr int kWBytes = (BLOCK_N / CG) * BK * 2;   // CTA-pair mode: each CTA stages half of the N rows
   static constexpr int kSlabBytes = kBlockM * 128;   // epilogue transpose slab: 128 rows x 32 fp32, 128B-swizzled
@@ -147,7 +149,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_a_hi);
     prefetch_tmap(&tm_w_hi);
-    if (NTERMS == 3) {
+    if (NTERMS >= 2) {
       prefetch_tmap(&tm_a_lo);
       prefetch_tmap(&tm_w_lo);
     }
@@ -204,14 +206,14 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
             const uint32_t sa = smem_base + stage * Cfg::kStage1Bytes;
             if (leader) mbar_expect_tx(full_bar(stage), CG * a_tx);   // bytes of every CTA of the pair
             load_a(sa, &tm_a_hi, full_bar(stage), kc * BK, l0 + p.taps.shift[ph][0], b);
-            if (NTERMS == 3) load_a(sa + Cfg::kAHaloBytes, &tm_a_lo, full_bar(stage), kc * BK, l0 + p.taps.shift[ph][0], b);
+            if (NTERMS >= 2) load_a(sa + Cfg::kAHaloBytes, &tm_a_lo, full_bar(stage), kc * BK, l0 + p.taps.shift[ph][0], b);
             if (++stage == S) { stage = 0; phase ^= 1u; }
             for (int j = 0; j < ntaps; ++j) {
               mbar_wait(wempty_bar(ws), wphase ^ 1u);
               const uint32_t sw = ring2_base + ws * Cfg::kStage2Bytes;
               if (leader) mbar_expect_tx(wfull_bar(ws), CG * Cfg::kStage2Bytes);
               load_w(sw, &tm_w_hi, wfull_bar(ws), j * p.c_in + kc * BK, n0);
-              if (NTERMS == 3) load_w(sw + Cfg::kWBytes, &tm_w_lo, wfull_bar(ws), j * p.c_in + kc * BK, n0);
+              if (NTERMS >= 2) load_w(sw + Cfg::kWBytes, &tm_w_lo, wfull_bar(ws), j * p.c_in + kc * BK, n0);
               if (++ws == S2) { ws = 0; wphase ^= 1u; }
             }
           }
@@ -225,7 +227,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
               if (leader) mbar_expect_tx(full_bar(stage), CG * Cfg::kStage1Bytes);
               load_a(sa, &tm_a_hi, full_bar(stage), kc * BK, row, b);
               load_w(sw, &tm_w_hi, full_bar(stage), j * p.c_in + kc * BK, n0);
-              if (NTERMS == 3) {
+              if (NTERMS >= 2) {
                 load_a(sa + Cfg::kABytes, &tm_a_lo, full_bar(stage), kc * BK, row, b);
                 load_w(sw + Cfg::kWBytes, &tm_w_lo, full_bar(stage), j * p.c_in + kc * BK, n0);
               }
@@ -239,10 +241,18 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     // ================================ MMA issuer ================================
     // pair mode: the leader CTA's thread issues the M = 256 MMAs for both CTAs
     if (leader && elect_one()) {
-      constexpr uint32_t idesc = CG > 1 ? make_idesc_cg2<BLOCK_N>() : make_idesc<BLOCK_N>();
+      constexpr int HF = NTERMS == 2 ? 0 : 1;   // kind::f16 operand format: fp16 (two-term mode) or bf16
+      constexpr uint32_t idesc = CG > 1 ? make_idesc_cg2<BLOCK_N, HF>() : make_idesc<BLOCK_N, HF>();
+      constexpr uint32_t idesc8 = CG > 1 ? make_idesc_cg2<BLOCK_N, 1>() : make_idesc<BLOCK_N, 1>();   // e5m2 x e5m2
       auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t accumulate) {
         if (CG > 1) umma_bf16_cg2(d, a, b, idesc, accumulate);
         else umma_bf16(d, a, b, idesc, accumulate);
+      };
+      // cross terms of the two-term mode: 32 e5m2 values per K step = the same 32 B stride as a kind::f16 step; the
+      // packed planes alternate [A_lo | A_hi] against [W_hi | W_lo] every 32 bytes
+      auto mma8 = [&](uint32_t d, uint64_t a, uint64_t b) {
+        if (CG > 1) umma_f8_cg2(d, a, b, idesc8, 1u);
+        else umma_f8(d, a, b, idesc8, 1u);
       };
       auto commit = [&](uint32_t bar) {     // pair mode: arrives on the barrier at this offset in BOTH CTAs
         if (CG > 1) umma_commit_cg2(bar);
@@ -271,13 +281,18 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
               const uint64_t w_hi = make_smem_desc<BK>(sw);
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) mma(d_tmem, a_hi + 2 * k, w_hi + 2 * k, (kc | j | k) != 0);
-              if (NTERMS == 3) {
+              if (NTERMS >= 2) {
                 const uint64_t a_lo = make_smem_desc_rows<BK>(sa + Cfg::kAHaloBytes + a_off, p.halo_bo_mode);
                 const uint64_t w_lo = make_smem_desc<BK>(sw + Cfg::kWBytes);
+                if (NTERMS == 2) {
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k) mma(d_tmem, a_lo + 2 * k, w_hi + 2 * k, 1u);
+                  for (int k = 0; k < BK / 16; ++k) mma8(d_tmem, a_lo + 2 * k, w_lo + 2 * k);
+                } else {
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k) mma(d_tmem, a_hi + 2 * k, w_lo + 2 * k, 1u);
+                  for (int k = 0; k < BK / 16; ++k) mma(d_tmem, a_lo + 2 * k, w_hi + 2 * k, 1u);
+#pragma unroll
+                  for (int k = 0; k < BK / 16; ++k) mma(d_tmem, a_hi + 2 * k, w_lo + 2 * k, 1u);
+                }
               }
               commit(wempty_bar(ws));
               if (++ws == S2) { ws = 0; wphase ^= 1u; }
@@ -297,13 +312,18 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)   // +32 B (=2 in >>4 units) per 16-element K step inside the swizzle row
               mma(d_tmem, a_hi + 2 * k, w_hi + 2 * k, (ki | k) != 0);
-            if (NTERMS == 3) {
+            if (NTERMS >= 2) {
               const uint64_t a_lo = make_smem_desc<BK>(sa + Cfg::kABytes);
               const uint64_t w_lo = make_smem_desc<BK>(sw + Cfg::kWBytes);
+              if (NTERMS == 2) {
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) mma(d_tmem, a_lo + 2 * k, w_hi + 2 * k, 1u);
+                for (int k = 0; k < BK / 16; ++k) mma8(d_tmem, a_lo + 2 * k, w_lo + 2 * k);
+              } else {
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) mma(d_tmem, a_hi + 2 * k, w_lo + 2 * k, 1u);
+                for (int k = 0; k < BK / 16; ++k) mma(d_tmem, a_lo + 2 * k, w_hi + 2 * k, 1u);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) mma(d_tmem, a_hi + 2 * k, w_lo + 2 * k, 1u);
+              }
             }
             commit(empty_bar(stage));                    // smem slot free once these MMAs retire
             if (ki == n_k - 1) commit(tfull_bar(acc));   // accumulator complete -> epilogue
@@ -444,6 +464,20 @@ int g_halo_mode = [] {
   return e ? atoi(e) : 1;
 }();
 
+}  // namespace
+
+// MMA terms of the fp32 precision mode (common.cuh): 2 = fp16 main term + two e5m2 cross terms (default), 3 = bf16 x 3
+int fp32_terms() {
+  static const int t = [] {
+    const char* e = getenv("SPARKCODEC_FP32_TERMS");
+    const int v = e ? atoi(e) : 2;
+    return v == 3 ? 3 : 2;
+  }();
+  return t;
+}
+
+namespace {
+
 int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                const uint32_t* box, int bk, bool weights, bool fp32 = false) {
   cuuint64_t gdim[3], gstr[2];
@@ -477,8 +511,12 @@ int launch_inst(const GemmWeights& w, const OpBuf& a, int batch, int L, const Co
   const uint64_t strides[2] = {(uint64_t)w.c_in * 2, (uint64_t)L * w.c_in * 2};
   const uint32_t box[3] = {(uint32_t)BK, (uint32_t)(HALO ? p.halo_rows : kBlockM), 1u};
   SC_TRY(encode_map(&ta_hi, a.hi, 3, dims, strides, box, BK, false));
-  if (NTERMS == 3) SC_TRY(encode_map(&ta_lo, a.lo, 3, dims, strides, box, BK, false));
+  if (NTERMS >= 2) SC_TRY(encode_map(&ta_lo, a.lo, 3, dims, strides, box, BK, false));
   else ta_lo = ta_hi;
+  if (a.fmt != (NTERMS == 2 ? OPFMT_F16F8 : OPFMT_BF16)) {
+    set_error("conv_gemm: operand planes are in format %d, the %d-term kernel needs the other one", a.fmt, NTERMS);
+    return SPARKCODEC_EINVAL;
+  }
   CUtensorMap t_res = ta_hi;
   if (RES) {
     const uint64_t rdims[3] = {(uint64_t)w.n_total, (uint64_t)L, (uint64_t)batch};
@@ -488,13 +526,14 @@ int launch_inst(const GemmWeights& w, const OpBuf& a, int batch, int L, const Co
   }
   // weight maps: the cached (BK x BLOCK_N) boxes, or (BK x BLOCK_N / 2) boxes for a CTA pair
   constexpr int mi = BK == 64 ? 0 : 1;
-  CUtensorMap tw_hi = w.tmap_hi[mi], tw_lo = NTERMS == 3 ? w.tmap_lo[mi] : w.tmap_hi[mi];
+  CUtensorMap tw_hi = NTERMS == 2 ? w.tmap_h16[mi] : w.tmap_hi[mi];
+  CUtensorMap tw_lo = NTERMS == 3 ? w.tmap_lo[mi] : (NTERMS == 2 ? w.tmap_p8[mi] : w.tmap_hi[mi]);
   if (CG > 1) {
     const uint64_t wd[2] = {(uint64_t)w.kt * w.c_in, (uint64_t)w.n_total};
     const uint64_t ws[1] = {(uint64_t)w.kt * w.c_in * 2};
     const uint32_t wb[2] = {(uint32_t)BK, (uint32_t)(BLOCK_N / CG)};
-    SC_TRY(encode_map(&tw_hi, w.w_hi, 2, wd, ws, wb, BK, true));
-    if (NTERMS == 3) SC_TRY(encode_map(&tw_lo, w.w_lo, 2, wd, ws, wb, BK, true));
+    SC_TRY(encode_map(&tw_hi, w.hi_for(NTERMS), 2, wd, ws, wb, BK, true));
+    if (NTERMS >= 2) SC_TRY(encode_map(&tw_lo, w.lo_for(NTERMS), 2, wd, ws, wb, BK, true));
     else tw_lo = tw_hi;
   }
   auto kern = conv_gemm_tc_kernel<BLOCK_N, BK, NTERMS, RES, HALO, CG>;
@@ -592,6 +631,8 @@ int make_weight_tmaps(GemmWeights& w) {
     const uint32_t box[2] = {(uint32_t)bk, (uint32_t)w.block_n};
     SC_TRY(encode_map(&w.tmap_hi[mi], w.w_hi, 2, dims, strides, box, bk, true));
     SC_TRY(encode_map(&w.tmap_lo[mi], w.w_lo, 2, dims, strides, box, bk, true));
+    SC_TRY(encode_map(&w.tmap_h16[mi], w.w_h16, 2, dims, strides, box, bk, true));
+    SC_TRY(encode_map(&w.tmap_p8[mi], w.w_p8, 2, dims, strides, box, bk, true));
   }
   return 0;
 }
@@ -613,6 +654,11 @@ int fill_params(const GemmWeights& w, int batch, int L, const Epilogue& ep, int 
   p->alpha = ep.alpha; p->inv_alpha = ep.inv_alpha; p->act = ep.act;
   p->out_f32 = ep.out_f32; p->out_hi = ep.out_op.hi;
   p->out_lo = (precision == SPARKCODEC_PREC_FP32) ? ep.out_op.lo : nullptr;
+  p->out_fmt = ep.out_op.fmt;
+  if (ep.out_op.hi != nullptr && ep.out_op.fmt != op_fmt_for(precision)) {
+    set_error("output operand planes are not in the format of this precision mode");
+    return SPARKCODEC_EINVAL;
+  }
   return 0;
 }
 
@@ -621,6 +667,7 @@ int launch_conv_gemm_tc(const GemmWeights& w, const OpBuf& a, int batch, int L, 
   ConvGemmParams p;
   SC_TRY(fill_params(w, batch, L, ep, precision, &p));
   const bool f32 = precision == SPARKCODEC_PREC_FP32;
+  const int terms = f32 ? fp32_terms() : 1;
   const bool res = ep.residual != nullptr;
   // halo reuse: every conv with more than one tap (k=7 convs, conv-in, embed convs, polyphase up-samplers)
   int max_taps = 0, span = 0;
@@ -653,14 +700,14 @@ int launch_conv_gemm_tc(const GemmWeights& w, const OpBuf& a, int batch, int L, 
     if (p.halo_rows > kHaloRowsMax) halo = false;
     else bk = choose_bk_halo(w.c_in, w.block_n, precision);
   }
-#define SC_INST2(BN, BKK, CGV)                                                                         \
-    if (halo)                                                                                          \
-      return f32 ? launch_inst<BN, BKK, 3, false, true, CGV>(w, a, batch, L, p, num_sms, stream)       \
-                 : launch_inst<BN, BKK, 1, false, true, CGV>(w, a, batch, L, p, num_sms, stream);      \
-    return res ? (f32 ? launch_inst<BN, BKK, 3, true, false, CGV>(w, a, batch, L, p, num_sms, stream)  \
-                      : launch_inst<BN, BKK, 1, true, false, CGV>(w, a, batch, L, p, num_sms, stream)) \
-               : (f32 ? launch_inst<BN, BKK, 3, false, false, CGV>(w, a, batch, L, p, num_sms, stream) \
-                      : launch_inst<BN, BKK, 1, false, false, CGV>(w, a, batch, L, p, num_sms, stream));
+#define SC_INST3(BN, BKK, CGV, RESV, HALOV)                                                            \
+    return terms == 3 ? launch_inst<BN, BKK, 3, RESV, HALOV, CGV>(w, a, batch, L, p, num_sms, stream)  \
+         : terms == 2 ? launch_inst<BN, BKK, 2, RESV, HALOV, CGV>(w, a, batch, L, p, num_sms, stream)  \
+                      : launch_inst<BN, BKK, 1, RESV, HALOV, CGV>(w, a, batch, L, p, num_sms, stream);
+#define SC_INST2(BN, BKK, CGV)                       \
+    if (halo) { SC_INST3(BN, BKK, CGV, false, true) } \
+    if (res) { SC_INST3(BN, BKK, CGV, true, false) }  \
+    SC_INST3(BN, BKK, CGV, false, false)
 #define SC_INST(BN, BKK)                   \
   if (w.block_n == BN && bk == BKK) {      \
     if (pair) { SC_INST2(BN, BKK, 2) }     \
@@ -668,6 +715,7 @@ int launch_conv_gemm_tc(const GemmWeights& w, const OpBuf& a, int batch, int L, 
   }
   SC_INST(256, 64) SC_INST(192, 64) SC_INST(128, 64) SC_INST(96, 64) SC_INST(64, 64)
   SC_INST(256, 32) SC_INST(192, 32) SC_INST(128, 32) SC_INST(96, 32) SC_INST(64, 32)
+#undef SC_INST3
 #undef SC_INST2
 #undef SC_INST
   set_error("no tcgen05 instantiation for block_n=%d bk=%d", w.block_n, bk);

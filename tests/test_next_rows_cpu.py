@@ -16,7 +16,8 @@ def _write_checkpoint(tmp_path, cfg, state_dict):
     d = tmp_path / "BiCodec"
     d.mkdir()
     doc = {"audio_tokenizer": {
-        "mel_params": {"sample_rate": 16000, "n_fft": 1024, "win_length": 640, "hop_length": 320, "num_mels": 128},
+        "mel_params": {"sample_rate": 16000, "n_fft": 1024, "win_length": 640, "hop_length": 320, "mel_fmin": 10, "mel_fmax": None,
+                       "num_mels": 128},
         "encoder": {"input_channels": 1024, "vocos_dim": 384, "vocos_intermediate_dim": 2048, "vocos_num_layers": 12,
                     "out_channels": 1024, "sample_ratios": [1, 1]},
         "decoder": {"input_channel": cfg.d_model, "channels": cfg.dec_channels, "rates": list(cfg.rates),

@@ -1,6 +1,7 @@
 """First-contact GPU diagnostic: runs each check in its own subprocess with a timeout (a trapped kernel
 poisons its CUDA context), prints one line per check.  Usage on the GPU box:
-    python tools/gpu_diag.py [group ...]        groups: ops_simt ops_tc taps_simt taps_tc full
+    python tools/gpu_diag.py [group ...]        groups: ops_simt ops_tc taps_simt taps_tc taps_tc_unfused full
+    (SPARKCODEC_FP32_TERMS=3 in the environment selects the three-term bf16 split of the fp32 mode)
 """
 import os
 import subprocess
@@ -74,7 +75,7 @@ def child(name: str):
     sd = synthetic_state_dict(cfg, 0)
     model = BiCodec.from_state_dict(cfg, sd, device=dev)
     if name.startswith("taps_"):
-        impl = name.split("_")[1]
+        impl = name.split("_", 1)[1]          # simt | tc | tc_unfused
         model.set_impl(impl)
         B, T = 2, 40
         sem, glob = synthetic_tokens(cfg, B, T, 77)

@@ -35,7 +35,8 @@ for _ in range(passes):          # min over passes per launch: the pool's GPUs /
             a["ms"] = min(a["ms"], b["ms"])
 total = sum(r["ms"] for r in rows)
 print(f"# B={B} T={T} {prec}: {len(rows)} launches, {total:.2f} ms total (sum of per-launch events, min over {passes} passes)")
-work = 3.0 if prec == "fp32" else 1.0
+from spark_tts_b200 import _lib
+work = float(_lib.load().sparkcodec_fp32_terms()) if prec == "fp32" else 1.0   # bf16-MMA equivalents per MAC
 agg = {}
 order = []
 for r in rows:
