@@ -48,7 +48,10 @@ enum { SPARKCODEC_I32 = 0, SPARKCODEC_I64 = 1 };
  *          (env SPARKCODEC_FP32_TERMS=3; sparkcodec_fp32_terms() reports which)
  *          (parity bound vs the reference fp32: max-abs 1e-3, SNR >= 60 dB)
  *   BF16 : single bf16 product, fp32 accumulate (looser stated bound)            */
-enum { SPARKCODEC_PREC_FP32 = 0, SPARKCODEC_PREC_BF16 = 1 };
+enum { SPARKCODEC_PREC_FP32 = 0, SPARKCODEC_PREC_BF16 = 1,
+       /* FP32 with the three-term bf16 split whatever the process default (~2^-17 per product, 1.5 x the tensor time):
+        * what the encode side (tokenize) asks for, where a rounding flips a discrete token */
+       SPARKCODEC_PREC_FP32X3 = 2 };
 
 /* which implementation of the dense contractions runs: tcgen05 tensor cores (product path: one kernel
  * per conv, the narrow ResidualUnits as ONE fused kernel each), the CUDA-core verification kernel with
@@ -249,6 +252,12 @@ SPARKCODEC_API int sparkcodec_profile_read(sparkcodec_handle* h, char* buf, size
 /* Number of this library's kernel launches issued since the handle was created (bench.py's
  * `gpu_launches`). */
 SPARKCODEC_API int sparkcodec_launch_count(sparkcodec_handle* h, int64_t* count);
+
+/* Test hook, no GPU needed: like sparkcodec_pack_conv, but returns the weight planes of the two-term fp32 mode --
+ * w_h16 = fp16(W) bits and w_p8 = per row and group of 32 K values, 64 bytes [ e5m2(fp16(W) * 2^-4) x 32 |
+ * e5m2((W - fp16(W)) * 2^8) x 32 ], both (n_total, kt*c_in) x 2 bytes.  EINVAL when kt*c_in is not a multiple of 32. */
+SPARKCODEC_API int sparkcodec_pack_conv_f16f8(int kind, const float* w_host, const int64_t* wshape, int param,
+                                              uint16_t* w_h16, uint16_t* w_p8, size_t w_capacity);
 
 /* Tensor-core products per multiply-accumulate of the FP32 precision mode in this process: 2 (fp16 main term + two
  * e5m2 cross terms = 2 bf16-MMA equivalents of tensor time) or 3 (bf16 x 3).  bench.py's `tensor_work_factor`. */

@@ -12,11 +12,12 @@ LIB_PATH = os.environ.get("SPARKCODEC_LIB") or os.path.join(_HERE, "libsparkcode
 
 OK, EINVAL, EINDEX, ECUDA, ESTATE, ENOMEM, EMISSING = 0, -1, -2, -3, -4, -5, -6
 I32, I64 = 0, 1
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_BF16, PREC_FP32X3 = 0, 1, 2
 IMPL_TC, IMPL_SIMT, IMPL_TC_UNFUSED = 0, 1, 2
 ACT_NONE, ACT_GELU, ACT_SNAKE = 0, 1, 2
 
-PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16}
+# "fp32x3": the fp32 mode with the three-term bf16 split whatever the process default (the encode side uses it)
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "fp32x3": PREC_FP32X3}
 
 
 class SparkCodecConfig(C.Structure):
@@ -73,6 +74,8 @@ SIGNATURES = {
     "sparkcodec_pack_conv": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_int64), C.c_int, C.c_void_p, C.c_void_p,
                                        C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32),
                                        C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "sparkcodec_pack_conv_f16f8": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_int64), C.c_int, C.c_void_p, C.c_void_p,
+                                             C.c_size_t]),
     "sparkcodec_launch_count": (C.c_int, [_H, C.POINTER(C.c_int64)]),
     "sparkcodec_fp32_terms": (C.c_int, []),
     "sparkcodec_profile": (C.c_int, [_H, C.c_int]),

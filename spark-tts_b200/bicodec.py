@@ -379,7 +379,11 @@ class BiCodec:
         ``quantizer.tokenize(encoder(feat.transpose(1, 2)))``.  feat (B, T, d_model) fp32 (the wav2vec2 feature
         mix) -> semantic tokens (B, T) int64.  Needs a checkpoint that carries ``encoder.*`` and
         ``quantizer.in_project.*``.  With ``return_margin`` also returns the (B, T) fp32 gap between the best and
-        the second-best code distance (a near-zero gap marks a numerical tie).  (Speaker half: ``tokenize_speaker``.)"""
+        the second-best code distance (a near-zero gap marks a numerical tie).  (Speaker half: ``tokenize_speaker``.)
+        A model in "fp32" mode runs this side as "fp32x3" (three bf16 products per MAC, ~2^-17 relative) unless the
+        caller names a precision: the output is a discrete index, and the encoder runs once per prompt."""
+        if precision is None and self.precision == "fp32":
+            precision = "fp32x3"
         self._ensure(feat)
         if feat.dim() != 3 or feat.shape[2] != self.cfg.d_model or feat.dtype != torch.float32:
             raise ValueError(f"feat must be float32 (B, T, {self.cfg.d_model})")

@@ -714,7 +714,7 @@ struct TapReq {
 };
 
 static OpBuf mode_op(OpBuf o, int prec) {
-  if (prec != SPARKCODEC_PREC_FP32) o.lo = nullptr;
+  if (!is_split(prec)) o.lo = nullptr;
   o.fmt = op_fmt_for(prec);
   return o;
 }
@@ -748,7 +748,7 @@ struct Pass {
         macs += (double)w.taps.ntaps[r] * w.c_in * w.taps.cols_per_phase;
         tmax = std::max(tmax, w.taps.ntaps[r]);
       }
-      const double planes = prec == SPARKCODEC_PREC_FP32 ? 4.0 : 2.0;   // bytes per operand element
+      const double planes = is_split(prec) ? 4.0 : 2.0;   // bytes per operand element
       double bytes = (double)B * L * w.c_in * planes + (double)w.n_total * w.kt * w.c_in * planes;
       if (ep.residual) bytes += (double)B * L * w.n_total * 4;
       if (ep.out_f32) bytes += (double)B * L * w.n_total * 4;
@@ -810,7 +810,7 @@ static int run_backbone(Pass& P, Backbone& bb, const std::string& name, Workspac
     ConvNeXt& blk = bb.blocks[i];
     sc = ada ? ada + (size_t)(i + 1) * 2 * C : blk.ln_w;
     sh = ada ? ada + (size_t)(i + 1) * 2 * C + C : blk.ln_b;
-    SC_TRY(P.prof_begin("dwconv_ln", 0, (double)B * T * C * (4 + (prec == SPARKCODEC_PREC_FP32 ? 4 : 2))));
+    SC_TRY(P.prof_begin("dwconv_ln", 0, (double)B * T * C * (4 + (is_split(prec) ? 4 : 2))));
     SC_TRY(launch_dwconv_ln(W.px, B, T, C, blk.dw_w, blk.dw_b, sc, sh, ada ? ada_n : 0, 1e-6f, nullptr, pa, st));
     SC_TRY(P.prof_end());
     Epilogue e1;
@@ -944,7 +944,7 @@ static int run_pass(Pass& P, const void* sem, int sem_dt, const void* glob, int 
       if (h->impl == SPARKCODEC_IMPL_TC && resunit_fusable(ru.c7, ru.c1, &dil)) {
         // narrow stages: the whole ResidualUnit is one kernel, `mid` never reaches HBM
         if (h->profile) {
-          const double planes = prec == SPARKCODEC_PREC_FP32 ? 4.0 : 2.0, C = ub.c_out;
+          const double planes = is_split(prec) ? 4.0 : 2.0, C = ub.c_out;
           char nm[160];
           snprintf(nm, sizeof(nm), "resunit_fused c=%d dil=%d L=%d", ub.c_out, dil, L);
           SC_TRY(P.prof_begin(nm, 2.0 * B * L * 8.0 * C * C,
@@ -1112,7 +1112,7 @@ static int check_common(sparkcodec_handle* h, int batch, int frames, int precisi
   if (!h) { set_error("null handle"); return SPARKCODEC_EINVAL; }
   if (!h->finalized) { set_error("sparkcodec_finalize has not been called"); return SPARKCODEC_ESTATE; }
   if (batch < 0 || frames < 0) { set_error("negative batch/frames"); return SPARKCODEC_EINVAL; }
-  if (precision != SPARKCODEC_PREC_FP32 && precision != SPARKCODEC_PREC_BF16) {
+  if (precision != SPARKCODEC_PREC_FP32 && precision != SPARKCODEC_PREC_BF16 && precision != SPARKCODEC_PREC_FP32X3) {
     set_error("unknown precision %d", precision);
     return SPARKCODEC_EINVAL;
   }
@@ -1521,6 +1521,20 @@ int sparkcodec_launch_count(sparkcodec_handle* h, int64_t* count) {
 
 int sparkcodec_fp32_terms(void) { return fp32_terms(); }
 
+int sparkcodec_pack_conv_f16f8(int kind, const float* w_host, const int64_t* wshape, int param, uint16_t* w_h16,
+                               uint16_t* w_p8, size_t w_capacity) {
+  if (!w_host || !wshape || !w_h16 || !w_p8) { set_error("null argument"); return SPARKCODEC_EINVAL; }
+  PackedGemm pk;
+  if (kind == 0) pack_conv1d(w_host, (int)wshape[0], (int)wshape[1], (int)wshape[2], param, nullptr, nullptr, pk);
+  else if (kind == 1) pack_conv_transpose1d(w_host, (int)wshape[0], (int)wshape[1], (int)wshape[2], param, nullptr, pk);
+  else { set_error("kind must be 0 (Conv1d) or 1 (ConvTranspose1d)"); return SPARKCODEC_EINVAL; }
+  if (pk.w_h16.empty()) { set_error("K = %d x %d is not a multiple of 32", pk.kt, pk.c_in); return SPARKCODEC_EINVAL; }
+  if (pk.w_h16.size() > w_capacity) { set_error("w buffers too small (%zu needed)", pk.w_h16.size()); return SPARKCODEC_ENOMEM; }
+  memcpy(w_h16, pk.w_h16.data(), pk.w_h16.size() * 2);
+  memcpy(w_p8, pk.w_p8.data(), pk.w_p8.size() * 2);
+  return 0;
+}
+
 int sparkcodec_pack_conv(int kind, const float* w_host, const int64_t* wshape, int param, uint16_t* w_hi,
                          uint16_t* w_lo, size_t w_capacity, int32_t* shifts, int32_t* ntaps, int32_t* kt,
                          int32_t* n_phase, int32_t* n_total) {
@@ -1598,13 +1612,13 @@ int sparkcodec_op_conv(int device, int kind, const float* w_host, const int64_t*
         e.alpha = sp.alpha; e.inv_alpha = sp.inv;
       }
     }
-    if (precision != SPARKCODEC_PREC_FP32) { a.lo = nullptr; }
+    if (!is_split(precision)) { a.lo = nullptr; }
     if (impl == SPARKCODEC_IMPL_SIMT) rc = launch_conv_gemm_simt(g, a, batch, L, e, precision, st);
     else rc = launch_conv_gemm_tc(g, a, batch, L, e, precision, prop.multiProcessorCount, st);
     if (rc) break;
     if (act != ACT_NONE) {
       OpBuf m = o;
-      if (precision != SPARKCODEC_PREC_FP32) m.lo = nullptr;
+      if (!is_split(precision)) m.lo = nullptr;
       if ((rc = launch_merge(m, y_dev, n_out, st))) break;
     }
     cudaError_t ce = cudaStreamSynchronize(st);

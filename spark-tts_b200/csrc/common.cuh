@@ -63,9 +63,12 @@ struct OpBuf {
 };
 // MMA terms of the fp32 precision mode: 2 (default, OPFMT_F16F8) or 3 (OPFMT_BF16); env SPARKCODEC_FP32_TERMS
 int fp32_terms();
-inline int op_fmt_for(int precision) {
-  return (precision == SPARKCODEC_PREC_FP32 && fp32_terms() == 2) ? OPFMT_F16F8 : OPFMT_BF16;
+// tensor-core products per MAC of a precision mode: BF16 1, FP32 fp32_terms(), FP32X3 3
+inline int terms_for(int precision) {
+  return precision == SPARKCODEC_PREC_BF16 ? 1 : (precision == SPARKCODEC_PREC_FP32X3 ? 3 : fp32_terms());
 }
+inline bool is_split(int precision) { return precision != SPARKCODEC_PREC_BF16; }   // two operand planes
+inline int op_fmt_for(int precision) { return terms_for(precision) == 2 ? OPFMT_F16F8 : OPFMT_BF16; }
 
 constexpr int kMaxPhases = 8;   // polyphase branches of a transposed conv (= stride)
 constexpr int kMaxTaps = 7;     // taps per branch (k=7 convs; <=3 for the transposed convs)

@@ -65,8 +65,10 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// bf16 mode: the operand is rounded to 8 mantissa bits right after, so the SFU sine's own range handling is enough
-// (its absolute error grows with |alpha x| but stays orders of magnitude below 2^-9 for any activation seen here).
+// bf16 mode and the two-term fp32 mode: the SFU sine's own range handling is enough.  Its absolute error grows with
+// |alpha x| (~|alpha x| 2^-23) but stays far below what the operand rounding right after it costs (2^-9 in bf16 mode,
+// ~2^-15 for the e5m2 cross terms of the two-term mode): measured on the B200, the two-term waveform SNR is 73.0 dB with
+// either sine (profiles/r2_two_term_ab.txt).  Only the three-term bf16 split (~2^-17 per product) keeps the reduction.
 __device__ __forceinline__ float snake_fast(float x, float a, float inv) {
   const float s = __sinf(a * x);
   return fmaf(inv * s, s, x);
@@ -112,8 +114,13 @@ __device__ __forceinline__ void epilogue_store4(const ConvGemmParams& p, float4 
   if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + row_off + n) = acc;
   if (p.out_hi) {
     if (p.act == ACT_SNAKE) {
-      acc.x = snake_f(acc.x, alpha.x, inv.x); acc.y = snake_f(acc.y, alpha.y, inv.y);
-      acc.z = snake_f(acc.z, alpha.z, inv.z); acc.w = snake_f(acc.w, alpha.w, inv.w);
+      if (p.out_fmt == OPFMT_BF16 && p.out_lo != nullptr) {   // three-term fp32 mode: range-reduced sine
+        acc.x = snake_f(acc.x, alpha.x, inv.x); acc.y = snake_f(acc.y, alpha.y, inv.y);
+        acc.z = snake_f(acc.z, alpha.z, inv.z); acc.w = snake_f(acc.w, alpha.w, inv.w);
+      } else {
+        acc.x = snake_fast(acc.x, alpha.x, inv.x); acc.y = snake_fast(acc.y, alpha.y, inv.y);
+        acc.z = snake_fast(acc.z, alpha.z, inv.z); acc.w = snake_fast(acc.w, alpha.w, inv.w);
+      }
     } else if (p.act == ACT_GELU) {
       acc.x = gelu_erf(acc.x); acc.y = gelu_erf(acc.y); acc.z = gelu_erf(acc.z); acc.w = gelu_erf(acc.w);
     }

@@ -175,7 +175,7 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
                      const __grid_constant__ CUtensorMap tm_o_lo, const RuParams p) {
   static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of two");
   constexpr int PG = PAIR ? 2 : 1;
-  constexpr bool EXACT = NTERMS >= 2;   // both fp32 modes: range-reduced sine
+  constexpr bool EXACT = NTERMS == 3;   // range-reduced sine only where the products are accurate enough to see it
   using Cfg = RuCfg<C, NTERMS, PG>;
   constexpr int SA = Cfg::SA, SW = Cfg::SW, SR = Cfg::SR, NB1 = Cfg::NB1, NB2 = Cfg::NB2;
   constexpr int G = Cfg::G, SKEW = Cfg::SKEW, NMID = Cfg::kNumMid, NH = Cfg::NH, N2 = Cfg::N2;
@@ -928,7 +928,7 @@ int launch_resunit_fused(const GemmWeights& c7, const GemmWeights& c1, const OpB
     set_error("resunit_fused: unsupported layer shapes (C=%d)", c7.c_in);
     return SPARKCODEC_EINVAL;
   }
-  const bool f32 = precision == SPARKCODEC_PREC_FP32;
+  const bool f32 = is_split(precision);
   if (f32 && (!a.lo || (out.hi && !out.lo))) {
     set_error("resunit_fused: fp32 mode needs both operand planes");
     return SPARKCODEC_EINVAL;
@@ -937,7 +937,7 @@ int launch_resunit_fused(const GemmWeights& c7, const GemmWeights& c1, const OpB
     set_error("resunit_fused: operand planes are not in the format of this precision mode");
     return SPARKCODEC_EINVAL;
   }
-  const int terms = f32 ? fp32_terms() : 1;
+  const int terms = terms_for(precision);
   RuParams p;
   p.batch = batch; p.L = L; p.dil = dil;
   p.halo_rows = (kBlockM + 6 * dil + 7) / 8 * 8;

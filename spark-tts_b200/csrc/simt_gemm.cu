@@ -106,10 +106,10 @@ int launch_conv_gemm_simt(const GemmWeights& w, const OpBuf& a, int batch, int L
     set_error("simt gemm: unsupported shape n=%d c_in=%d", w.n_total, w.c_in);
     return SPARKCODEC_EINVAL;
   }
-  const bool f32 = precision == SPARKCODEC_PREC_FP32;
+  const bool f32 = is_split(precision);
   const int mt = (L + TM - 1) / TM;
   dim3 grid(batch * mt, w.n_total / TN);
-  const int terms = f32 ? fp32_terms() : 1;
+  const int terms = terms_for(precision);
   if (a.fmt != op_fmt_for(precision)) {
     set_error("simt gemm: operand planes are not in the format of this precision mode");
     return SPARKCODEC_EINVAL;

@@ -604,7 +604,7 @@ int choose_block_n(int cols_per_phase, int* block_n) {
 // still gets >= 3 stages, else 32 (64 B swizzle rows).
 int choose_bk(int c_in, int block_n, int precision, bool residual) {
   if (c_in % 64 != 0) return 32;
-  const int planes = precision == SPARKCODEC_PREC_FP32 ? 2 : 1;
+  const int planes = is_split(precision) ? 2 : 1;
   const int stage64 = planes * (kBlockM * 64 * 2 + block_n * 64 * 2);
   const int budget = 192 * 1024 - (residual ? kResSlots * kBlockM * 128 : 0);
   return budget / stage64 >= 3 ? 64 : 32;
@@ -613,7 +613,7 @@ int choose_bk(int c_in, int block_n, int precision, bool residual) {
 // K chunk for the halo mainloop: the W ring must keep >= 4 stages next to the halo tiles.
 int choose_bk_halo(int c_in, int block_n, int precision) {
   if (c_in % 64 != 0) return 32;
-  const int planes = precision == SPARKCODEC_PREC_FP32 ? 2 : 1;
+  const int planes = is_split(precision) ? 2 : 1;
   const int a64 = planes * align_up(kHaloRowsMax * 64 * 2, 1024), w64 = planes * block_n * 64 * 2;
   return (192 * 1024 - 2 * a64) / w64 >= 4 ? 64 : 32;
 }
@@ -638,7 +638,7 @@ int make_weight_tmaps(GemmWeights& w) {
 }
 
 int fill_params(const GemmWeights& w, int batch, int L, const Epilogue& ep, int precision, ConvGemmParams* p) {
-  if ((ep.out_op.hi != nullptr) && precision == SPARKCODEC_PREC_FP32 && ep.out_op.lo == nullptr) {
+  if ((ep.out_op.hi != nullptr) && is_split(precision) && ep.out_op.lo == nullptr) {
     set_error("fp32 mode needs both operand planes");
     return SPARKCODEC_EINVAL;
   }
@@ -653,7 +653,7 @@ int fill_params(const GemmWeights& w, int batch, int L, const Epilogue& ep, int 
   p->bias = w.bias; p->rowbias = ep.rowbias; p->residual = ep.residual;
   p->alpha = ep.alpha; p->inv_alpha = ep.inv_alpha; p->act = ep.act;
   p->out_f32 = ep.out_f32; p->out_hi = ep.out_op.hi;
-  p->out_lo = (precision == SPARKCODEC_PREC_FP32) ? ep.out_op.lo : nullptr;
+  p->out_lo = is_split(precision) ? ep.out_op.lo : nullptr;
   p->out_fmt = ep.out_op.fmt;
   if (ep.out_op.hi != nullptr && ep.out_op.fmt != op_fmt_for(precision)) {
     set_error("output operand planes are not in the format of this precision mode");
@@ -666,8 +666,8 @@ int launch_conv_gemm_tc(const GemmWeights& w, const OpBuf& a, int batch, int L, 
                         int num_sms, cudaStream_t stream) {
   ConvGemmParams p;
   SC_TRY(fill_params(w, batch, L, ep, precision, &p));
-  const bool f32 = precision == SPARKCODEC_PREC_FP32;
-  const int terms = f32 ? fp32_terms() : 1;
+  const bool f32 = is_split(precision);
+  const int terms = terms_for(precision);
   const bool res = ep.residual != nullptr;
   // halo reuse: every conv with more than one tap (k=7 convs, conv-in, embed convs, polyphase up-samplers)
   int max_taps = 0, span = 0;
@@ -686,8 +686,10 @@ int launch_conv_gemm_tc(const GemmWeights& w, const OpBuf& a, int batch, int L, 
   // SPARKCODEC_PAIR = 0 never, 1 heuristic (default), 2 always.
   static const int pair_mode = [] { const char* e = getenv("SPARKCODEC_PAIR"); return e ? atoi(e) : 1; }();
   const int k_total = max_taps * w.c_in;
-  const bool pair = p.num_m_tiles >= 2 &&
-                    (pair_mode == 2 || (pair_mode == 1 && k_total >= (f32 ? 768 : 1536)));
+  // (SPARKCODEC_PAIR_MINK: threshold experiments)
+  static const int pair_mink = [] { const char* e = getenv("SPARKCODEC_PAIR_MINK"); return e ? atoi(e) : 0; }();
+  const int mink = pair_mink ? pair_mink : (f32 ? 768 : 1536);
+  const bool pair = p.num_m_tiles >= 2 && (pair_mode == 2 || (pair_mode == 1 && k_total >= mink));
   bool halo = g_halo_mode != 0 && max_taps > 1 && ascending && !res;
   int bk = choose_bk(w.c_in, w.block_n, precision, res);
   if (halo) {

@@ -63,3 +63,18 @@ def pack_conv(weight: torch.Tensor, *, transposed: bool, param: int):
     return dict(w_hi=hi.reshape(n_total.value, kt.value * c_in), w_lo=lo.reshape(n_total.value, kt.value * c_in),
                 shifts=shifts.reshape(n_phase.value, kt.value), ntaps=ntaps, kt=kt.value, n_phase=n_phase.value,
                 n_total=n_total.value, c_in=c_in)
+
+
+def pack_conv_f16f8(weight: torch.Tensor, *, transposed: bool, param: int):
+    """Host-side weight planes of the two-term fp32 mode (no GPU): dict(w_h16 uint16 (n_total, K) = fp16 bits,
+    w_p8 uint8 (n_total, 2 K): per group of 32 K values 64 bytes [e5m2(fp16(W) 2^-4) x 32 | e5m2((W - fp16(W)) 2^8) x 32])."""
+    lib = _lib.load()
+    meta = pack_conv(weight, transposed=transposed, param=param)
+    w = weight.detach().to("cpu", torch.float32).contiguous()
+    wshape = (C.c_int64 * 3)(*w.shape)
+    n_total, K = meta["n_total"], meta["kt"] * meta["c_in"]
+    h16 = np.empty(n_total * K, dtype=np.uint16)
+    p8 = np.empty(n_total * K, dtype=np.uint16)
+    _lib.check(lib.sparkcodec_pack_conv_f16f8(1 if transposed else 0, C.c_void_p(w.data_ptr()), wshape, int(param),
+                                              h16.ctypes.data_as(C.c_void_p), p8.ctypes.data_as(C.c_void_p), n_total * K))
+    return dict(w_h16=h16.reshape(n_total, K), w_p8=p8.view(np.uint8).reshape(n_total, 2 * K), **{k: meta[k] for k in ("kt", "c_in", "n_total")})

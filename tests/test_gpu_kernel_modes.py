@@ -57,3 +57,9 @@ def test_all_kernel_modes_agree(tmp_path, prec):
         got = _run(tmp_path, name, prec, env)
         snr = snr_db(torch.from_numpy(ref), torch.from_numpy(got))
         assert snr >= floor, f"{name}: {snr:.1f} dB vs default"
+    if prec == "fp32":
+        # the other operand split of the fp32 mode (three bf16 products instead of fp16 + two e5m2 products) is
+        # different arithmetic: the two waveforms agree to the accuracy of the coarser one (~73 dB vs the oracle)
+        got = _run(tmp_path, "three_term_split", prec, {"SPARKCODEC_FP32_TERMS": "3"})
+        snr = snr_db(torch.from_numpy(ref), torch.from_numpy(got))
+        assert snr >= 66.0, f"three_term_split: {snr:.1f} dB vs default"

@@ -107,6 +107,49 @@ def test_matches_oracle(B, T, seed, model, cfg, state_dict, dev):
     _check(ref, wav, FP32_MAX_ABS, FP32_SNR)
 
 
+@pytest.mark.parametrize("prec", ["fp32", "fp32x3"])
+def test_both_fp32_operand_splits_meet_the_fp32_bar(prec, model, cfg, state_dict, dev):
+    """"fp32" = this process's default split (fp16 main product + two e5m2 cross products unless
+    SPARKCODEC_FP32_TERMS=3); "fp32x3" = three bf16 products whatever the default.  Both must meet the fp32 bar; the
+    three-term split must not be the less accurate one."""
+    from oracle import bicodec_oracle as O
+    from spark_tts_b200 import _lib
+    from spark_tts_b200.synthetic import synthetic_tokens
+    sem, glob = synthetic_tokens(cfg, 2, 150, 4242)
+    ref = O.detokenize(state_dict, cfg, sem, glob)
+    wav = model.detokenize(sem.to(dev), glob.to(dev), precision=prec).cpu()
+    _check(ref, wav, FP32_MAX_ABS, FP32_SNR)
+    if prec == "fp32x3":
+        assert O.snr_db(ref, wav) >= 74.0
+        dflt = model.detokenize(sem.to(dev), glob.to(dev), precision="fp32").cpu()
+        assert O.snr_db(ref, wav) >= O.snr_db(ref, dflt) - 0.5
+        assert _lib.load().sparkcodec_fp32_terms() in (2, 3)
+
+
+@pytest.mark.parametrize("prec,floor", [("fp32", 88.0), ("fp32x3", 95.0), ("bf16", 45.0)])
+def test_conv_op_tensor_cores_vs_cuda_cores_vs_float64(prec, floor, dev):
+    """One dilated k7 conv with a Snake epilogue through the stand-alone op entry point: the tcgen05 kernel and the
+    CUDA-core verification kernel (which forms the same operand products with FFMA) agree, and both sit at the
+    accuracy their operand split allows against a float64 convolution."""
+    import torch.nn.functional as F
+    from oracle.bicodec_oracle import snr_db
+    from spark_tts_b200 import ops
+    g = torch.Generator().manual_seed(31)
+    c = 192
+    w = torch.randn(c, c, 7, generator=g) / (c * 7) ** 0.5
+    b = torch.randn(c, generator=g) * 0.1
+    alpha = torch.rand(c, generator=g) + 0.5
+    x = torch.randn(2, 300, c, generator=g)
+    ref = F.conv1d(x.transpose(1, 2).double(), w.double(), b.double(), dilation=3, padding=9).transpose(1, 2)
+    ref = ref + torch.sin(alpha.double() * ref) ** 2 / (alpha.double() + 1e-9)
+    out = {}
+    for impl in ("tc", "simt"):
+        out[impl] = ops.conv(x.to(dev), w, b, transposed=False, param=3, act="snake", alpha=alpha, precision=prec,
+                             impl=impl).cpu()
+        assert snr_db(ref, out[impl]) >= floor, (impl, snr_db(ref, out[impl]))
+    assert snr_db(out["simt"], out["tc"]) >= floor + 6.0
+
+
 def test_tensor_core_path_matches_cuda_core_path(model, cfg, dev):
     """tcgen05 kernels vs the CUDA-core verification kernels fed the same operands."""
     from oracle.bicodec_oracle import snr_db

@@ -132,3 +132,28 @@ int main(void) {
                     "-lsparkcodec", f"-Wl,-rpath,{libdir}"], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and "abi ok" in out.stdout, (out.returncode, out.stdout, out.stderr)
+
+
+def test_two_term_weight_planes_follow_their_definition():
+    """OPFMT_F16F8 weight planes (csrc/common.cuh, csrc/pack.cpp): fp16(W), and per group of 32 K values the 64 bytes
+    [e5m2(fp16(W) * 2^-4) x 32 | e5m2((W - fp16(W)) * 2^8) x 32] -- checked against torch's own fp16 / float8_e5m2
+    round-to-nearest conversions, plus the error budget the two-term product relies on."""
+    from spark_tts_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    w = torch.randn(96, 64, 7, generator=g) / (64 * 7) ** 0.5
+    pk = ops.pack_conv_f16f8(w, transposed=False, param=3)
+    K = pk["kt"] * pk["c_in"]
+    wk = w.permute(0, 2, 1).reshape(96, K).contiguous()              # (n, tap * c_in + c): the packed K order
+    h16 = torch.from_numpy(pk["w_h16"].astype(np.int16)).view(torch.float16)
+    assert torch.equal(h16, wk.to(torch.float16))
+    p8 = torch.from_numpy(pk["w_p8"]).reshape(96, K // 32, 2, 32)
+    hi8 = p8[:, :, 0, :].reshape(96, K).contiguous().view(torch.float8_e5m2)
+    lo8 = p8[:, :, 1, :].reshape(96, K).contiguous().view(torch.float8_e5m2)
+    hf = h16.float()
+    assert torch.equal(hi8.view(torch.uint8), (hf * 2.0 ** -4).to(torch.float8_e5m2).view(torch.uint8))
+    assert torch.equal(lo8.view(torch.uint8), ((wk - hf) * 2.0 ** 8).to(torch.float8_e5m2).view(torch.uint8))
+    # what the tensor cores see of a weight: hi exactly, hi and lo again with 3 significant bits
+    assert ((hi8.float() * 2.0 ** 4 - hf).abs() <= hf.abs() * 2.0 ** -3 + 2.0 ** -13).all()
+    assert ((lo8.float() * 2.0 ** -8 - (wk - hf)).abs() <= (wk - hf).abs() * 2.0 ** -3 + 2.0 ** -25).all()
+    with pytest.raises(ValueError):
+        ops.pack_conv_f16f8(torch.randn(8, 24, 1), transposed=False, param=1)   # K = 24 is not a multiple of 32
