@@ -223,7 +223,7 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
   // barrier of the pair's leader CTA / arrive on it from either CTA
   auto lead = [&](uint32_t bar) { return PAIR ? mapa_shared(bar, 0) : bar; };
   auto arrive_lead = [&](uint32_t bar) {
-    if (PAIR) mbar_arrive_cluster(mapa_shared(bar, 0));
+    if (PAIR) mbar_arrive_cluster_relaxed(mapa_shared(bar, 0));   // tensor-memory hand-offs only (mid_full, acc2_empty)
     else mbar_arrive(bar);
   };
   const int cid = (int)blockIdx.x / CL, ncl = (int)gridDim.x / CL;

@@ -409,7 +409,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
         // after the team's last chunk ONE thread hands the TMEM stage back (a cluster-scope arrive by every thread
         // costs thousands of cycles in pair mode; the leader's MMA warp waits for both teams of both CTAs)
         if (ci == my_last && ew == 0 && lane == 0) {
-          if (CG > 1) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
+          if (CG > 1) mbar_arrive_cluster_relaxed(mapa_shared(tempty_bar(acc), 0));   // tensor-memory hand-off
           else mbar_arrive(tempty_bar(acc));
         }
         uint32_t rslab = 0, rs = 0;
@@ -435,7 +435,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
         if (RES) mbar_arrive(rempty_bar(rs));
       }
       if (my_last < 0 && ew == 0 && lane == 0) {   // (BLOCK_N == 32 only) a team without a chunk still releases the accumulator
-        if (CG > 1) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
+        if (CG > 1) mbar_arrive_cluster_relaxed(mapa_shared(tempty_bar(acc), 0));
         else mbar_arrive(tempty_bar(acc));
       }
     }

@@ -182,6 +182,15 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local_shared_addr, uint
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Same without the release: for hand-offs of TENSOR MEMORY only (an accumulator drained with tcgen05.ld, a mid operand
+// written with tcgen05.st).  Those are ordered by tcgen05.wait::ld / ::st + tcgen05.fence::before_thread_sync on this
+// side and tcgen05.fence::after_thread_sync behind the waiter's mbarrier wait; the release form additionally makes the
+// thread wait until all its earlier MEMORY operations are visible cluster-wide, which was measured at 3-5 k cycles
+// per arrive under load (event trace of the fused ResidualUnit: the chunk that hands an accumulator back took 4.8-6.9 k
+// cycles instead of 1.6 k) and stalled the whole team at its next named barrier.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // TMA loads of a CTA pair: data lands in THIS CTA, the bytes are completed on the barrier `cluster_bar`
 // (shared::cluster address, normally the leader CTA's)
 __device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0, int c1) {
