@@ -16,6 +16,9 @@ struct ConvGemmParams {
   int halo_bo_mode;      // halo mainloop: descriptor base-offset convention (see tc_gemm.cu)
   int halo_stages;       // halo mainloop: halo tiles in flight (2 or 3); the weight ring gets the rest of smem
   int dbg_skip_store;    // timing experiments only (SPARKCODEC_DEBUG_SKIP_STORE): skip the epilogue maths + stores
+  int ring_bytes;        // tcgen05 kernel: shared memory of the operand ring(s) (what the output staging leaves)
+  int xs_bytes;          // per epilogue team: fp32 output staging tile (0 when there is no fp32 output or it goes through the residual slab)
+  int ps_bytes;          // per epilogue team: operand-plane staging tiles (0 / 8 KB / 16 KB)
   // epilogue
   const float* bias;
   const float* rowbias;
@@ -31,7 +34,7 @@ struct ConvGemmParams {
 
 int fill_params(const GemmWeights& w, int batch, int L, const Epilogue& ep, int precision, ConvGemmParams* p);
 int choose_block_n(int cols_per_phase, int* block_n);
-int choose_bk(int c_in, int block_n, int precision, bool residual);
+int choose_bk(int c_in, int block_n, int precision, int ring_bytes);
 
 // snake(x) = x + sin(alpha x)^2 / (alpha + 1e-9)   (reference sparktts/modules/blocks/layers.py:32-39)
 // sin: two-constant Cody-Waite reduction to [-pi, pi], then the SFU sine (abs err ~2^-21 there).

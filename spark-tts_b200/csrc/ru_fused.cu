@@ -743,8 +743,14 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
             }
           }
         }
-        // the TMA unit has finished reading the slot's previous contents
-        mbar_wait(out_empty(slot), (n_use & 1u) ^ 1u);
+      }
+      // The TMA unit has finished reading the slot's previous contents.  Waited for even when there are no operand
+      // planes to stage (the last unit): without it the team could run up to SR chunks ahead of the output thread and
+      // complete a SECOND phase of the slot's `out_full` barrier before the output thread has looked at the first --
+      // a parity wait cannot tell two completed phases from none, and the output thread would wait forever (seen as a
+      // rare bounded-wait trap after a cold start, when the first TMA stores are slow).
+      mbar_wait(out_empty(slot), (n_use & 1u) ^ 1u);
+      if (has_out) {
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj) {
           const uint32_t off = (((uint32_t)(2 * half + jj)) ^ swz64) << 4;   // SWIZZLE_64B box layout

@@ -8,17 +8,19 @@
 // box and TMA out-of-bounds zero fill IS the convolution's zero padding (3-D map C x L x batch:
 // rows never bleed across utterances).
 //
-// Structure (persistent, warp specialised, one CTA per SM, 608 threads; optionally clusters of two CTAs that issue
-// cta_group::2 M = 256 MMAs -- "pair mode"):
+// Structure (persistent, warp specialised, one CTA per SM, 640 threads = 20 warps; optionally clusters of two CTAs that
+// issue cta_group::2 M = 256 MMAs -- "pair mode"):
 //   warp 0 / one lane  : TMA producer -> shared-memory rings (mbarrier full / empty).  Convs with several taps use the
 //                        HALO mainloop: one activation tile with the conv halo per K chunk (all taps read it through
 //                        row-offset descriptors) + a ring of per-(tap, K chunk) weight tiles; 1x1 convs / Linear layers
 //                        use one ring of {A, W} stages
 //   warp 1 / one lane  : tcgen05.mma issuer, accumulators in TMEM (2 stages of BLOCK_N columns)
-//   warps 2..9, 10..17 : two epilogue teams on alternate 32-column chunks of an accumulator: tcgen05.ld -> swizzled
-//                        transpose slab -> bias / residual / Snake / GELU -> coalesced fp32 + bf16 hi/lo stores,
-//                        overlapped with the next tile's MMAs through the second TMEM stage
-//   warp 18 / one lane : residual TMA producer (instantiations with a residual input)
+//   warps 2..9, 10..17 : two epilogue teams on alternate 32-column chunks of an accumulator.  A thread owns 16 columns
+//                        of its row: tcgen05.ld -> (+ residual slab, in place) + bias -> fp32 staging tile -> Snake /
+//                        GELU -> operand-plane split -> plane staging tiles, all in the TMA box layouts; overlapped with
+//                        the next tile's MMAs through the second TMEM stage
+//   warps 18, 19 / one lane each : output threads, one per team: TMA stores of the staged tiles (fp32 and / or operand
+//                        planes) and TMA loads of the fp32 residual slabs (instantiations with a residual input)
 // Precision modes: NTERMS == 1 : A_hi*W_hi (bf16);  NTERMS == 3 : A_hi*W_hi + A_lo*W_hi + A_hi*W_lo in bf16
 // (error-compensated split, ~2^-16 relative per product, fp32 accumulate);  NTERMS == 2 (the default "fp32" mode):
 // A_hi*W_hi in fp16 (kind::f16) + both cross terms as e5m2 products (kind::f8f6f4, K = 32 per MMA) read from the packed
@@ -31,7 +33,7 @@
 
 namespace sparkcodec {
 
-int choose_bk_halo(int c_in, int block_n, int precision);
+int choose_bk_halo(int c_in, int block_n, int precision, int ring_bytes);
 
 namespace {
 
@@ -53,10 +55,13 @@ struct TileCfg {
   static constexpr int kPlanes = (NTERMS >= 2) ? 2 : 1;
   static constexpr int kABytes = kBlockM * BK * 2;
   static constexpr int kWBytes = (BLOCK_N / CG) * BK * 2;   // CTA-pair mode: each CTA stages half of the N rows
-  static constexpr int kSlabBytes = kBlockM * 128;   // epilogue transpose slab: 128 rows x 32 fp32, 128B-swizzled
-  static constexpr int kResBytes = RES ? kResSlots * kSlabBytes : 0;   // residual slabs (same swizzled format)
-  // smem ring budget: 227 KB - 2 slabs - residual ring - barriers - alignment slack
-  static constexpr int kBudget = 192 * 1024 - kResBytes;
+  static constexpr int kSlabBytes = kBlockM * 128;   // 128 rows x 32 fp32, 128B-swizzled: residual slab / fp32 output staging
+  static constexpr int kResBytes = RES ? kResSlots * kSlabBytes : 0;   // residual slabs
+  // Shared memory: [operand ring(s)] [output staging of the two epilogue teams] [residual slabs] [barriers].  The
+  // staging size depends on what the layer writes (fp32 and / or operand planes), so the ring budget and the ring
+  // depths are RUNTIME values (ConvGemmParams::ring_bytes); kBudget is the largest ring any layer can get.
+  static constexpr int kFixedBytes = kResBytes + 1024 /* barriers */ + 1024 /* alignment */;
+  static constexpr int kBudget = 227 * 1024 - kFixedBytes - (RES ? 0 : 2 * kSlabBytes);
   // ring 1
   static constexpr int kAHaloBytes = align_up(kHaloRowsMax * BK * 2, 1024);            // per plane
   static constexpr int kStage1Bytes = HALO ? kPlanes * kAHaloBytes : kPlanes * (kABytes + kWBytes);
@@ -64,22 +69,26 @@ struct TileCfg {
   // tiles, the rest of the budget goes to the weight ring -> depths are runtime values, barrier slots are laid
   // out for the maxima.
   static constexpr int kS1Raw = HALO ? 3 : kBudget / kStage1Bytes;
-  static constexpr int kS1 = kS1Raw > 8 ? 8 : (kS1Raw < 1 ? 1 : kS1Raw);      // (HALO: maximum)
+  static constexpr int kS1 = kS1Raw > 8 ? 8 : (kS1Raw < 1 ? 1 : kS1Raw);      // barrier slots (maximum depth)
+  static constexpr int s1_for(int ring_bytes) {
+    const int raw = ring_bytes / kStage1Bytes;
+    return raw > kS1 ? kS1 : raw;
+  }
   // ring 2 (HALO only)
   static constexpr int kStage2Bytes = kPlanes * kWBytes;
   static constexpr int kS2Max = 8;
-  static constexpr int s2_for(int halo_stages) {
-    const int raw = (kBudget - halo_stages * kStage1Bytes) / kStage2Bytes;
+  static constexpr int s2_for(int halo_stages, int ring_bytes) {
+    const int raw = (ring_bytes - halo_stages * kStage1Bytes) / kStage2Bytes;
     return raw > kS2Max ? kS2Max : (raw < 0 ? 0 : raw);
   }
   static constexpr int kS2 = HALO ? kS2Max : 0;                               // barrier slots
-  static constexpr int kRingBytes = HALO ? kBudget : kS1 * kStage1Bytes;
   static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
                                    : (2 * BLOCK_N <= 256) ? 256 : 512;
-  static constexpr int kBarBytes = (2 * kS1 + 2 * kS2 + 4 + 2 * kResSlots) * 8 + 16;
-  static constexpr int kSmemBytes = kRingBytes + 2 * kSlabBytes + kResBytes + kBarBytes + 1024 /* alignment */;
-  static constexpr bool kValid = HALO ? (s2_for(2) >= 3) : (kS1Raw >= 2);
-  static_assert(!kValid || kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
+  // barriers: ring full/empty, TMEM full/empty (2 + 2), residual full (kResSlots), staging full/empty per team (2 + 2),
+  // weight ring full/empty
+  static constexpr int kBarBytes = (2 * kS1 + 2 * kS2 + 4 + kResSlots + 4) * 8 + 16;
+  static constexpr bool kValid = HALO ? (s2_for(2, kBudget) >= 3) : (kS1Raw >= 2);
+  static_assert(kBarBytes <= 1024, "barrier block larger than budgeted");
   static_assert(2 * BLOCK_N <= 512, "two accumulator stages must fit TMEM");
   static_assert(kABytes % 1024 == 0 && kWBytes % 1024 == 0, "swizzled tiles must stay 1024 B aligned");
 };
@@ -93,33 +102,39 @@ struct TileCfg {
 constexpr int kEpiTeams = 2;
 constexpr int kEpiWarps = 8;                    // per team
 constexpr int kEpiThreads = kEpiWarps * 32;     // per team
-constexpr int kResWarp = 2 + kEpiTeams * kEpiWarps;
-constexpr int kNumThreads = (kResWarp + 1) * 32;
+constexpr int kResWarp = 2 + kEpiTeams * kEpiWarps;   // first of the two output warps (one per epilogue team)
+constexpr int kNumThreads = (kResWarp + kEpiTeams) * 32;   // 20 warps: five per scheduler, 96 registers per thread
 
 template <int BLOCK_N, int BK, int NTERMS, bool RES, bool HALO, int CG>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                     const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
-                    const __grid_constant__ CUtensorMap tm_res, const ConvGemmParams p) {
+                    const __grid_constant__ CUtensorMap tm_res, const __grid_constant__ CUtensorMap tm_o_f32,
+                    const __grid_constant__ CUtensorMap tm_o_hi, const __grid_constant__ CUtensorMap tm_o_lo,
+                    const ConvGemmParams p) {
   using Cfg = TileCfg<BLOCK_N, BK, NTERMS, RES, HALO, CG>;
   constexpr int SB = Cfg::kS1, S2B = Cfg::kS2;                        // barrier slots (maxima)
-  const int S = HALO ? p.halo_stages : Cfg::kS1;                       // ring depths actually used
-  const int S2 = HALO ? Cfg::s2_for(p.halo_stages) : 0;
+  const int S = HALO ? p.halo_stages : Cfg::s1_for(p.ring_bytes);      // ring depths actually used
+  const int S2 = HALO ? Cfg::s2_for(p.halo_stages, p.ring_bytes) : 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t ring2_base = smem_base + S * Cfg::kStage1Bytes;
-  const uint32_t slab_base = smem_base + Cfg::kRingBytes;          // 2 epilogue slabs, 1024 B aligned
-  const uint32_t res_base = slab_base + 2 * Cfg::kSlabBytes;       // kResSlots residual slabs (RES only)
+  // output staging of the two epilogue teams: per team [fp32 tile (xs_bytes: 0 or 16 KB)] [operand-plane tiles (ps_bytes)]
+  const uint32_t stage_base = smem_base + (uint32_t)p.ring_bytes;      // 1024 B aligned
+  const uint32_t team_stage_bytes = (uint32_t)(p.xs_bytes + p.ps_bytes);
+  const uint32_t res_base = stage_base + 2 * team_stage_bytes;        // kResSlots residual slabs (RES only)
   const uint32_t bar_base = res_base + Cfg::kResBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (SB + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * SB + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * SB + 2 + a); };
   auto rfull_bar = [&](int r) { return bar_base + 8u * (2 * SB + 4 + r); };
-  auto rempty_bar = [&](int r) { return bar_base + 8u * (2 * SB + 4 + kResSlots + r); };
-  auto wfull_bar = [&](int s) { return bar_base + 8u * (2 * SB + 4 + 2 * kResSlots + s); };
-  auto wempty_bar = [&](int s) { return bar_base + 8u * (2 * SB + 4 + 2 * kResSlots + S2B + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * SB + 4 + 2 * kResSlots + 2 * S2B);
+  // a team's staging tiles: written by the team -> output thread (ofull) / read by the TMA unit -> team (oempty)
+  auto ofull_bar = [&](int t) { return bar_base + 8u * (2 * SB + 4 + kResSlots + t); };
+  auto oempty_bar = [&](int t) { return bar_base + 8u * (2 * SB + 4 + kResSlots + 2 + t); };
+  auto wfull_bar = [&](int s) { return bar_base + 8u * (2 * SB + 4 + kResSlots + 4 + s); };
+  auto wempty_bar = [&](int s) { return bar_base + 8u * (2 * SB + 4 + kResSlots + 4 + S2B + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * SB + 4 + kResSlots + 4 + 2 * S2B);
   uint32_t* tmem_slot_ptr =
       reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -165,9 +180,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), CG * kEpiTeams);   // one arrive per epilogue team (pair mode: of both CTAs)
     }
-    for (int r = 0; r < kResSlots; ++r) {
-      mbar_init(rfull_bar(r), 1);
-      mbar_init(rempty_bar(r), kEpiThreads);
+    for (int r = 0; r < kResSlots; ++r) mbar_init(rfull_bar(r), 1);
+    for (int t = 0; t < kEpiTeams; ++t) {
+      mbar_init(ofull_bar(t), 1);
+      mbar_init(oempty_bar(t), 1);
     }
     fence_barrier_init();
   }
@@ -332,49 +348,84 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
         }
       }
     }
-  } else if (warp == kResWarp) {
-    // ================================ residual TMA producer ================================
-    // Streams the fp32 residual tile (B, L, N) as 128-row x 32-column boxes into a ring of slabs that
-    // have exactly the epilogue's swizzled slab format (SWIZZLE_128B), kResSlots boxes in flight.
-    if (RES && elect_one()) {
-      prefetch_tmap(&tm_res);
-      uint32_t rs = 0, rphase = 0;
-      for (int st = cid; st < num_super; st += ncl) {
-        const Tile t = tile_of(st);
-        const int b = t.b, l0 = t.l0, n0 = t.n0;
-        for (int c = 0; c < BLOCK_N; c += 32) {
-          mbar_wait(rempty_bar(rs), rphase ^ 1u);
-          mbar_expect_tx(rfull_bar(rs), Cfg::kSlabBytes);
-          tma_load_3d(res_base + rs * Cfg::kSlabBytes, &tm_res, rfull_bar(rs), n0 + c, l0, b);
-          if (++rs == kResSlots) { rs = 0; rphase ^= 1u; }
+  } else if (warp >= kResWarp) {
+    // ================================ output threads: residual slabs in, TMA stores out ================================
+    // One per epilogue team (warp kResWarp + team).  The teams take alternate 32-column chunks of the CTA's tiles; with
+    // q = running chunk number (tile iteration * kChunks + chunk) the team of chunk q is q & 1 in every case (an odd
+    // chunk count alternates the first team from tile to tile), so this thread walks q = team, team + 2, ...  Per chunk:
+    // wait until the team has written its staging tiles (and, with a residual, the new x into the residual slab), issue
+    // the TMA stores, wait until the TMA unit has READ them, hand the staging back and refill the slab with the residual
+    // of chunk q + kResSlots -- the thread that frees a slab (slots q % kResSlots of its own parity) refills it, so the
+    // slab ring needs no "empty" barriers.  Rows beyond the utterance and dummy tiles are clipped by the TMA unit.
+    // One thread for both teams was the bottleneck of the layers that write fp32 AND operand planes (32 KB per chunk).
+    if (elect_one()) {
+      constexpr int kChunks = BLOCK_N / 32;
+      const int team = warp - kResWarp;
+      const bool st_f32 = p.out_f32 != nullptr && p.dbg_skip_store == 0;
+      const bool st_op = p.out_hi != nullptr && p.dbg_skip_store == 0;
+      if (RES) prefetch_tmap(&tm_res);
+      if (st_f32) prefetch_tmap(&tm_o_f32);
+      if (st_op) prefetch_tmap(&tm_o_hi);
+      const uint32_t my_tiles = cid < num_super ? (uint32_t)((num_super - cid + ncl - 1) / ncl) : 0u;
+      const uint32_t total = my_tiles * kChunks;
+      auto load_res = [&](uint32_t q) {
+        const Tile t = tile_of(cid + (int)(q / kChunks) * ncl);
+        const uint32_t rs = q % kResSlots;
+        mbar_expect_tx(rfull_bar(rs), Cfg::kSlabBytes);
+        tma_load_3d(res_base + rs * Cfg::kSlabBytes, &tm_res, rfull_bar(rs), t.n0 + (int)(q % kChunks) * 32, t.l0, t.b);
+      };
+      static_assert(kResSlots % kEpiTeams == 0, "each output thread owns the slabs of its parity");
+      if (RES)
+        for (uint32_t q = (uint32_t)team; q < (uint32_t)kResSlots && q < total; q += kEpiTeams) load_res(q);
+      const uint32_t stg = stage_base + (uint32_t)team * team_stage_bytes;
+      const uint32_t ps = stg + (uint32_t)p.xs_bytes;
+      uint32_t used = 0;
+      for (uint32_t q = (uint32_t)team; q < total; q += kEpiTeams, ++used) {
+        const Tile t = tile_of(cid + (int)(q / kChunks) * ncl);
+        const int ci = (int)(q % kChunks);
+        mbar_wait(ofull_bar(team), used & 1u);
+        const uint32_t xs = RES ? res_base + (q % kResSlots) * Cfg::kSlabBytes : stg;
+        if (st_f32) tma_store_3d(&tm_o_f32, xs, t.n0 + ci * 32, t.l0, t.b);
+        if (st_op) {
+          tma_store_3d(&tm_o_hi, ps, t.n0 + ci * 32, t.l0, t.b);
+          if (NTERMS >= 2) tma_store_3d(&tm_o_lo, ps + kBlockM * 64, t.n0 + ci * 32, t.l0, t.b);
         }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the TMA unit has read the slab / the staging
+        mbar_arrive(oempty_bar(team));
+        if (RES && q + kResSlots < total) load_res(q + kResSlots);
       }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output stores have landed
     }
   } else {
     // ================================ epilogue warps ================================
-    // Two phases per 32-column chunk so that every global access is coalesced:
-    //  (1) tcgen05.ld hands each thread 32 columns of ITS row (TMEM lane); the thread parks them in a
-    //      128B-swizzled smem slab (row r, 16 B chunk j -> chunk j ^ (r & 7): conflict-free both ways);
-    //  (2) after a 128-thread named barrier the slab is read back transposed: 8 lanes cover the 32
-    //      columns of one row (float4 each), a warp covers 4 rows per access, so residual loads and
-    //      fp32 / bf16 stores are full 128 B / 64 B row segments.  Per-column parameters (bias, Snake
-    //      alpha) are fixed per lane and loaded once per chunk.
+    // A thread owns 16 columns of ITS row (TMEM lane) of a 32-column chunk: tcgen05.ld -> + residual (slab row, in
+    // place) + bias (+ per-utterance row bias) -> fp32 into the x staging tile -> Snake / GELU -> operand-plane split ->
+    // plane staging tiles (all in the TMA box layouts), then the team arrives on its `ofull` barrier and the output
+    // thread stores the tiles with TMA.  No transposed re-read, no per-thread global stores or address arithmetic.
+    // (Before: tcgen05.ld -> transpose slab -> barrier -> transposed read-back -> per-thread global stores; the
+    // short-reduction layers -- pw1, the narrow up-samplers -- were bound by exactly that.)
     const int group = warp & 3;                 // TMEM lane quarter this warp may read
     const int row_in_tile = group * 32 + lane;
-    const int team = (warp - 2) / kEpiWarps;    // 0 / 1: even / odd chunks of every accumulator
+    const int team = (warp - 2) / kEpiWarps;    // 0 / 1: alternate chunks of every accumulator
     const int ew = (warp - 2) % kEpiWarps;      // 0..7 within the team
     const int half = ew >> 2;                   // which 16 of a chunk's 32 columns this warp drains from TMEM
-    const int q4 = lane & 7, rsub = lane >> 3;  // phase-2 mapping: column quad, row within a 4-row group
     constexpr int kChunks = BLOCK_N / 32;
-    const uint32_t slab = slab_base + (uint32_t)team * Cfg::kSlabBytes;
+    constexpr bool EXACT = NTERMS == 3;         // range-reduced sine only for the three-term split (gemm_params.cuh)
+    // (Writing the fp32 output straight from the registers -- 64 contiguous bytes per thread, rows n_total apart --
+    // was measured at + 30-90 % on the up-samplers: 32 row segments per warp store.  Everything goes out by TMA.)
+    const bool st_f32 = p.out_f32 != nullptr, st_op = p.out_hi != nullptr;
+    const uint32_t stg = stage_base + (uint32_t)team * team_stage_bytes;
     const int bar_a = 1 + 2 * team, bar_b = 2 + 2 * team;   // named barriers of this team
-    uint32_t iter = 0;
-    // The residual (fp32, may alias out_f32: every element is read by TMA before the thread that owns it
-    // stores the sum) arrives through the slab ring filled by the residual producer warp, one slot per chunk.
+    uint8_t* const smem_gen = smem_raw - smem_u32(smem_raw);   // generic pointer of shared-window offset 0
+    uint8_t* const xs_row = smem_gen + stg + (size_t)row_in_tile * 128;
+    uint8_t* const hi_row = smem_gen + stg + p.xs_bytes + (size_t)row_in_tile * 64;
+    uint8_t* const lo_row = hi_row + kBlockM * 64;
+    const uint32_t swz128 = (uint32_t)row_in_tile & 7u, swz64 = (uint32_t)(row_in_tile >> 1) & 3u;
+    uint32_t iter = 0, n_use = 0;
     for (int st = cid; st < num_super; st += ncl, ++iter) {
       const Tile t = tile_of(st);
-      const int b = t.b, l0 = t.l0, n0 = t.n0;
-      const size_t tile_off = ((size_t)b * p.L + l0) * (size_t)p.n_total;
+      const int b = t.b, n0 = t.n0;
       const uint32_t acc = iter & 1u, acc_phase = (iter >> 1) & 1u;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
@@ -384,57 +435,114 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       const int first = (kChunks & 1) ? ((team + (int)iter) & 1) : team;
       const int my_last = ((kChunks - 1 - first) & ~1) + first;   // last chunk of this team (may be < 0: no chunk)
 #pragma unroll 1
-      for (int ci = first; ci < kChunks; ci += kEpiTeams) {
+      for (int ci = first; ci < kChunks; ci += kEpiTeams, ++n_use) {
         const int c = ci * 32;
-        // per-column parameters of this lane's 4 columns: issued first so their latency hides behind the
-        // TMEM load, the slab write and the barrier
-        const int n = n0 + c + q4 * 4;
-        float4 bias4, alpha4, inv4;
-        load_col_params4(p, n, bias4, alpha4, inv4);
+        const int nc = n0 + c + 16 * half;       // first of this thread's 16 output columns
         uint32_t r[16];
         tmem_ld_x16(t_row + c + 16 * half, r);
-        // the previous chunk of this team has been read back out of the slab by every warp of the team
-        asm volatile("bar.sync %0, %1;" ::"r"(bar_a), "n"(kEpiThreads) : "memory");
+        // per-column parameters (same addresses in every lane: broadcast loads that hit L1), issued under the TMEM load
+        float4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = __ldg(reinterpret_cast<const float4*>(p.bias + nc) + j);
         tmem_ld_wait();
-        {   // plain C++ shared-memory accesses: the named barriers / mbarrier waits are the compiler barriers
-          uint8_t* const row_ptr = smem_raw + (slab - smem_u32(smem_raw)) + (size_t)row_in_tile * 128;
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(row_ptr + (((4 * half + j) ^ (row_in_tile & 7)) << 4)) =
-                make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-        }
         tc_fence_before();
-        asm volatile("bar.sync %0, %1;" ::"r"(bar_b), "n"(kEpiThreads) : "memory");
-        // every thread of the team has drained its share of the accumulator (tcgen05.wait::ld precedes the barrier):
-        // after the team's last chunk ONE thread hands the TMEM stage back (a cluster-scope arrive by every thread
-        // costs thousands of cycles in pair mode; the leader's MMA warp waits for both teams of both CTAs)
-        if (ci == my_last && ew == 0 && lane == 0) {
-          if (CG > 1) mbar_arrive_cluster_relaxed(mapa_shared(tempty_bar(acc), 0));   // tensor-memory hand-off
-          else mbar_arrive(tempty_bar(acc));
-        }
-        uint32_t rslab = 0, rs = 0;
-        if (RES) {
-          const uint32_t cg = iter * kChunks + (uint32_t)ci;     // running chunk number -> ring slot / phase
-          rs = cg % kResSlots;
-          rslab = res_base + rs * Cfg::kSlabBytes;
-          mbar_wait(rfull_bar(rs), (cg / kResSlots) & 1u);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r_ = ew * 16 + i * 4 + rsub;
-          const uint32_t off = r_ * 128 + ((q4 ^ (r_ & 7)) << 4);
-          float4 v = *reinterpret_cast<const float4*>(smem_raw + (slab - smem_u32(smem_raw)) + off);
-          if (RES) {
-            const float4 rr = *reinterpret_cast<const float4*>(smem_raw + (rslab - smem_u32(smem_raw)) + off);
-            v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+        // every thread of the team has drained its share of the accumulator: after the team's last chunk ONE thread
+        // hands the TMEM stage back (the leader's MMA warp waits for both teams of both CTAs)
+        if (ci == my_last) {
+          asm volatile("bar.sync %0, %1;" ::"r"(bar_a), "n"(kEpiThreads) : "memory");
+          if (ew == 1 && lane == 0) {
+            if (CG > 1) mbar_arrive_cluster_relaxed(mapa_shared(tempty_bar(acc), 0));   // tensor-memory hand-off
+            else mbar_arrive(tempty_bar(acc));
           }
-          if (l0 + r_ < p.L && p.dbg_skip_store == 0)
-            epilogue_store4(p, v, b, tile_off + (size_t)((uint32_t)r_ * (uint32_t)p.n_total), n, bias4, alpha4, inv4,
-                            /*add_residual=*/false);
         }
-        if (RES) mbar_arrive(rempty_bar(rs));
+        uint8_t* x_row = xs_row;
+        if (RES) {
+          const uint32_t q = iter * kChunks + (uint32_t)ci;     // running chunk number -> residual slab / phase
+          const uint32_t rs = q % kResSlots;
+          mbar_wait(rfull_bar(rs), (q / kResSlots) & 1u);
+          x_row = smem_gen + res_base + rs * Cfg::kSlabBytes + (size_t)row_in_tile * 128;
+        }
+        if (p.dbg_skip_store == 0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float4 a = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                   __uint_as_float(r[4 * j + 3]));
+            if (RES) {   // same association as before: (acc + residual) + bias
+              const float4 rr = *reinterpret_cast<const float4*>(x_row + ((((uint32_t)(4 * half + j)) ^ swz128) << 4));
+              a.x += rr.x; a.y += rr.y; a.z += rr.z; a.w += rr.w;
+            }
+            v[j].x += a.x; v[j].y += a.y; v[j].z += a.z; v[j].w += a.w;
+          }
+          if (p.rowbias) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 rb = __ldg(reinterpret_cast<const float4*>(p.rowbias + (size_t)b * p.n_total + nc) + j);
+              v[j].x += rb.x; v[j].y += rb.y; v[j].z += rb.z; v[j].w += rb.w;
+            }
+          }
+          if (RES && st_f32) {   // the slab is this chunk's own: the new x goes in right away
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<float4*>(x_row + ((((uint32_t)(4 * half + j)) ^ swz128) << 4)) = v[j];
+          }
+        }
+        // activation + operand-plane split into registers first: the staging tiles may still be read by the TMA unit
+        uint4 hp[2], lp[2];
+        if (st_op && p.dbg_skip_store == 0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float s0 = v[j].x, s1 = v[j].y, s2 = v[j].z, s3 = v[j].w;
+            if (p.act == ACT_SNAKE) {
+              const float4 al = __ldg(reinterpret_cast<const float4*>(p.alpha + nc) + j);
+              const float4 iv = __ldg(reinterpret_cast<const float4*>(p.inv_alpha + nc) + j);
+              s0 = snake_sel<EXACT>(s0, al.x, iv.x); s1 = snake_sel<EXACT>(s1, al.y, iv.y);
+              s2 = snake_sel<EXACT>(s2, al.z, iv.z); s3 = snake_sel<EXACT>(s3, al.w, iv.w);
+            } else if (p.act == ACT_GELU) {
+              s0 = gelu_erf(s0); s1 = gelu_erf(s1); s2 = gelu_erf(s2); s3 = gelu_erf(s3);
+            }
+            uint32_t* hpp = reinterpret_cast<uint32_t*>(&hp[j >> 1]);
+            if (NTERMS == 2) {   // lp[0] = the 16 lo8 bytes of this thread's columns, lp[1] = the 16 hi8 bytes
+              const Split4F8 sp = split4_f16f8(s0, s1, s2, s3);
+              hpp[2 * (j & 1)] = sp.hi[0];
+              hpp[2 * (j & 1) + 1] = sp.hi[1];
+              reinterpret_cast<uint32_t*>(&lp[0])[j] = sp.lo8;
+              reinterpret_cast<uint32_t*>(&lp[1])[j] = sp.hi8;
+            } else {
+              const Split4Bf sp = split4_bf16(s0, s1, s2, s3, NTERMS == 3);
+              hpp[2 * (j & 1)] = sp.hi[0];
+              hpp[2 * (j & 1) + 1] = sp.hi[1];
+              if (NTERMS == 3) {
+                uint32_t* lpp = reinterpret_cast<uint32_t*>(&lp[j >> 1]);
+                lpp[2 * (j & 1)] = sp.lo[0];
+                lpp[2 * (j & 1) + 1] = sp.lo[1];
+              }
+            }
+          }
+        }
+        // the TMA unit has finished reading this team's staging tiles of its previous chunk
+        mbar_wait(oempty_bar(team), (n_use & 1u) ^ 1u);
+        if (p.dbg_skip_store == 0) {
+          if (!RES && st_f32) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<float4*>(x_row + ((((uint32_t)(4 * half + j)) ^ swz128) << 4)) = v[j];
+          }
+          if (st_op) {
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+              const uint32_t off = (((uint32_t)(2 * half + jj)) ^ swz64) << 4;   // SWIZZLE_64B box layout
+              *reinterpret_cast<uint4*>(hi_row + off) = hp[jj];
+              if (NTERMS == 3) *reinterpret_cast<uint4*>(lo_row + off) = lp[jj];
+              // two-term mode: the 64 B row of the packed plane is [lo8 x 32 | hi8 x 32]; jj = 0 lo8, jj = 1 hi8
+              if (NTERMS == 2) *reinterpret_cast<uint4*>(lo_row + ((((uint32_t)(2 * jj + half)) ^ swz64) << 4)) = lp[jj];
+            }
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA unit
+        asm volatile("bar.sync %0, %1;" ::"r"(bar_b), "n"(kEpiThreads) : "memory");
+        if (ew == 0 && lane == 0) mbar_arrive(ofull_bar(team));
       }
-      if (my_last < 0 && ew == 0 && lane == 0) {   // (BLOCK_N == 32 only) a team without a chunk still releases the accumulator
+      if (my_last < 0 && ew == 1 && lane == 0) {   // (BLOCK_N == 32 only) a team without a chunk still releases the accumulator
         if (CG > 1) mbar_arrive_cluster_relaxed(mapa_shared(tempty_bar(acc), 0));
         else mbar_arrive(tempty_bar(acc));
       }
@@ -517,13 +625,34 @@ int launch_inst(const GemmWeights& w, const OpBuf& a, int batch, int L, const Co
     set_error("conv_gemm: operand planes are in format %d, the %d-term kernel needs the other one", a.fmt, NTERMS);
     return SPARKCODEC_EINVAL;
   }
-  CUtensorMap t_res = ta_hi;
-  if (RES) {
-    const uint64_t rdims[3] = {(uint64_t)w.n_total, (uint64_t)L, (uint64_t)batch};
-    const uint64_t rstr[2] = {(uint64_t)w.n_total * 4, (uint64_t)L * w.n_total * 4};
-    const uint32_t rbox[3] = {32u, (uint32_t)kBlockM, 1u};
-    SC_TRY(encode_map(&t_res, p.residual, 3, rdims, rstr, rbox, 64, false, /*fp32=*/true));
+  // residual in / outputs: (n_total x L x batch) tensors, boxes of 32 columns x 128 rows
+  CUtensorMap t_res = ta_hi, to_f32 = ta_hi, to_hi = ta_hi, to_lo = ta_hi;
+  const uint64_t rdims[3] = {(uint64_t)w.n_total, (uint64_t)L, (uint64_t)batch};
+  const uint64_t rstr[2] = {(uint64_t)w.n_total * 4, (uint64_t)L * w.n_total * 4};
+  const uint64_t ostr[2] = {(uint64_t)w.n_total * 2, (uint64_t)L * w.n_total * 2};
+  const uint32_t rbox[3] = {32u, (uint32_t)kBlockM, 1u};
+  if (RES) SC_TRY(encode_map(&t_res, p.residual, 3, rdims, rstr, rbox, 64, false, /*fp32=*/true));
+  if (p.out_f32) SC_TRY(encode_map(&to_f32, p.out_f32, 3, rdims, rstr, rbox, 64, false, /*fp32=*/true));
+  if (p.out_hi) {
+    SC_TRY(encode_map(&to_hi, p.out_hi, 3, rdims, ostr, rbox, 32, false));
+    if (NTERMS >= 2) SC_TRY(encode_map(&to_lo, p.out_lo, 3, rdims, ostr, rbox, 32, false));
   }
+  // shared memory: what the output staging of the two epilogue teams leaves goes to the operand ring(s)
+  ConvGemmParams pp = p;
+  pp.xs_bytes = (p.out_f32 && !RES) ? Cfg::kSlabBytes : 0;
+  pp.ps_bytes = p.out_hi ? Cfg::kPlanes * kBlockM * 64 : 0;
+  pp.ring_bytes = (227 * 1024 - Cfg::kFixedBytes - 2 * (pp.xs_bytes + pp.ps_bytes)) / 1024 * 1024;
+  if (HALO) {
+    if (Cfg::s2_for(pp.halo_stages, pp.ring_bytes) < 3 && pp.halo_stages > 2) pp.halo_stages = 2;
+    if (Cfg::s2_for(pp.halo_stages, pp.ring_bytes) < 3) {
+      set_error("conv_gemm: weight ring too shallow (tile %dx%d, %d terms)", BLOCK_N, BK, NTERMS);
+      return SPARKCODEC_EINVAL;
+    }
+  } else if (Cfg::s1_for(pp.ring_bytes) < 2) {
+    set_error("conv_gemm: operand ring too shallow (tile %dx%d, %d terms)", BLOCK_N, BK, NTERMS);
+    return SPARKCODEC_EINVAL;
+  }
+  const int smem_bytes = pp.ring_bytes + 2 * (pp.xs_bytes + pp.ps_bytes) + Cfg::kFixedBytes;
   // weight maps: the cached (BK x BLOCK_N) boxes, or (BK x BLOCK_N / 2) boxes for a CTA pair
   constexpr int mi = BK == 64 ? 0 : 1;
   CUtensorMap tw_hi = NTERMS == 2 ? w.tmap_h16[mi] : w.tmap_hi[mi];
@@ -544,12 +673,12 @@ int launch_inst(const GemmWeights& w, const OpBuf& a, int batch, int L, const Co
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.blockDim = dim3(kNumThreads);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
   cfg.attrs = attr;
   cfg.numAttrs = CG > 1 ? 1 : 0;
   if (!max_clusters) {
-    SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if (CG > 1) {
       cfg.gridDim = dim3(num_sms / CG * CG);
       SC_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
@@ -562,7 +691,7 @@ int launch_inst(const GemmWeights& w, const OpBuf& a, int batch, int L, const Co
   const int supers = ((p.num_m_tiles + CG - 1) / CG) * p.num_n_tiles;
   const int clusters = std::min(std::min(supers, max_clusters), num_sms / CG);
   cfg.gridDim = dim3(clusters * CG);
-  SC_CUDA(cudaLaunchKernelEx(&cfg, kern, ta_hi, ta_lo, tw_hi, tw_lo, t_res, p));
+  SC_CUDA(cudaLaunchKernelEx(&cfg, kern, ta_hi, ta_lo, tw_hi, tw_lo, t_res, to_f32, to_hi, to_lo, pp));
   SC_LAUNCH_CHECK();
   return 0;
   }
@@ -602,20 +731,19 @@ int choose_block_n(int cols_per_phase, int* block_n) {
 
 // K chunk per (layer, precision): 64 bf16 (128 B swizzle rows) when C_in allows it and the smem ring
 // still gets >= 3 stages, else 32 (64 B swizzle rows).
-int choose_bk(int c_in, int block_n, int precision, bool residual) {
+int choose_bk(int c_in, int block_n, int precision, int ring_bytes) {
   if (c_in % 64 != 0) return 32;
   const int planes = is_split(precision) ? 2 : 1;
   const int stage64 = planes * (kBlockM * 64 * 2 + block_n * 64 * 2);
-  const int budget = 192 * 1024 - (residual ? kResSlots * kBlockM * 128 : 0);
-  return budget / stage64 >= 3 ? 64 : 32;
+  return ring_bytes / stage64 >= 3 ? 64 : 32;
 }
 
 // K chunk for the halo mainloop: the W ring must keep >= 4 stages next to the halo tiles.
-int choose_bk_halo(int c_in, int block_n, int precision) {
+int choose_bk_halo(int c_in, int block_n, int precision, int ring_bytes) {
   if (c_in % 64 != 0) return 32;
   const int planes = is_split(precision) ? 2 : 1;
   const int a64 = planes * align_up(kHaloRowsMax * 64 * 2, 1024), w64 = planes * block_n * 64 * 2;
-  return (192 * 1024 - 2 * a64) / w64 >= 4 ? 64 : 32;
+  return (ring_bytes - 2 * a64) / w64 >= 4 ? 64 : 32;
 }
 
 int make_weight_tmaps(GemmWeights& w) {
@@ -648,6 +776,7 @@ int fill_params(const GemmWeights& w, int batch, int L, const Epilogue& ep, int 
   p->num_m_tiles = batch * p->m_tiles_per_utt;
   p->num_n_tiles = w.n_total / w.block_n;
   p->halo_rows = 0; p->halo_bo_mode = 0; p->halo_stages = 3;
+  p->ring_bytes = 0; p->xs_bytes = 0; p->ps_bytes = 0;
   static const int skip = [] { const char* e = getenv("SPARKCODEC_DEBUG_SKIP_STORE"); return e ? atoi(e) : 0; }();
   p->dbg_skip_store = skip;   // timing experiments only: drain the accumulators but do not finish / store them
   p->bias = w.bias; p->rowbias = ep.rowbias; p->residual = ep.residual;
@@ -680,18 +809,23 @@ int launch_conv_gemm_tc(const GemmWeights& w, const OpBuf& a, int batch, int L, 
   }
   // CTA-pair mode (cta_group::2, M = 256): each CTA stages half of the weight rows, which halves the weight
   // traffic per SM and doubles the depth of the weight ring in tensor-pipe time.  SPARKCODEC_PAIR=0 disables.
-  // Measured per layer (profiles/r1_pair_mode_ab.txt): the pair wins where a tile carries a long reduction
-  // (k7 convs, the wide up-samplers, pw2), and loses where the tile is short and the epilogue / HBM dominates
-  // (pw1, the narrow 1x1 convs): the two CTAs of a pair run in lock step, which costs overlap there.
-  // SPARKCODEC_PAIR = 0 never, 1 heuristic (default), 2 always.
+  // Round 1 (transposing epilogue, three-term fp32 mode; profiles/r1_pair_mode_ab.txt): the pair won where a tile
+  // carries a long reduction (k7 convs, the wide up-samplers, pw2) and lost on short tiles whose epilogue dominated
+  // (pw1, the narrow 1x1 convs), so the threshold was K >= 768 (1536 in bf16 mode).
+  // SPARKCODEC_PAIR = 0 never, 1 threshold on K (default), 2 always; SPARKCODEC_PAIR_MINK overrides the threshold.
   static const int pair_mode = [] { const char* e = getenv("SPARKCODEC_PAIR"); return e ? atoi(e) : 1; }();
   const int k_total = max_taps * w.c_in;
-  // (SPARKCODEC_PAIR_MINK: threshold experiments)
   static const int pair_mink = [] { const char* e = getenv("SPARKCODEC_PAIR_MINK"); return e ? atoi(e) : 0; }();
-  const int mink = pair_mink ? pair_mink : (f32 ? 768 : 1536);
+  // (round 2, TMA-store epilogue + two-term fp32 mode: with the epilogue off the teams' critical path the pair wins from
+  // K = 384 on in both modes -- pw1 -12 %, the narrow up-samplers -3..-11 %; profiles/r2_pair_threshold_ab.txt)
+  const int mink = pair_mink ? pair_mink : 384;
   const bool pair = p.num_m_tiles >= 2 && (pair_mode == 2 || (pair_mode == 1 && k_total >= mink));
   bool halo = g_halo_mode != 0 && max_taps > 1 && ascending && !res;
-  int bk = choose_bk(w.c_in, w.block_n, precision, res);
+  // operand-ring budget of this layer: what the residual slabs and the output staging of the two epilogue teams leave
+  // (launch_inst computes the same figure from the instantiation's constants)
+  const int staging = 2 * (((ep.out_f32 && !res) ? kBlockM * 128 : 0) + (ep.out_op.hi ? (f32 ? 2 : 1) * kBlockM * 64 : 0));
+  const int ring_bytes = 227 * 1024 - 2048 - (res ? kResSlots * kBlockM * 128 : 0) - staging;
+  int bk = choose_bk(w.c_in, w.block_n, precision, ring_bytes);
   if (halo) {
     p.halo_rows = (kBlockM + span + 7) / 8 * 8;
     // a halo tile is consumed over max_taps weight stages: with 7 taps two tiles in flight are plenty and the
@@ -700,7 +834,7 @@ int launch_conv_gemm_tc(const GemmWeights& w, const OpBuf& a, int batch, int L, 
     p.halo_stages = forced ? forced : (max_taps >= 5 ? 2 : 3);
     p.halo_bo_mode = 0;
     if (p.halo_rows > kHaloRowsMax) halo = false;
-    else bk = choose_bk_halo(w.c_in, w.block_n, precision);
+    else bk = choose_bk_halo(w.c_in, w.block_n, precision, ring_bytes);
   }
 #define SC_INST3(BN, BKK, CGV, RESV, HALOV)                                                            \
     return terms == 3 ? launch_inst<BN, BKK, 3, RESV, HALOV, CGV>(w, a, batch, L, p, num_sms, stream)  \

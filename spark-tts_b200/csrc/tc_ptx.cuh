@@ -45,6 +45,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       if (now - t0 > 4000000000LL) {   // ~2 s
         printf("sparkcodec: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
                threadIdx.x, bar, parity);
+        // let the other stuck waiters of the grid report too (they started waiting within the same 2 s) before the
+        // trap tears the context down: the set of (thread, barrier) pairs is what identifies a protocol bug
+        while (clock64() - now < 1000000000LL) {}
         __trap();
       }
     }

@@ -8,6 +8,9 @@ python bench.py --steps 20 --warmup 5 > $O/bench_1gpu_fp32.json 2> $O/bench_fp32
 python bench.py --impl reference --steps 5 --warmup 3 > $O/bench_reference.json 2> $O/bench_ref.err
 python tools/profile_layers.py 64 500 fp32 > $O/layers_fp32.txt 2>&1
 python tools/profile_layers.py 64 500 bf16 > $O/layers_bf16.txt 2>&1
+SPARKCODEC_FP32_TERMS=3 python tools/profile_layers.py 64 500 fp32 > $O/layers_fp32_three_term.txt 2>&1
+SPARKCODEC_FP32_TERMS=3 python bench.py --steps 20 --warmup 5 --sub none --no-cpu-baseline > $O/bench_1gpu_fp32_three_term.json 2> $O/bench_t3.err
+[ -x tools/micro/umma_kinds ] && timeout 120 tools/micro/umma_kinds 2>&1 | grep -v illegal > $O/umma_kinds.txt
 python tools/bench_tokenize.py > $O/tokenize.txt 2>&1
 python tools/latency_single.py > $O/latency_single.txt 2>&1
 [ "$1" = quick ] && exit 0
