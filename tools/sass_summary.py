@@ -1,5 +1,6 @@
 """Counts the Blackwell-specific SASS instructions per kernel of libsparkcodec.so (cuobjdump -sass):
-UTCHMMA (tcgen05.mma, .2CTA = cta_group::2), LDTM / STTM (tcgen05.ld / st), UTMALDG / UTMASTG (TMA tensor
+UTCHMMA (tcgen05.mma kind::f16, .2CTA = cta_group::2), UTCQMMA (tcgen05.mma kind::f8f6f4: the e5m2 cross terms of the
+two-term fp32 mode), LDTM / STTM (tcgen05.ld / st), UTMALDG / UTMASTG (TMA tensor
 loads / stores), UBLKCP (cp.async.bulk), UTCBAR (tcgen05.commit), SYNCS (mbarrier).  Runs without a GPU.
 
     python tools/sass_summary.py > profiles/r2_sass_summary.txt
@@ -12,7 +13,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "spark-tts_b200", "libsparkcodec.so")
-PATTERNS = [("UTCHMMA.2CTA", r"\bUTCHMMA\.2CTA"), ("UTCHMMA", r"\bUTCHMMA\b(?!\.2CTA)"), ("LDTM", r"\bLDTM"), ("STTM", r"\bSTTM"),
+PATTERNS = [("UTCHMMA.2CTA", r"\bUTCHMMA\.2CTA"), ("UTCHMMA", r"\bUTCHMMA\b(?!\.2CTA)"),
+            ("UTCQMMA.2CTA", r"\bUTCQMMA\.2CTA"), ("UTCQMMA", r"\bUTCQMMA\b(?!\.2CTA)"), ("LDTM", r"\bLDTM"), ("STTM", r"\bSTTM"),
             ("UTMALDG", r"\bUTMALDG"), ("UTMASTG", r"\bUTMASTG"), ("UBLKCP", r"\bUBLKCP"), ("UTCBAR", r"\bUTCBAR"),
             ("SYNCS", r"\bSYNCS"), ("UTMAPF", r"\bUTMAPF|UTMACCTL")]
 
