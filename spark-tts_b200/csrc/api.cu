@@ -978,7 +978,9 @@ static int run_pass(Pass& P, const void* sem, int sem_dt, const void* glob, int 
   }
   NvtxRange range_head("sparkcodec.head");
   SC_TRY(P.prof_begin("head", 0, (double)B * L * (h->head_c * 4 + 4)));
-  SC_TRY(launch_head(W.x, B, L, h->head_c, h->s_head.alpha, h->s_head.inv, h->head_w, h->head_bias, wav_out, 0, L, st));
+  // range-reduced sine only next to the three-term split (as in the conv epilogues, gemm_params.cuh)
+  SC_TRY(launch_head(W.x, B, L, h->head_c, h->s_head.alpha, h->s_head.inv, h->head_w, h->head_bias, wav_out,
+                     terms_for(P.prec) == 3 ? 1 : 0, L, st));
   SC_TRY(P.prof_end());
   return 0;
 }

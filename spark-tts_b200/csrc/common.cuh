@@ -175,7 +175,7 @@ int launch_dwconv_ln(const float* x, int batch, int rows, int c, const float* dw
                      const float* scale, const float* shift, int ss_batch_stride, float eps,
                      float* out_f32, OpBuf out_op, cudaStream_t s);
 int launch_head(const float* x, int batch, int rows, int c, const float* alpha, const float* inv_alpha,
-                const float* w, float bias, float* wav, int crop_begin, int crop_rows, cudaStream_t s);
+                const float* w, float bias, float* wav, int exact_sin, int crop_rows, cudaStream_t s);
 
 // ---- speaker half of tokenize (speaker_kernels.cu): plain fp32 FFMA kernels, channels-last activations ----
 struct SpkGemm {

@@ -7,6 +7,48 @@
 
 namespace sparkcodec {
 
+// ---- packed fp32 pairs (sm_100: FADD2 / FMUL2 / FFMA2 do two IEEE fp32 operations per issue slot) -----------------
+// Same FMA-pipe throughput as the scalar forms (tools/micro/ffma2_bench: 72 vs 70 TFLOP/s), but half the issue slots:
+// they pay where a kernel is bound by instruction issue (the waveform head, 75 % issue-active under ncu).  Each half of
+// a packed op rounds exactly like the scalar op.  In the conv / fused-unit epilogues (Snake, GELU, the operand split)
+// they were measured at no gain on one box (profiles/r2_packed_math_ab.txt): those epilogues wait on latency chains,
+// not on issue slots, so they keep the scalar code.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+  return d;
+}
+__device__ __forceinline__ f32x2 pk2(float v) { return pk2(v, v); }
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// a += b, four lanes (two packed adds)
+__device__ __forceinline__ void add4(float4& a, const float4& b) {
+  upk2(add2(pk2(a.x, a.y), pk2(b.x, b.y)), a.x, a.y);
+  upk2(add2(pk2(a.z, a.w), pk2(b.z, b.w)), a.z, a.w);
+}
+
 // {b : upper half, a : lower half} as fp16, round to nearest, finite saturation (an fp16 inf would poison the MMAs)
 __device__ __forceinline__ uint32_t cvt_f16x2(float a, float b) {
   uint32_t d;

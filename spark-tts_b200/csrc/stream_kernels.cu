@@ -513,20 +513,57 @@ dwconv_ln_kernel(const float* __restrict__ x, int rows, const float* __restrict_
 // ------------------------------------------------------------------------------------ waveform head
 // wav[b, l] = tanh(bias + sum_j sum_c w[j, c] * snake(x[b, l + j - 3, c]))     (wave_generator.py:77-81)
 // A warp walks a run of kHeadRun consecutive samples of one utterance.  The rows of a run are contiguous in
-// memory, so the warp streams them into its own shared-memory ring with coalesced 16 B cp.async copies, 7 granules
-// (28 rows, 10.5 KB) ahead of the row it is working on: ~130 KB are in flight per SM, which is what it takes
-// to keep HBM busy (the first version kept 8 rows per warp in registers: 36 KB per SM, latency bound).
+// memory, so the warp streams them into its own shared-memory ring with coalesced 16 B cp.async copies, 3 granules
+// (12 rows, 4.5 KB) ahead of the row it is working on; 20 warps per SM keep ~90 KB in flight (the first version kept
+// 8 rows per warp in registers: 36 KB per SM, latency bound).
 // Rows outside the utterance are zero-filled by cp.async; snake(0) == 0, so that IS the conv's zero padding.
-// Every lane owns C/32 channels (conflict-free LDS), Snakes each element once and keeps the 7-row window
-// in registers.  The per-lane partial sums of 32 consecutive samples are transposed through a padded
-// per-warp smem tile (one st.shared + one ld.shared per sample instead of a 5-step shuffle tree per sample);
-// lane L ends up with sample L, so the stores are coalesced 128 B lines.
-constexpr int kHeadRun = 128;
+// Every lane owns C/32 channels (conflict-free LDS) and Snakes each element once.
+//
+// The kernel is bound by instruction issue (ncu: 75 % issue-active at 59 % of the DRAM peak), so it works on TWO ROWS
+// per step with packed fp32x2 arithmetic (FMUL2 / FFMA2, op_split.cuh): a register pair holds the Snake'd values of one
+// channel in rows 2t and 2t + 1, and tap j adds w[j] * (s[2t], s[2t + 1]) -- the weight is a broadcast scalar operand
+// -- into the running sums of the ADJACENT outputs (2t - j, 2t + 1 - j).  Even taps hit pairs that start at an even
+// output, odd taps pairs that start at an odd one, so there are two sets of four pair accumulators:
+//   E[k] = outputs (2k, 2k + 1)   <- taps 0, 2, 4, 6 of step t go to E[t], E[t-1], E[t-2], E[t-3]
+//   O[k] = outputs (2k + 1, 2k + 2) <- taps 1, 3, 5    of step t go to O[t-1], O[t-2], O[t-3]
+// After step t: out[2t - 6] = E[t-3].x + O[t-4].y and out[2t - 5] = E[t-3].y + O[t-3].x are complete.  The loop body
+// is unrolled over four steps (two granules), so every accumulator index is a compile-time constant (no register
+// moves): 21 FFMA2 per two rows instead of 42 FFMA, 33 issue slots per row instead of 55.
+// The per-lane partial sums of 32 consecutive samples are transposed through a padded per-warp smem tile (one
+// st.shared + one ld.shared per sample instead of a 5-step shuffle tree per sample); lane L ends up with sample L, so
+// the stores are coalesced 128 B lines.
+// Run length and ring depth (same-box A/B, 64 x 160000 rows, profiles/r2_head_ab.txt): a ring of 4 granules leaves room
+// for 5 blocks = 20 warps per SM (8 granules: 12 warps) -- with half the instructions per row the kernel needs warps
+// to hide latency more than bytes in flight (90 KB per SM are enough) -- and a run of 256 samples halves the
+// per-warp prologue (27 parameter loads) and the 6-row halo per run: 1.04 ms (128 / 8) -> 0.86 ms (256 / 4).
+#ifndef SC_HEAD_RUN
+#define SC_HEAD_RUN 256
+#endif
+#ifndef SC_HEAD_RING
+#define SC_HEAD_RING 4
+#endif
+constexpr int kHeadRun = SC_HEAD_RUN;
 constexpr int kHeadWarps = 4;
 constexpr int kHeadGranRows = 4;     // rows per cp.async group (4 rows x 96 ch = 3 x 32 float4 for C = 96)
-constexpr int kHeadRingGran = 8;     // granules in the ring (7 in flight + the one being read)
+constexpr int kHeadRingGran = SC_HEAD_RING;     // granules in the ring (all but one in flight + the one being read)
 
-template <int NCH>
+// (s0, s1) = snake of the pair x with per-channel alpha / 1 / alpha.  EXACT: range-reduced sine (gemm_params.cuh
+// snake_f, same operations per element); otherwise the SFU sine on the raw argument (snake_fast).
+template <bool EXACT>
+__device__ __forceinline__ f32x2 snake_pair(f32x2 x, float a, float inv) {
+  f32x2 t = mul2(pk2(a), x);
+  if (EXACT) {
+    const f32x2 k = add2(fma2(t, pk2(0.15915494309189535f), pk2(12582912.0f)), pk2(-12582912.0f));
+    t = fma2(k, pk2(-6.2831854820251465f), t);
+    t = fma2(k, pk2(1.7484555e-7f), t);
+  }
+  float t0, t1;
+  upk2(t, t0, t1);
+  const f32x2 sn = pk2(__sinf(t0), __sinf(t1));
+  return fma2(mul2(pk2(inv), sn), sn, x);
+}
+
+template <int NCH, bool EXACT>
 __global__ void __launch_bounds__(kHeadWarps * 32)
 head_kernel(const float* __restrict__ x, int rows, const float* __restrict__ alpha,
             const float* __restrict__ inv_alpha, const float* __restrict__ w /* [7][C] */, float bias,
@@ -535,6 +572,7 @@ head_kernel(const float* __restrict__ x, int rows, const float* __restrict__ alp
   constexpr int GRAN_F4 = kHeadGranRows * C / 4;          // float4s per granule (multiple of 32 for C % 32 == 0)
   constexpr int RING_ROWS = kHeadGranRows * kHeadRingGran;
   constexpr int N_GRAN = (kHeadRun + 6 + kHeadGranRows - 1) / kHeadGranRows;   // granules of a run incl. halo
+  static_assert(kHeadGranRows == 4, "a granule is two steps of two rows");
   extern __shared__ __align__(16) float s_head[];         // per warp: ring [RING_ROWS][C] | part [32][33]
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* ring = s_head + (size_t)wib * (RING_ROWS * C + 32 * 33);
@@ -554,19 +592,27 @@ head_kernel(const float* __restrict__ x, int rows, const float* __restrict__ alp
 #pragma unroll
     for (int j = 0; j < 7; ++j) wt[j][k] = __ldg(w + j * C + lane + 32 * k);
   }
-  // granule g holds rows l0 - 3 + 4g .. +3 of the utterance
+  // granule g holds rows l0 - 3 + 4g .. +3 of the utterance.  Per lane and copy: row inside the granule and element
+  // offset inside the row are loop invariants; the address is 32-bit element arithmetic + one widening multiply-add
+  // (an utterance has < 2^31 elements: checked by the launcher).
+  int g_row[GRAN_F4 / 32], g_col[GRAN_F4 / 32];
+#pragma unroll
+  for (int i = 0; i < GRAN_F4 / 32; ++i) {
+    const int f = i * 32 + lane;                           // float4 index inside the granule
+    g_row[i] = (f * 4) / C;
+    g_col[i] = (f * 4) % C;
+  }
   auto issue = [&](int g) {
     if (g < N_GRAN) {
-      const int slot = g % kHeadRingGran;
+      const uint32_t dst = ring_s + (uint32_t)(((g % kHeadRingGran) * GRAN_F4 + lane) * 16);
+      const int r0 = l0 - 3 + g * kHeadGranRows;
 #pragma unroll
       for (int i = 0; i < GRAN_F4 / 32; ++i) {
-        const int f = i * 32 + lane;                       // float4 index inside the granule
-        const int r = l0 - 3 + g * kHeadGranRows + (f * 4) / C;
-        const bool ok = r >= 0 && r < rows;
-        const float* src = xb + (size_t)(ok ? r : 0) * C + (f * 4) % C;
-        const int sz = ok ? 16 : 0;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ring_s + (uint32_t)((slot * GRAN_F4 + f) * 16)),
-                     "l"(src), "r"(sz)
+        const int r = r0 + g_row[i];
+        const bool ok = (unsigned)r < (unsigned)rows;
+        const int off = (ok ? r * C : 0) + g_col[i];       // (a zero-size copy still gets a valid address)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)(i * 32 * 16)), "l"(xb + off),
+                     "r"(ok ? 16 : 0)
                      : "memory");
       }
     }
@@ -575,54 +621,65 @@ head_kernel(const float* __restrict__ x, int rows, const float* __restrict__ alp
 #pragma unroll
   for (int g = 0; g < kHeadRingGran - 1; ++g) issue(g);
 
-  // Scatter form of the 7-tap conv: the Snake'd row ri (row 0 = sample l0 - 3) adds w[j] * s into the running sum of
-  // output sample ri - j, j = 0..6; sample ri - 6 is complete once row ri has been added.  The seven running sums
-  // live in acc[sample mod 7]; the loop body is unrolled over 28 rows (7 granules of 4 rows) so that every slot index
-  // is a compile-time constant: no sliding-window register moves (the first version spent 18 MOVs per row on them
-  // and was issue bound once the sustained clock dropped to ~1.25 GHz under the power cap).
-  float acc[7];
+  // Row ri of the run (row 0 = sample l0 - 3) feeds output sample ri - j through tap j.  Step t = rows 2t, 2t + 1.
+  f32x2 E[4], O[4];
 #pragma unroll
-  for (int j = 0; j < 7; ++j) acc[j] = 0.f;
+  for (int i = 0; i < 4; ++i) { E[i] = 0ull; O[i] = 0ull; }
   const int l_end = min(l0 + kHeadRun, rows);
-  constexpr int N_GRAN7 = (N_GRAN + 6) / 7 * 7;
+  constexpr int N_GRAN2 = (N_GRAN + 1) / 2 * 2;
 #pragma unroll 1
-  for (int g0 = 0; g0 < N_GRAN7; g0 += 7) {
+  for (int g0 = 0; g0 < N_GRAN2; g0 += 2) {
 #pragma unroll
-    for (int gg = 0; gg < 7; ++gg) {
+    for (int gg = 0; gg < 2; ++gg) {
       const int g = g0 + gg;
       if (g < N_GRAN) {
         asm volatile("cp.async.wait_group %0;" ::"n"(kHeadRingGran - 2) : "memory");   // granule g has landed
         __syncwarp();
         const float* gp = ring + (g % kHeadRingGran) * (kHeadGranRows * C);
 #pragma unroll
-        for (int u = 0; u < kHeadGranRows; ++u) {
-          constexpr int kPeriod = 7;
-          const int rr = gg * kHeadGranRows + u;            // compile-time row index inside the 28-row block
-          const int ri = g * kHeadGranRows + u;             // row index inside the run (0 = l0 - 3); ri = rr (mod 7)
-          float sv[NCH];
+        for (int u = 0; u < 2; ++u) {
+          constexpr int kP = 4;
+          const int tt = gg * 2 + u;              // compile-time step index inside the 4-step block (= t mod 4)
+          const int t = g * 2 + u;                // step of the run
+          f32x2 sv[NCH];
 #pragma unroll
-          for (int k = 0; k < NCH; ++k) sv[k] = snake_f(gp[u * C + lane + 32 * k], a[k], ia[k]);
+          for (int k = 0; k < NCH; ++k)
+            sv[k] = snake_pair<EXACT>(pk2(gp[(2 * u) * C + lane + 32 * k], gp[(2 * u + 1) * C + lane + 32 * k]), a[k], ia[k]);
 #pragma unroll
-          for (int j = 0; j < 7; ++j) {
-            const int slot = ((rr - j) % kPeriod + kPeriod) % kPeriod;
+          for (int m = 0; m < 4; ++m) {           // even taps j = 2m -> E[t - m]
+            const int e = ((tt - m) % kP + kP) % kP;
 #pragma unroll
-            for (int k = 0; k < NCH; ++k) acc[slot] = fmaf(wt[j][k], sv[k], acc[slot]);
+            for (int k = 0; k < NCH; ++k) E[e] = fma2(pk2(wt[2 * m][k]), sv[k], E[e]);
           }
-          const int done = ((rr - 6) % kPeriod + kPeriod) % kPeriod;   // output sample ri - 6 is complete
-          const int so = ri - 6;
+#pragma unroll
+          for (int m = 0; m < 3; ++m) {           // odd taps j = 2m + 1 -> O[t - m - 1]
+            const int o = ((tt - m - 1) % kP + kP) % kP;
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) O[o] = fma2(pk2(wt[2 * m + 1][k]), sv[k], O[o]);
+          }
+          // outputs 2t - 6 = E[t-3].x + O[t-4].y and 2t - 5 = E[t-3].y + O[t-3].x are complete
+          const int e3 = ((tt - 3) % kP + kP) % kP, o3 = e3, o4 = ((tt - 4) % kP + kP) % kP;
+          float ex, ey, o3x, o3y, o4x, o4y;
+          upk2(E[e3], ex, ey);
+          upk2(O[o3], o3x, o3y);
+          upk2(O[o4], o4x, o4y);
+          (void)o3y; (void)o4x;
+          const int so = 2 * t - 6;               // first of the two finished samples (even)
           if (so >= 0 && so < kHeadRun) {
-            sp[so & 31][lane] = acc[done];
-            if ((so & 31) == 31) {   // 32 samples done: transpose-reduce through shared memory, lane L gets sample L
+            sp[so & 31][lane] = ex + o4y;
+            sp[(so + 1) & 31][lane] = ey + o3x;
+            if (((so + 1) & 31) == 31) {   // 32 samples done: transpose-reduce through shared memory, lane L gets sample L
               __syncwarp();
               float tot = 0.f;
 #pragma unroll
               for (int j = 0; j < 32; ++j) tot += sp[lane][j];
               __syncwarp();
-              const int l = l0 + so - 31 + lane;
+              const int l = l0 + so + 1 - 31 + lane;
               if (l < l_end) wav[(size_t)b * rows + l] = tanhf(tot + bias);
             }
           }
-          acc[done] = 0.f;
+          E[e3] = 0ull;    // becomes E[t + 1]
+          O[o4] = 0ull;    // becomes O[t]  (first written by tap 1 of step t + 1)
         }
         __syncwarp();            // all lanes are done reading this granule's slot before it is refilled
         issue(g + kHeadRingGran - 1);
@@ -770,31 +827,36 @@ int launch_dwconv_ln(const float* x, int batch, int rows, int c, const float* dw
   }
 }
 
-template <int NCH>
+template <int NCH, bool EXACT>
 static int launch_head_t(const float* x, int batch, int rows, const float* alpha, const float* inv_alpha, const float* w,
                          float bias, float* wav, cudaStream_t s) {
   const int runs = (rows + kHeadRun - 1) / kHeadRun, total = batch * runs;
   const int grid = (total + kHeadWarps - 1) / kHeadWarps, blk = kHeadWarps * 32;
+  if ((long long)rows * NCH * 32 >= (1ll << 31)) { set_error("head: %d rows x %d channels overflow the 32-bit row offsets", rows, NCH * 32); return SPARKCODEC_EINVAL; }
   const size_t smem = (size_t)kHeadWarps * (kHeadGranRows * kHeadRingGran * NCH * 32 + 32 * 33) * sizeof(float);
   static PerDevice done;
   if (!done.here().load(std::memory_order_relaxed)) {
-    SC_CUDA(cudaFuncSetAttribute(head_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SC_CUDA(cudaFuncSetAttribute(head_kernel<NCH, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     done.here().store(1, std::memory_order_relaxed);
   }
-  head_kernel<NCH><<<grid, blk, smem, s>>>(x, rows, alpha, inv_alpha, w, bias, wav, runs, total);
+  head_kernel<NCH, EXACT><<<grid, blk, smem, s>>>(x, rows, alpha, inv_alpha, w, bias, wav, runs, total);
   SC_LAUNCH_CHECK();
   return 0;
 }
 
 int launch_head(const float* x, int batch, int rows, int c, const float* alpha, const float* inv_alpha,
-                const float* w, float bias, float* wav, int, int, cudaStream_t s) {
+                const float* w, float bias, float* wav, int exact_sin, int, cudaStream_t s) {
+#define SC_HEAD(NCH)                                                                                             \
+  return exact_sin ? launch_head_t<NCH, true>(x, batch, rows, alpha, inv_alpha, w, bias, wav, s)                 \
+                   : launch_head_t<NCH, false>(x, batch, rows, alpha, inv_alpha, w, bias, wav, s);
   switch (c) {
-    case 32: return launch_head_t<1>(x, batch, rows, alpha, inv_alpha, w, bias, wav, s);
-    case 64: return launch_head_t<2>(x, batch, rows, alpha, inv_alpha, w, bias, wav, s);
-    case 96: return launch_head_t<3>(x, batch, rows, alpha, inv_alpha, w, bias, wav, s);
-    case 128: return launch_head_t<4>(x, batch, rows, alpha, inv_alpha, w, bias, wav, s);
+    case 32: SC_HEAD(1)
+    case 64: SC_HEAD(2)
+    case 96: SC_HEAD(3)
+    case 128: SC_HEAD(4)
     default: set_error("head: unsupported channel count %d (32/64/96/128)", c); return SPARKCODEC_EINVAL;
   }
+#undef SC_HEAD
 }
 
 }  // namespace sparkcodec
