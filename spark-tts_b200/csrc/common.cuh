@@ -41,6 +41,29 @@ extern thread_local int64_t* g_launch_counter;   // points at the active handle'
     SC_CUDA(cudaGetLastError());                                                           \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------
+// The four kernels that make up a pass (conv_gemm_tc, resunit_fused, dwconv_ln, head) are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel's CTAs may become resident as soon as every CTA of
+// the previous one has passed its own griddep_wait() (SMs it does not fill, or CTAs that have exited), so barrier
+// initialisation, tensor-memory allocation, tensor-map prefetches, parameter loads and the launch latency itself
+// overlap the previous kernel's tail.  EVERY thread executes griddep_wait() before the kernel touches anything another
+// kernel may have written or may still be reading (it returns once all prerequisite grids have completed and their
+// memory is visible; a no-op for a kernel launched without the attribute), so completion stays transitive along the
+// chain and buffer reuse (ping-pong planes, the in-place residual stream) is as safe as with plain stream order.
+// SPARKCODEC_PDL=0 launches everything with plain stream order.
+#ifdef __CUDACC__
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+bool pdl_enabled();
+// appends the PDL attribute to attr[n] (room for it is the caller's business); returns the new attribute count
+inline int add_pdl_attr(cudaLaunchAttribute* attr, int n) {
+  if (!pdl_enabled()) return n;
+  attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[n].val.programmaticStreamSerializationAllowed = 1;
+  return n + 1;
+}
+
 // ---- activations -------------------------------------------------------------------------------
 // All activations are channels-last (batch, rows, channels).  A dense-contraction operand is stored as two
 // 2-byte-per-element planes (the "OP" format), in one of two formats:

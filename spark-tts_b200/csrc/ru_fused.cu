@@ -270,6 +270,9 @@ resunit_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // PDL (common.cuh): everything above overlapped the previous kernel's tail; from here on its outputs are read
+  griddep_wait();
+  griddep_launch_dependents();
 
   if (warp == kRuTmaAWarp) {
     // ================================ TMA producer: activation halo tiles ================================
@@ -856,7 +859,7 @@ int launch_ru(const GemmWeights& c7, const GemmWeights& c1, const OpBuf& a, int 
   static PerDevice cache;   // per instantiation and device: clusters that fit (0 = not initialised yet)
   int max_clusters = cache.here().load(std::memory_order_relaxed);
   cudaLaunchConfig_t cfg = {};
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.blockDim = dim3(kRuThreads);
@@ -887,6 +890,7 @@ int launch_ru(const GemmWeights& c7, const GemmWeights& c1, const OpBuf& a, int 
     SC_CUDA(cudaMemsetAsync(dbg, 0, dbg_n * sizeof(long long), stream));
     pp.dbg = dbg;
   }
+  cfg.numAttrs = add_pdl_attr(attr, CL > 1 ? 1 : 0);   // (the occupancy query above saw the cluster shape only)
   SC_CUDA(cudaLaunchKernelEx(&cfg, kern, ta_hi, ta_lo, tw[0], tw[1], tw[2], tw[3], t_res, to_hi, to_lo, pp));
   SC_LAUNCH_CHECK();
   if (trace) {

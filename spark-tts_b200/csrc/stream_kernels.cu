@@ -398,11 +398,9 @@ dwconv_ln_kernel(const float* __restrict__ x, int rows, const float* __restrict_
 
   int tile = blockIdx.x, buf = 0;
   uint32_t phase = 0;
-#pragma unroll
-  for (int i = 0; i < kLnStages - 1; ++i)   // prologue: kLnStages - 1 tiles in flight
-    if (tile + i * (int)gridDim.x < total_tiles) issue(tile + i * gridDim.x, i);
 
-  // depthwise taps / bias of this lane's channels: registers for the whole kernel
+  // depthwise taps / bias of this lane's channels: registers for the whole kernel (model constants: loaded before the
+  // PDL wait, so the loads overlap the previous kernel's tail)
   float4 wt[TAPS][NV], bias[NV];
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
@@ -412,6 +410,11 @@ dwconv_ln_kernel(const float* __restrict__ x, int rows, const float* __restrict_
     for (int j = 0; j < TAPS; ++j)
       wt[j][v] = DW ? __ldg(reinterpret_cast<const float4*>(dw_w + j * C + c)) : make_float4(1.f, 1.f, 1.f, 1.f);
   }
+  griddep_wait();                 // PDL (common.cuh): x, scale and shift are outputs of earlier kernels
+  griddep_launch_dependents();
+#pragma unroll
+  for (int i = 0; i < kLnStages - 1; ++i)   // prologue: kLnStages - 1 tiles in flight
+    if (tile + i * (int)gridDim.x < total_tiles) issue(tile + i * gridDim.x, i);
 
   for (; tile < total_tiles; tile += gridDim.x) {
     const int nxt = tile + (kLnStages - 1) * gridDim.x;
@@ -592,6 +595,8 @@ head_kernel(const float* __restrict__ x, int rows, const float* __restrict__ alp
 #pragma unroll
     for (int j = 0; j < 7; ++j) wt[j][k] = __ldg(w + j * C + lane + 32 * k);
   }
+  griddep_wait();                 // PDL (common.cuh): x is the previous kernel's output
+  griddep_launch_dependents();
   // granule g holds rows l0 - 3 + 4g .. +3 of the utterance.  Per lane and copy: row inside the granule and element
   // offset inside the row are loop invariants; the address is 32-bit element arithmetic + one widening multiply-add
   // (an utterance has < 2^31 elements: checked by the launcher).
@@ -797,20 +802,28 @@ static int launch_dwconv_ln_t(const float* x, int batch, int rows, const float* 
     sms.here().store(num_sms, std::memory_order_relaxed);
   }
   const int grid = std::min(total, num_sms);   // one persistent CTA per SM
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cfg.attrs = attr;
+  cfg.numAttrs = add_pdl_attr(attr, 0);
   if (dw) {
     if (!done_dw.here().load(std::memory_order_relaxed)) {
       SC_CUDA(cudaFuncSetAttribute(dwconv_ln_kernel<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       done_dw.here().store(1, std::memory_order_relaxed);
     }
-    dwconv_ln_kernel<NV, true><<<grid, 256, smem, s>>>(x, rows, dw_w, dw_b, scale, shift, ss, eps, out_f32, out_op,
-                                                       tiles, total);
+    SC_CUDA(cudaLaunchKernelEx(&cfg, dwconv_ln_kernel<NV, true>, x, rows, dw_w, dw_b, scale, shift, ss, eps, out_f32,
+                               out_op, tiles, total));
   } else {
     if (!done_ln.here().load(std::memory_order_relaxed)) {
       SC_CUDA(cudaFuncSetAttribute(dwconv_ln_kernel<NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       done_ln.here().store(1, std::memory_order_relaxed);
     }
-    dwconv_ln_kernel<NV, false><<<grid, 256, smem, s>>>(x, rows, dw_w, dw_b, scale, shift, ss, eps, out_f32, out_op,
-                                                        tiles, total);
+    SC_CUDA(cudaLaunchKernelEx(&cfg, dwconv_ln_kernel<NV, false>, x, rows, dw_w, dw_b, scale, shift, ss, eps, out_f32,
+                               out_op, tiles, total));
   }
   SC_LAUNCH_CHECK();
   return 0;
@@ -839,7 +852,15 @@ static int launch_head_t(const float* x, int batch, int rows, const float* alpha
     SC_CUDA(cudaFuncSetAttribute(head_kernel<NCH, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     done.here().store(1, std::memory_order_relaxed);
   }
-  head_kernel<NCH, EXACT><<<grid, blk, smem, s>>>(x, rows, alpha, inv_alpha, w, bias, wav, runs, total);
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(blk);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cfg.attrs = attr;
+  cfg.numAttrs = add_pdl_attr(attr, 0);
+  SC_CUDA(cudaLaunchKernelEx(&cfg, head_kernel<NCH, EXACT>, x, rows, alpha, inv_alpha, w, bias, wav, runs, total));
   SC_LAUNCH_CHECK();
   return 0;
 }

@@ -196,6 +196,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // PDL (common.cuh): everything above overlapped the previous kernel's tail; from here on its outputs are read
+  griddep_wait();
+  griddep_launch_dependents();
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -574,6 +577,15 @@ int g_halo_mode = [] {
 
 }  // namespace
 
+// programmatic dependent launch of the pass's kernels (common.cuh); SPARKCODEC_PDL=0 disables
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("SPARKCODEC_PDL");
+    return e ? atoi(e) != 0 : true;
+  }();
+  return on;
+}
+
 // MMA terms of the fp32 precision mode (common.cuh): 2 = fp16 main term + two e5m2 cross terms (default), 3 = bf16 x 3
 int fp32_terms() {
   static const int t = [] {
@@ -669,14 +681,14 @@ int launch_inst(const GemmWeights& w, const OpBuf& a, int batch, int L, const Co
   static PerDevice cache;   // per instantiation and device: clusters that fit (0 = not initialised yet)
   int max_clusters = cache.here().load(std::memory_order_relaxed);
   cudaLaunchConfig_t cfg = {};
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.blockDim = dim3(kNumThreads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
   cfg.attrs = attr;
-  cfg.numAttrs = CG > 1 ? 1 : 0;
+  cfg.numAttrs = CG > 1 ? 1 : 0;   // (the occupancy query below sees the cluster shape only)
   if (!max_clusters) {
     SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if (CG > 1) {
@@ -691,6 +703,8 @@ int launch_inst(const GemmWeights& w, const OpBuf& a, int batch, int L, const Co
   const int supers = ((p.num_m_tiles + CG - 1) / CG) * p.num_n_tiles;
   const int clusters = std::min(std::min(supers, max_clusters), num_sms / CG);
   cfg.gridDim = dim3(clusters * CG);
+  if (CG == 1) cfg.numAttrs = 0;
+  cfg.numAttrs = add_pdl_attr(attr, cfg.numAttrs);
   SC_CUDA(cudaLaunchKernelEx(&cfg, kern, ta_hi, ta_lo, tw_hi, tw_lo, t_res, to_f32, to_hi, to_lo, pp));
   SC_LAUNCH_CHECK();
   return 0;
