@@ -669,7 +669,7 @@ int launch_inst(const GemmWeights& w, const OpBuf& a, int batch, int L, const Co
   constexpr int mi = BK == 64 ? 0 : 1;
   CUtensorMap tw_hi = NTERMS == 2 ? w.tmap_h16[mi] : w.tmap_hi[mi];
   CUtensorMap tw_lo = NTERMS == 3 ? w.tmap_lo[mi] : (NTERMS == 2 ? w.tmap_p8[mi] : w.tmap_hi[mi]);
-  if (CG > 1) {
+  if (CG > 1 || BLOCK_N != w.block_n) {   // (a narrowed N tile of a few-tile launch has no cached map either)
     const uint64_t wd[2] = {(uint64_t)w.kt * w.c_in, (uint64_t)w.n_total};
     const uint64_t ws[1] = {(uint64_t)w.kt * w.c_in * 2};
     const uint32_t wb[2] = {(uint32_t)BK, (uint32_t)(BLOCK_N / CG)};
@@ -839,6 +839,24 @@ int launch_conv_gemm_tc(const GemmWeights& w, const OpBuf& a, int batch, int L, 
   // (launch_inst computes the same figure from the instantiation's constants)
   const int staging = 2 * (((ep.out_f32 && !res) ? kBlockM * 128 : 0) + (ep.out_op.hi ? (f32 ? 2 : 1) * kBlockM * 64 : 0));
   const int ring_bytes = 227 * 1024 - 2048 - (res ? kResSlots * kBlockM * 128 : 0) - staging;
+  // Few-tile launches (single utterances, short chunks): with the packed tile width a layer's whole weight matrix
+  // streams through a handful of SMs at ~64 B/clk each (conv-in at 1 x 500 frames: 24 tiles, 3.7 MB of weights per
+  // CTA) while the rest of the chip idles.  A narrower N tile spreads the stream: narrow while at most half of the SMs
+  // would be busy.  The K chunk stays the one the packed width gets (a narrower tile only deepens the ring), so every
+  // output element sees the same sequence of MMAs -- in the two-term mode the fp16 and e5m2 products alternate per K
+  // chunk -- and the result has the same bits; launches with more tiles than that (every layer of the batched
+  // configs) keep the packed width.  SPARKCODEC_SMALL_N=0 disables.
+  int bn = w.block_n;
+  static const int small_n = [] { const char* e = getenv("SPARKCODEC_SMALL_N"); return e ? atoi(e) : 1; }();
+  if (small_n) {
+    const int cands[] = {128, 96, 64};
+    for (int c : cands) {
+      if (2 * p.num_m_tiles * (w.n_total / bn) > num_sms) break;
+      if (c >= bn || w.taps.cols_per_phase % c != 0) continue;
+      bn = c;
+    }
+    p.num_n_tiles = w.n_total / bn;
+  }
   int bk = choose_bk(w.c_in, w.block_n, precision, ring_bytes);
   if (halo) {
     p.halo_rows = (kBlockM + span + 7) / 8 * 8;
@@ -859,7 +877,7 @@ int launch_conv_gemm_tc(const GemmWeights& w, const OpBuf& a, int batch, int L, 
     if (res) { SC_INST3(BN, BKK, CGV, true, false) }  \
     SC_INST3(BN, BKK, CGV, false, false)
 #define SC_INST(BN, BKK)                   \
-  if (w.block_n == BN && bk == BKK) {      \
+  if (bn == BN && bk == BKK) {             \
     if (pair) { SC_INST2(BN, BKK, 2) }     \
     SC_INST2(BN, BKK, 1)                   \
   }
@@ -868,7 +886,7 @@ int launch_conv_gemm_tc(const GemmWeights& w, const OpBuf& a, int batch, int L, 
 #undef SC_INST3
 #undef SC_INST2
 #undef SC_INST
-  set_error("no tcgen05 instantiation for block_n=%d bk=%d", w.block_n, bk);
+  set_error("no tcgen05 instantiation for block_n=%d bk=%d", bn, bk);
   return SPARKCODEC_EINVAL;
 }
 

@@ -3,7 +3,7 @@
 The modes are process-wide switches read once from the environment (SPARKCODEC_PAIR: CTA pairs in the conv
 kernel never / heuristic / always; SPARKCODEC_CLUSTER: single CTAs / weight multicast / CTA pairs in the fused
 ResidualUnit kernel; SPARKCODEC_HALO_STAGES: halo tiles in flight; SPARKCODEC_PDL: programmatic dependent launch of the
-pass's kernels on / off), so each one runs in its own interpreter and
+pass's kernels on / off; SPARKCODEC_SMALL_N: narrow N tiles for few-tile launches on / off), so each one runs in its own interpreter and
 writes its waveform to a file; the test compares them with the default configuration."""
 import os
 import subprocess
@@ -51,6 +51,7 @@ def test_all_kernel_modes_agree(tmp_path, prec):
         "multicast_fused": {"SPARKCODEC_CLUSTER": "2"},
         "three_halo_tiles": {"SPARKCODEC_HALO_STAGES": "3"},
         "plain_stream_order": {"SPARKCODEC_PDL": "0"},     # no programmatic dependent launch
+        "packed_tile_width": {"SPARKCODEC_SMALL_N": "0"},  # no narrow N tiles for few-tile launches
     }
     # fp32 mode: every mode feeds the tensor cores the same operands in the same order -> >= 100 dB;
     # bf16 mode: last-bit differences of fp32 sums can flip a bf16 rounding (see test_gpu_parity.py) -> >= 60 dB
