@@ -263,6 +263,12 @@ SPARKCODEC_API int sparkcodec_pack_conv_f16f8(int kind, const float* w_host, con
  * e5m2 cross terms = 2 bf16-MMA equivalents of tensor time) or 3 (bf16 x 3).  bench.py's `tensor_work_factor`. */
 SPARKCODEC_API int sparkcodec_fp32_terms(void);
 
+/* Test hook, no GPU needed: the N tile width the tcgen05 conv kernel uses for a layer with `n_total` output columns in
+ * polyphase branches of `cols_per_phase` columns when a launch has `m_tiles` 128-row tiles on a device with `num_sms`
+ * SMs: the packed width (largest of 256/192/128/96/64 that divides cols_per_phase), narrowed to 128/96/64 while the
+ * launch would keep at most half of the SMs busy.  Returns the width, or EINVAL when no width divides cols_per_phase. */
+SPARKCODEC_API int sparkcodec_tile_width(int n_total, int cols_per_phase, int m_tiles, int num_sms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,6 +78,7 @@ SIGNATURES = {
                                              C.c_size_t]),
     "sparkcodec_launch_count": (C.c_int, [_H, C.POINTER(C.c_int64)]),
     "sparkcodec_fp32_terms": (C.c_int, []),
+    "sparkcodec_tile_width": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "sparkcodec_profile": (C.c_int, [_H, C.c_int]),
     "sparkcodec_profile_read": (C.c_int, [_H, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
 }

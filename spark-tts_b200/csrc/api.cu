@@ -1523,6 +1523,17 @@ int sparkcodec_launch_count(sparkcodec_handle* h, int64_t* count) {
 
 int sparkcodec_fp32_terms(void) { return fp32_terms(); }
 
+int sparkcodec_tile_width(int n_total, int cols_per_phase, int m_tiles, int num_sms) {
+  if (n_total <= 0 || cols_per_phase <= 0 || n_total % cols_per_phase != 0 || m_tiles < 0 || num_sms <= 0) {
+    set_error("tile_width: bad arguments");
+    return SPARKCODEC_EINVAL;
+  }
+  int packed = 0;
+  const int rc = choose_block_n(cols_per_phase, &packed);
+  if (rc != 0) return rc;
+  return launch_block_n(packed, n_total, cols_per_phase, m_tiles, num_sms);
+}
+
 int sparkcodec_pack_conv_f16f8(int kind, const float* w_host, const int64_t* wshape, int param, uint16_t* w_h16,
                                uint16_t* w_p8, size_t w_capacity) {
   if (!w_host || !wshape || !w_h16 || !w_p8) { set_error("null argument"); return SPARKCODEC_EINVAL; }

@@ -34,6 +34,7 @@ struct ConvGemmParams {
 
 int fill_params(const GemmWeights& w, int batch, int L, const Epilogue& ep, int precision, ConvGemmParams* p);
 int choose_block_n(int cols_per_phase, int* block_n);
+int launch_block_n(int packed_bn, int n_total, int cols_per_phase, int num_m_tiles, int num_sms);
 int choose_bk(int c_in, int block_n, int precision, int ring_bytes);
 
 // snake(x) = x + sin(alpha x)^2 / (alpha + 1e-9)   (reference sparktts/modules/blocks/layers.py:32-39)

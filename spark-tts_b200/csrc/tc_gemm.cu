@@ -760,6 +760,21 @@ int choose_bk_halo(int c_in, int block_n, int precision, int ring_bytes) {
   return (ring_bytes - 2 * a64) / w64 >= 4 ? 64 : 32;
 }
 
+// N tile of one launch: the packed width, narrowed for few-tile launches (see launch_conv_gemm_tc)
+int launch_block_n(int packed_bn, int n_total, int cols_per_phase, int num_m_tiles, int num_sms) {
+  static const int small_n = [] { const char* e = getenv("SPARKCODEC_SMALL_N"); return e ? atoi(e) : 1; }();
+  int bn = packed_bn;
+  if (small_n) {
+    const int cands[] = {128, 96, 64};
+    for (int c : cands) {
+      if (2 * num_m_tiles * (n_total / bn) > num_sms) break;
+      if (c >= bn || cols_per_phase % c != 0) continue;
+      bn = c;
+    }
+  }
+  return bn;
+}
+
 int make_weight_tmaps(GemmWeights& w) {
   SC_TRY(tma_init());
   if (w.c_in % 32 != 0) { set_error("C_in=%d is not a multiple of 32", w.c_in); return SPARKCODEC_EINVAL; }
@@ -846,17 +861,8 @@ int launch_conv_gemm_tc(const GemmWeights& w, const OpBuf& a, int batch, int L, 
   // output element sees the same sequence of MMAs -- in the two-term mode the fp16 and e5m2 products alternate per K
   // chunk -- and the result has the same bits; launches with more tiles than that (every layer of the batched
   // configs) keep the packed width.  SPARKCODEC_SMALL_N=0 disables.
-  int bn = w.block_n;
-  static const int small_n = [] { const char* e = getenv("SPARKCODEC_SMALL_N"); return e ? atoi(e) : 1; }();
-  if (small_n) {
-    const int cands[] = {128, 96, 64};
-    for (int c : cands) {
-      if (2 * p.num_m_tiles * (w.n_total / bn) > num_sms) break;
-      if (c >= bn || w.taps.cols_per_phase % c != 0) continue;
-      bn = c;
-    }
-    p.num_n_tiles = w.n_total / bn;
-  }
+  const int bn = launch_block_n(w.block_n, w.n_total, w.taps.cols_per_phase, p.num_m_tiles, num_sms);
+  p.num_n_tiles = w.n_total / bn;
   int bk = choose_bk(w.c_in, w.block_n, precision, ring_bytes);
   if (halo) {
     p.halo_rows = (kBlockM + span + 7) / 8 * 8;
