@@ -50,8 +50,9 @@ def test_all_kernel_modes_agree(tmp_path, prec):
         "pairs_everywhere": {"SPARKCODEC_PAIR": "2", "SPARKCODEC_CLUSTER": "3"},
         "multicast_fused": {"SPARKCODEC_CLUSTER": "2"},
         "three_halo_tiles": {"SPARKCODEC_HALO_STAGES": "3"},
-        "plain_stream_order": {"SPARKCODEC_PDL": "0"},     # no programmatic dependent launch
-        "packed_tile_width": {"SPARKCODEC_SMALL_N": "0"},  # no narrow N tiles for few-tile launches
+        # no programmatic dependent launch, no narrow N tiles for few-tile launches (one run for both: each is
+        # bit-identical to the default on its own -- profiles/r2_pdl_ab.txt, r2_small_n_ab.txt)
+        "plain_launches": {"SPARKCODEC_PDL": "0", "SPARKCODEC_SMALL_N": "0"},
     }
     # fp32 mode: every mode feeds the tensor cores the same operands in the same order -> >= 100 dB;
     # bf16 mode: last-bit differences of fp32 sums can flip a bf16 rounding (see test_gpu_parity.py) -> >= 60 dB
