@@ -84,6 +84,7 @@ class BiCodec:
         self._handle: Optional[C.c_void_p] = None
         self._device: Optional[torch.device] = None
         self._ws: Optional[torch.Tensor] = None
+        self._ws_stream = None               # the stream whose work last used the shared workspace
         self._impl = "tc"
         # Opt-in CUDA-graph replay for small calls (the CLI's one utterance per call is launch-latency bound: ~80
         # kernels for a few ms of work).  Calls of at most graph_max_frames token frames are captured once per
@@ -138,7 +139,7 @@ class BiCodec:
         self._free()
         self._graphs = {}
         self._generation += 1
-        self._handle, self._device, self._ws = h, device, None
+        self._handle, self._device, self._ws, self._ws_stream = h, device, None, None
         self.set_impl(self._impl)
 
     def _free(self) -> None:
@@ -197,6 +198,14 @@ class BiCodec:
             raise RuntimeError(f"model is on {self._device} but tokens are on {dev}")
 
     def _workspace(self, batch: int, frames: int) -> Tuple[int, int]:
+        """The shared scratch of this model, grown on demand.  Every pass of one model uses it, so passes issued on
+        DIFFERENT streams must not overlap: when the current stream is not the one that used it last, it first waits
+        for the work already queued on that stream (nothing happens on the usual single-stream path)."""
+        cur = torch.cuda.current_stream(self._device)
+        prev = self._ws_stream
+        if prev is not None and prev != cur and not torch.cuda.is_current_stream_capturing():
+            cur.wait_stream(prev)
+        self._ws_stream = cur
         need = C.c_size_t()
         _lib.check(_lib.load().sparkcodec_workspace_bytes(self._handle, batch, frames, C.byref(need)))
         want = min(need.value, max(self.workspace_limit_bytes, 1))

@@ -172,21 +172,33 @@ class StreamingDetokenizer:
         self._graphs[key] = g                                        # most recently used at the back
         return g
 
+    def _finish(self, validate: bool) -> None:
+        """The round's one stream synchronisation.  With token validation on (``model.validate_tokens``, the default)
+        the 16-byte error-flag read rides on it, so an out-of-range id raises IndexError here as it does in
+        ``BiCodec.detokenize`` and in the reference's CPU path."""
+        if validate:
+            self.model.check_tokens()
+        else:
+            torch.cuda.current_stream(self.model.device).synchronize()
+
     def decode_batch(self, sem: torch.Tensor, glob: torch.Tensor) -> torch.Tensor:
-        """(B,T) host/device tokens + (B,N) globals -> pinned host waveform (B, hop*T); one sync."""
+        """(B,T) host/device tokens + (B,N) globals -> pinned host waveform (B, hop*T); one sync.  When the shape is
+        replayed from a graph the result is the graph's own pinned buffer: it is overwritten by the next round of the
+        same shape, so callers that keep it must copy it (``poll`` does)."""
         model, dev = self.model, self.model.device
         B, T = sem.shape
+        check = bool(model.validate_tokens)
         g = self._graph_for(B, T)
         if g is not None:
             g.replay(sem.to(dev, non_blocking=True), glob.to(dev, non_blocking=True))
-            torch.cuda.current_stream(dev).synchronize()
+            self._finish(check)
             return g.host
-        check, model.validate_tokens = model.validate_tokens, False
+        model.validate_tokens = False          # (no separate sync inside detokenize: _finish does both)
         try:
             wav = model.detokenize(sem.to(dev, non_blocking=True), glob.to(dev, non_blocking=True).unsqueeze(1))
         finally:
             model.validate_tokens = check
         host = torch.empty((B, T * model.hop), dtype=torch.float32, pin_memory=True)
         host.copy_(wav.view(B, -1), non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
+        self._finish(check)
         return host
