@@ -490,8 +490,13 @@ class BiCodec:
         sem, glob, B, T = self._tokens(semantic_tokens, global_tokens)
         wav = torch.empty((B, 1, self.hop * T), dtype=torch.float32, device=self._device)
         ws, ws_bytes = self._workspace(B, T)
-        cap = B * T * self.hop * 96 + 4096          # largest activation: (B, 320T, 96) / (B, 160T, 192)
-        cap = max(cap, B * T * max(self.cfg.dec_channels, self.cfg.vocos_intermediate_dim))
+        # largest activation a tap can name: a WaveGenerator stage (rows per frame x channels halve / multiply per
+        # up-block: (B, 320T, 96) and (B, 160T, 192) with the model-card config), conv-in, or the MLP's hidden layer
+        per_frame, rows, ch = 0, 1, self.cfg.dec_channels
+        for r in self.cfg.rates:
+            rows, ch = rows * r, ch // 2
+            per_frame = max(per_frame, rows * ch)
+        cap = B * T * max(per_frame, self.cfg.dec_channels, self.cfg.vocos_intermediate_dim, self.cfg.d_model) + 4096
         out = torch.empty(cap, dtype=torch.float32, device=self._device)
         shape = (C.c_int64 * 2)()
         _lib.check(_lib.load().sparkcodec_detokenize_tap(
