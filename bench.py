@@ -11,6 +11,7 @@ no data-path collective ("scaling": "weak").  Prints ONE JSON line (rank 0).
 
 The same line carries sub-records for the other BASELINE.json configs so that the driver's run sees them:
   "bf16"  config 2 in bf16 mode (value, roofline of its dominant kernel)
+  "c1"    config 1's shape on the GPU: one 10 s utterance, batch 1, p50 / p95 latency per call, fp32 and bf16 (N = 1 only)
   "c3"    batch 1024 x 30 s utterance-sharded = 128 utterances per GPU at every N
   "c4"    256 concurrent streams x 50-token chunks: p50/p99 chunk latency, fp32 and bf16 (N = 1 only)
   "c5"    batch 32 x 120 s time-sharded over the N GPUs (N = 1: the same 8-window schedule run by one process),
@@ -154,11 +155,12 @@ def main():
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--batch", type=int, default=64, help="utterances per GPU per step")
     ap.add_argument("--frames", type=int, default=500, help="token frames per utterance (50 Hz)")
-    ap.add_argument("--sub", default="all", help="sub-records: all | none | comma list of bf16,c3,c4,c5")
+    ap.add_argument("--sub", default="all", help="sub-records: all | none | comma list of bf16,c1,c3,c4,c5")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     args = ap.parse_args()
-    subs = {"bf16", "c3", "c4", "c5"} if args.sub == "all" else set(x for x in args.sub.split(",") if x and x != "none")
+    subs = ({"bf16", "c1", "c3", "c4", "c5"} if args.sub == "all"
+            else set(x for x in args.sub.split(",") if x and x != "none"))
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -474,6 +476,35 @@ def main():
             if m4 is not model:
                 del m4
         line["c4"] = rec4
+
+    if "c1" in subs and world == 1:
+        # BASELINE config 1's shape (1 utterance x 10 s): the call cli/SparkTTS.py:231-234 makes, tokens on the device
+        # -> waveform on the device, one CUDA-event pair per call (tools/latency_single.py is the stand-alone version)
+        try:
+            rec1 = {"config": "BASELINE config 1's shape: 1 utterance x 10 s (500 semantic + 32 global tokens), batch 1",
+                    "calls": 100, "timed": "BiCodec.detokenize, tokens on device -> waveform on device, CUDA events "
+                                           "around each call, eager launches (programmatic dependent launch, narrow "
+                                           "N tiles for few-tile launches)"}
+            s1, g1 = synthetic_tokens(cfg, 1, 500, 1000)
+            s1d, g1d = s1.to(dev), g1.to(dev)
+            for prec in ("fp32", "bf16"):
+                for _ in range(10):
+                    model.detokenize(s1d, g1d, precision=prec)
+                lat = []
+                for _ in range(rec1["calls"]):
+                    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    ev0.record()
+                    model.detokenize(s1d, g1d, precision=prec)
+                    ev1.record()
+                    ev1.synchronize()
+                    lat.append(ev0.elapsed_time(ev1))
+                lat.sort()
+                p50 = lat[len(lat) // 2]
+                rec1[prec] = {"p50_ms": p50, "p95_ms": lat[int(len(lat) * 0.95) - 1],
+                              "audio_s_per_s_at_p50": 500 / FRAME_RATE / (p50 * 1e-3)}
+            line["c1"] = rec1
+        except Exception as exc:                      # a latency side record must never cost the bench line
+            line["c1"] = {"error": repr(exc)}
 
     if rank == 0:
         # ---- CPU baseline beside it (bounded sample of the same step) ----
